@@ -1,0 +1,121 @@
+"""Seeded synthetic read/ref batches in the reference driver's input convention.
+
+The reference ships no test set (its driver reads ../testset/*.fa, main.cpp:86-90, which is
+not in the tree), so every parity and bench input comes from here.  A batch is two uint8
+arrays of shape (n, read_length) and (n, ref_length): each row is one sequence, '\\0'
+padded to the batch-wide maximum and NOT NUL terminated -- exactly what the reference's
+pad() (versalignUtil.cpp:17-33) hands to the kernels.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+# seed = 0x5EED0000 + config number
+BASE_SEED = 0x5EED0000
+
+
+def _rng(seed: int) -> np.random.Generator:
+    return np.random.Generator(np.random.PCG64(seed))
+
+
+def random_seqs(rng: np.random.Generator, n: int, length: int) -> np.ndarray:
+    return ACGT[rng.integers(0, 4, size=(n, length), dtype=np.uint8)]
+
+
+def mutate_from_ref(rng, refs: np.ndarray, read_len: int, p_sub: float, q_indel: float) -> np.ndarray:
+    """read = window of ref at a uniform offset, with per-base substitutions (p_sub) and
+    insertions/deletions (q_indel, half each)."""
+    n, ref_len = refs.shape
+    slack = max(ref_len - read_len, 0)
+    offset = rng.integers(0, slack + 1, size=(n, 1))
+    if q_indel > 0:
+        u = rng.random((n, read_len))
+        step = np.ones((n, read_len), dtype=np.int64)
+        step[u < q_indel / 2] = 0            # insertion: emit a random base, do not advance
+        step[(u >= q_indel / 2) & (u < q_indel)] = 2  # deletion: skip one ref base
+        src = offset + np.cumsum(step, axis=1) - 1
+        inserted = step == 0
+    else:
+        src = offset + np.arange(read_len)[None, :]
+        inserted = None
+    src = np.clip(src, 0, ref_len - 1)
+    reads = np.take_along_axis(refs, src, axis=1)
+    if inserted is not None:
+        reads = np.where(inserted, random_seqs(rng, n, read_len), reads)
+    if p_sub > 0:
+        sub = rng.random((n, read_len)) < p_sub
+        # substitute with one of the three OTHER bases
+        code = np.searchsorted(ACGT, reads)  # ACGT is sorted: A<C<G<T
+        new = ACGT[(code + rng.integers(1, 4, size=(n, read_len))) % 4]
+        reads = np.where(sub, new, reads)
+    return np.ascontiguousarray(reads.astype(np.uint8))
+
+
+def uniform_batch(n: int, read_len: int, ref_len: int, p_sub: float = 0.1, q_indel: float = 0.0,
+                  seed: int = BASE_SEED, independent: bool = False):
+    """All pairs have the full length (configs C1, C2, C4, C5)."""
+    rng = _rng(seed)
+    refs = random_seqs(rng, n, ref_len)
+    if independent:
+        reads = random_seqs(rng, n, read_len)
+    else:
+        reads = mutate_from_ref(rng, refs, read_len, p_sub, q_indel)
+    return reads, refs
+
+
+def mixed_batch(n: int, min_len: int, max_len: int, p_sub: float = 0.1, q_indel: float = 0.0,
+                seed: int = BASE_SEED + 3):
+    """Config C3: read length ~U{min..max}, ref length ~U{read..max}; buffers padded with
+    '\\0' to max_len.  Returns (reads, refs, read_lens, ref_lens)."""
+    rng = _rng(seed)
+    refs = random_seqs(rng, n, max_len)
+    reads = mutate_from_ref(rng, refs, max_len, p_sub, q_indel)
+    rl = rng.integers(min_len, max_len + 1, size=n)
+    fl = rng.integers(rl, max_len + 1)
+    col = np.arange(max_len)[None, :]
+    reads = np.where(col < rl[:, None], reads, 0).astype(np.uint8)
+    refs = np.where(col < fl[:, None], refs, 0).astype(np.uint8)
+    return np.ascontiguousarray(reads), np.ascontiguousarray(refs), rl.astype(np.int32), fl.astype(np.int32)
+
+
+def sprinkle(rng_seed: int, seqs: np.ndarray, frac: float, alphabet: bytes = b"NnacgtX-") -> np.ndarray:
+    """Replace a fraction of the non-pad bytes by N / lower case / junk (edge-case decks)."""
+    rng = _rng(rng_seed)
+    alpha = np.frombuffer(alphabet, dtype=np.uint8)
+    hit = (rng.random(seqs.shape) < frac) & (seqs != 0)
+    repl = alpha[rng.integers(0, len(alpha), size=seqs.shape)]
+    return np.where(hit, repl, seqs).astype(np.uint8)
+
+
+def edge_deck(read_len: int, ref_len: int):
+    """Hand-made corner cases (SURVEY.md 8(d) "edge deck"), padded to the given lengths."""
+    def row(s: bytes, L: int) -> np.ndarray:
+        s = s[:L]
+        return np.frombuffer(s + b"\0" * (L - len(s)), dtype=np.uint8)
+
+    cases = [
+        (b"ACGTACGTAC", b"ACGTACGTAC"),              # identical
+        (b"A", b"A"),                                # length 1
+        (b"A", b"C"),
+        (b"AAAAAAAA", b"CCCCCCCC"),                  # no match at all (score 0)
+        (b"NNNNNNNN", b"NNNNNNNN"),                  # all N
+        (b"acgtacgt", b"ACGTACGT"),                  # lower case
+        (b"ACGTNACGT", b"ACGTAACGT"),                # embedded N in read
+        (b"ACGTAACGT", b"ACGNTAACGT"),               # embedded N in ref
+        (b"ACGT-ACGT", b"ACGTACGT"),                 # junk byte inside the read
+        (b"ACGTACGT", b"ACG\0ACGT"),                 # embedded NUL inside the ref
+        (b"", b"ACGT"),                              # empty read
+        (b"ACGT", b""),                              # empty ref
+        (b"", b""),
+        (b"NACGT", b"ACGT"),                         # invalid first char
+        (b"ACGT" * 64, b"ACGT" * 64),                # full length repeats
+        (b"ACGT" * 64, b"TGCA" * 64),
+        (b"GATTACA", b"GCATGCU"),
+        (b"ACGTACGTTT", b"TTACGTACGT"),
+        (bytes([0xC1, 0x41, 0x43, 0xE7, 0x47]), b"AACGG"),  # bytes >= 0x80
+    ]
+    reads = np.stack([row(a, read_len) for a, _ in cases])
+    refs = np.stack([row(b, ref_len) for _, b in cases])
+    return np.ascontiguousarray(reads), np.ascontiguousarray(refs)
