@@ -1,0 +1,167 @@
+/* versalign_cuda.h -- C ABI of libCUDAKernel.so, the B200 (sm_100a) kernel plug-in for
+ * versalignLib's batched DP hot path.
+ *
+ * Two boundaries live in the same shared object:
+ *
+ *  (1) The reference's plug-in boundary, unchanged -- what its driver dlsym()s
+ *      (src/Kernels/default/DefaultKernel_dllexport.cpp:18-42, identical in the SSE, AVX
+ *      and OpenCL libraries):
+ *          AlignmentKernel* spawn_alignment_kernel();
+ *          void delete_alignment_kernel(AlignmentKernel*);
+ *          void set_parameters(AlignmentParameters*);
+ *          void set_logger(AlignmentLogger*);
+ *      plus the C++-linkage globals _parameters / _logger the interface headers declare
+ *      (include/AlignmentParameters.h:21, include/AlignmentLogger.h:21).  Declared in
+ *      versalign_plugin_abi.h; implemented in csrc/cuda_kernel_plugin.cpp on top of (2).
+ *
+ *  (2) The flat C ABI below: plain pointers and sizes, no C++ types, no torch types.
+ *      Each entry point names the reference interface it stands in for.  This is what a
+ *      non-C++ host (ctypes, cgo, JNI...) binds, and what the plug-in class itself calls.
+ *
+ * Conventions shared with the reference:
+ *   - a batch is n pairs; every read buffer holds exactly read_length bytes and every ref
+ *     buffer exactly ref_length bytes, '\0' padded, not NUL terminated;
+ *   - opt & 0xF: 0 = Smith-Waterman, 1 = "Needleman-Wunsch" (AlignmentKernel.h:26-32);
+ *     any other value is a silent no-op that leaves the outputs untouched
+ *     (DefaultKernel.cpp:35-40) -- these functions then return VA_OK;
+ *   - scores are 16-bit; results are exact wherever no DP cell leaves the int16 range.
+ *
+ * There is no CPU fallback: without a usable CUDA device va_cuda_create fails.
+ */
+#ifndef VERSALIGN_CUDA_H
+#define VERSALIGN_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VA_CUDA_ABI_VERSION 1
+
+/* status codes */
+#define VA_OK 0
+#define VA_ERR_ARG -1     /* bad argument                                   */
+#define VA_ERR_DEVICE -2  /* no CUDA device / CUDA runtime error            */
+#define VA_ERR_MEMORY -3  /* host or device allocation failed               */
+#define VA_ERR_RANGE -4   /* lengths or scores outside the supported domain */
+
+#define VA_OPT_SW 0
+#define VA_OPT_NW 1
+
+/* Traceback pointer rule.  The reference's kernels disagree:
+ *   VA_POLICY_DEFAULT_OCL  DefaultKernel.cpp:238-248,338-346 and alignment_kernels.cl:106-112,334-339
+ *   VA_POLICY_SIMD         SSEKernel.cpp:366-379,646-659 and AVXKernel.cpp:321-334,510-523          */
+#define VA_POLICY_DEFAULT_OCL 0
+#define VA_POLICY_SIMD 1
+
+typedef struct va_cuda_ctx va_cuda_ctx;
+
+/* The four scoring keys of AlignmentParameters (CustomParameters.h:9-47). */
+typedef struct va_cuda_scoring {
+    int32_t match;    /* score_match    */
+    int32_t mismatch; /* score_mismatch */
+    int32_t gap_read; /* score_gap_read */
+    int32_t gap_ref;  /* score_gap_ref  */
+} va_cuda_scoring;
+
+/* Per-call phase timings of the last host-buffer call on this context (seconds, wall
+ * clock on the calling thread's pipeline; phases overlap, so they do not add up to
+ * total).  kernel_ms is CUDA-event time of the device work summed over chunks and taken
+ * as the max over devices. */
+typedef struct va_cuda_timings {
+    double total_s;
+    double gather_s;   /* host: scattered/flat input -> pinned staging     */
+    double scatter_s;  /* host: pinned results -> caller's arrays          */
+    double kernel_ms;  /* device: prep + fill (+ traceback) kernels        */
+    int64_t cells;     /* DP cells actually computed (sum of rows x cols)  */
+    int64_t h2d_bytes;
+    int64_t d2h_bytes;
+    int32_t chunks;
+    int32_t launches;  /* kernels launched                                 */
+    int32_t devices;
+    int32_t reserved;
+} va_cuda_timings;
+
+int va_cuda_abi_version(void);
+
+/* Message of the last failure on the calling thread ("" if none). */
+const char *va_cuda_last_error(void);
+
+/* Number of visible CUDA devices (0 and VA_ERR_DEVICE when there is none). */
+int va_cuda_device_count(int *count);
+
+/* Create a context on the given device ordinals (n_devices == 0: every visible device).
+ * Stands in for the kernel constructors' environment set-up
+ * (OpenCLKernel.cpp:311-326 initialize_opencl_environment).  host_threads: worker threads
+ * for staging (<= 0: choose from the core count); the reference's num_threads key. */
+int va_cuda_create(va_cuda_ctx **ctx, const int *devices, int n_devices, int host_threads);
+void va_cuda_destroy(va_cuda_ctx *ctx);
+int va_cuda_set_host_threads(va_cuda_ctx *ctx, int host_threads);
+int va_cuda_get_timings(const va_cuda_ctx *ctx, va_cuda_timings *out);
+
+/* ---- host buffers, scattered: the reference's own calling convention ---------------- */
+
+/* AlignmentKernel::score_alignments (AlignmentKernel.h:40-41; DefaultKernel.cpp:52-81,
+ * SSEKernel.cpp:132-224, OpenCLKernel.cpp:28-162).  reads[i] / refs[i] are independent
+ * heap blocks; scores[0..n) is overwritten.  Pairs are sharded over the context's
+ * devices, no inter-device exchange. */
+int va_cuda_score_ptrs(va_cuda_ctx *ctx, int opt, const va_cuda_scoring *sc, int n,
+                       const char *const *reads, int read_length,
+                       const char *const *refs, int ref_length, int16_t *scores);
+
+/* AlignmentKernel::compute_alignments (AlignmentKernel.h:42-43; DefaultKernel.cpp:21-50,
+ * 391-525; SSEKernel.cpp:41-130,729-1005; OpenCLKernel.cpp:164-309).  out_read[i] /
+ * out_ref[i] must each point at read_length+ref_length writable bytes (the plug-in class
+ * passes fresh new char[] blocks).  On return bytes [start[i], L-1) hold the gapped
+ * strings, byte L-1 is NUL, bytes before start[i] are left untouched; start[i] is the value
+ * the reference stores in readStart and refStart (readEnd = refEnd = L-1).  end_cell may
+ * be NULL, else receives 2 shorts per pair: 0-based (read_pos, ref_pos) traceback began at. */
+int va_cuda_align_ptrs(va_cuda_ctx *ctx, int opt, int policy, const va_cuda_scoring *sc, int n,
+                       const char *const *reads, int read_length,
+                       const char *const *refs, int ref_length,
+                       char *const *out_read, char *const *out_ref, int16_t *start, int16_t *end_cell);
+
+/* ---- host buffers, contiguous (fixed stride) ----------------------------------------- */
+
+/* Same as va_cuda_score_ptrs with reads = n*read_length contiguous bytes (the layout
+ * OpenCLKernel.cpp:61-66 gathers into). */
+int va_cuda_score_flat(va_cuda_ctx *ctx, int opt, const va_cuda_scoring *sc, int n,
+                       const char *reads, int read_length, const char *refs, int ref_length,
+                       int16_t *scores);
+
+/* Same as va_cuda_align_ptrs with contiguous outputs: aln_read / aln_ref are n blocks of
+ * L = read_length+ref_length bytes (the layout OpenCLKernel.cpp:585-611 uses); bytes before
+ * start[i] are zero. */
+int va_cuda_align_flat(va_cuda_ctx *ctx, int opt, int policy, const va_cuda_scoring *sc, int n,
+                       const char *reads, int read_length, const char *refs, int ref_length,
+                       char *aln_read, char *aln_ref, int16_t *start, int16_t *end_cell);
+
+/* ---- device-resident buffers (device 0 of the context) ------------------------------- */
+
+/* Inputs and outputs already in HBM, same flat layouts as above; work is enqueued on
+ * `stream` (a cudaStream_t, NULL = the legacy default stream) and NOT synchronised.
+ * This is the kernel-only path bench.py times with CUDA events. */
+int va_cuda_score_device(va_cuda_ctx *ctx, int opt, const va_cuda_scoring *sc, int n,
+                         const void *d_reads, int read_length, const void *d_refs, int ref_length,
+                         void *d_scores, void *stream);
+int va_cuda_align_device(va_cuda_ctx *ctx, int opt, int policy, const va_cuda_scoring *sc, int n,
+                         const void *d_reads, int read_length, const void *d_refs, int ref_length,
+                         void *d_aln_read, void *d_aln_ref, void *d_start, void *d_end_cell,
+                         void *stream);
+
+/* Largest n one device-resident call accepts for these lengths with the workspace the
+ * context may allocate (direction matrix for align calls). */
+int va_cuda_max_resident_pairs(va_cuda_ctx *ctx, int align, int read_length, int ref_length, int64_t *max_n);
+
+/* Integer-pipe microbenchmark used for the roofline denominator: runs `iters` dependent
+ * rounds of `chains` independent VIADDMNMX chains per thread on every SM and reports
+ * lane-operations per second (kind 0: .S32, 1: .S16x2 counted as 2 lanes, 2: .S16x2.RELU,
+ * 3: VIMNMX3.S16x2). */
+int va_cuda_int_peak(va_cuda_ctx *ctx, int kind, double *lane_ops_per_s, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VERSALIGN_CUDA_H */

@@ -1,0 +1,161 @@
+"""Parity of the CUDA path against the CPU oracle (which tests/test_oracle_vs_reference.py pins
+against the reference's own kernels).  Every call goes through the C ABI or the plug-in boundary.
+Bit-exact: scores, start offsets, end cells and every byte of the gapped strings."""
+import numpy as np
+import pytest
+
+from oracle import binding as ora
+from versalignlib_b200 import capi, synth
+from versalignlib_b200.host import PluginHost
+from tests.helpers import used_region_equal
+
+pytestmark = pytest.mark.gpu
+
+PARAM_SETS = [(2, -1, -3, -3), (3, -2, -1, -4), (5, -4, -1, -7), (1, 0, -7, -1), (2, -1, 0, -2)]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = capi.CudaContext(devices=[0])
+    yield c
+    c.close()
+
+
+def _batches():
+    out = []
+    r, f = synth.uniform_batch(1000, 100, 150, p_sub=0.10, seed=synth.BASE_SEED + 1)
+    out.append(("c1_100x150", r, f))
+    r, f = synth.uniform_batch(777, 150, 150, p_sub=0.08, q_indel=0.02, seed=synth.BASE_SEED + 2)
+    out.append(("c2_150x150", r, f))
+    r, f = synth.uniform_batch(500, 64, 96, independent=True, seed=synth.BASE_SEED + 5)
+    out.append(("c5_random64x96", r, f))
+    r, f, _, _ = synth.mixed_batch(900, 30, 130, p_sub=0.08, q_indel=0.02, seed=synth.BASE_SEED + 3)
+    out.append(("mixed30-130", r, f))
+    out.append(("dirty", synth.sprinkle(11, r, 0.03), synth.sprinkle(12, f, 0.03)))
+    er, ef = synth.edge_deck(48, 64)
+    out.append(("edge", er, ef))
+    r, f = synth.uniform_batch(65, 17, 9, p_sub=0.3, seed=7)
+    out.append(("tiny17x9", r, f))
+    r, f = synth.uniform_batch(40, 250, 250, p_sub=0.1, q_indel=0.03, seed=8)
+    out.append(("250x250", r, f))
+    return out
+
+
+BATCHES = _batches()
+
+
+@pytest.mark.parametrize("opt", [ora.SW, ora.NW])
+def test_scores_flat_and_ptrs(ctx, opt):
+    for label, reads, refs in BATCHES:
+        for sc in PARAM_SETS:
+            want = ora.score(opt, reads, refs, sc)
+            got = ctx.score_flat(opt, reads, refs, sc)
+            bad = np.nonzero(got != want)[0]
+            assert bad.size == 0, f"flat {label} opt={opt} sc={sc}: {bad[:5]} got={got[bad[:5]]} want={want[bad[:5]]}"
+        got = ctx.score_ptrs(opt, reads, refs, PARAM_SETS[0])
+        assert np.array_equal(got, ora.score(opt, reads, refs, PARAM_SETS[0])), f"ptrs {label}"
+
+
+@pytest.mark.parametrize("policy", [ora.POLICY_DEFAULT_OCL, ora.POLICY_SIMD])
+@pytest.mark.parametrize("opt", [ora.SW, ora.NW])
+def test_alignments_flat(ctx, opt, policy):
+    for label, reads, refs in BATCHES:
+        for sc in PARAM_SETS[:4]:
+            oa, ob, ostart, oend = ora.align(opt, policy, reads, refs, sc)
+            a, b, start, end = ctx.align_flat(opt, policy, reads, refs, sc)
+            assert np.array_equal(end, oend), f"{label} opt={opt} pol={policy} sc={sc}: end cells differ at {np.nonzero((end != oend).any(axis=1))[0][:5]}"
+            bad = used_region_equal(a, b, start, oa, ob, ostart)
+            assert bad.size == 0, f"{label} opt={opt} pol={policy} sc={sc}: pairs {bad[:5]}"
+            # the flat entry point promises zeros before start and a NUL at L-1
+            assert np.array_equal(a, oa) and np.array_equal(b, ob)
+
+
+def test_alignments_ptrs(ctx):
+    label, reads, refs = BATCHES[1]
+    oa, ob, ostart, oend = ora.align(ora.NW, 0, reads, refs)
+    a, b, start, end = ctx.align_ptrs(ora.NW, 0, reads, refs)
+    assert np.array_equal(end, oend)
+    assert used_region_equal(a, b, start, oa, ob, ostart).size == 0
+    assert np.all(a[:, -1] == 0) and np.all(b[:, -1] == 0)
+
+
+@pytest.mark.parametrize("policy", [0, 1])
+def test_through_plugin_boundary(policy):
+    """dlopen + set_parameters + set_logger + spawn + the two virtual calls, like the reference driver."""
+    for label, reads, refs in BATCHES[:4]:
+        sc = PARAM_SETS[1]
+        with PluginHost(capi.library_path(), reads.shape[1], refs.shape[1], sc, num_threads=4,
+                        extra={"cuda_traceback_policy": policy, "cuda_devices": 1}, verbosity=0) as h:
+            h.stage(reads, refs, scattered=True)
+            for opt in (ora.SW, ora.NW):
+                got = h.score_staged(opt)
+                assert np.array_equal(got, ora.score(opt, reads, refs, sc)), f"{label} opt={opt}"
+                a, b, f = h.align_staged(opt)
+                assert h.alignments_terminated()
+                oa, ob, ostart, _ = ora.align(opt, policy, reads, refs, sc)
+                L = reads.shape[1] + refs.shape[1]
+                assert np.all(f[:, 0] == f[:, 2]) and np.all(f[:, 1] == L - 1) and np.all(f[:, 3] == L - 1)
+                assert used_region_equal(a, b, f[:, 0], oa, ob, ostart).size == 0, f"{label} opt={opt}"
+
+
+def test_unsupported_opt_touches_nothing(ctx):
+    _, reads, refs = BATCHES[0]
+    out = np.full(reads.shape[0], 1234, dtype=np.int16)
+    ctx.score_flat(7, reads, refs, out=out)
+    assert np.all(out == 1234)
+    with PluginHost(capi.library_path(), reads.shape[1], refs.shape[1], extra={"cuda_devices": 1}, verbosity=0) as h:
+        h.stage(reads, refs)
+        sc = np.full(reads.shape[0], 77, dtype=np.int16)
+        h.score_staged(5, out=sc)
+        assert np.all(sc == 77)
+
+
+@pytest.mark.parametrize("n", [0, 1, 63, 64, 65, 129])
+def test_ragged_batch_sizes(ctx, n):
+    reads, refs = synth.uniform_batch(max(n, 1), 33, 47, p_sub=0.2, seed=100 + n)
+    reads, refs = reads[:n], refs[:n]
+    for opt in (ora.SW, ora.NW):
+        assert np.array_equal(ctx.score_flat(opt, reads, refs), ora.score(opt, reads, refs) if n else np.zeros(0, np.int16))
+        a, b, start, end = ctx.align_flat(opt, 0, reads, refs)
+        if n:
+            oa, ob, ostart, oend = ora.align(opt, 0, reads, refs)
+            assert np.array_equal(a, oa) and np.array_equal(b, ob) and np.array_equal(start, ostart)
+
+
+def test_device_resident_entry_points(ctx):
+    import torch
+    _, reads, refs = BATCHES[1]
+    dev = torch.device("cuda:0")
+    dr, df = torch.from_numpy(reads).to(dev), torch.from_numpy(refs).to(dev)
+    n, L = reads.shape[0], reads.shape[1] + refs.shape[1]
+    stream = torch.cuda.current_stream().cuda_stream
+    for opt in (ora.SW, ora.NW):
+        ds = torch.zeros(n, dtype=torch.int16, device=dev)
+        ctx.score_device(opt, dr, df, ds, stream=stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(ds.cpu().numpy(), ora.score(opt, reads, refs))
+        da = torch.zeros((n, L), dtype=torch.uint8, device=dev)
+        db = torch.zeros((n, L), dtype=torch.uint8, device=dev)
+        dst = torch.zeros(n, dtype=torch.int16, device=dev)
+        de = torch.zeros((n, 2), dtype=torch.int16, device=dev)
+        ctx.align_device(opt, 0, dr, df, da, db, dst, de, stream=stream)
+        torch.cuda.synchronize()
+        oa, ob, ostart, oend = ora.align(opt, 0, reads, refs)
+        assert np.array_equal(dst.cpu().numpy(), ostart) and np.array_equal(de.cpu().numpy(), oend)
+        assert np.array_equal(da.cpu().numpy(), oa) and np.array_equal(db.cpu().numpy(), ob)
+
+
+def test_large_batch_properties(ctx):
+    """At a size the oracle cannot check pair by pair in seconds: size-independent properties.
+    (1) identical pairs score match*len in both modes; (2) SW score is invariant under the
+    '\\0' padding of the batch; (3) a sub-sample agrees with the oracle."""
+    n = 200_000
+    reads, refs = synth.uniform_batch(n, 100, 150, p_sub=0.1, seed=synth.BASE_SEED + 1)
+    got = ctx.score_flat(ora.SW, reads, refs)
+    idx = np.random.default_rng(0).choice(n, 3000, replace=False)
+    assert np.array_equal(got[idx], ora.score(ora.SW, np.ascontiguousarray(reads[idx]), np.ascontiguousarray(refs[idx])))
+    padded_r = np.zeros((n, 120), np.uint8); padded_r[:, :100] = reads
+    padded_f = np.zeros((n, 160), np.uint8); padded_f[:, :150] = refs
+    assert np.array_equal(ctx.score_flat(ora.SW, padded_r, padded_f), got)
+    same = ctx.score_flat(ora.NW, refs, refs, (3, -2, -5, -5))
+    assert np.all(same == 450)

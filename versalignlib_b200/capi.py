@@ -1,0 +1,223 @@
+"""ctypes binding of the flat C ABI declared in include/versalign_cuda.h.
+
+The library is libCUDAKernel.so itself (the plug-in exports both boundaries).  There is no
+fallback: if the shared object or a CUDA device is missing, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+from . import build as _build
+
+SW, NW = 0, 1
+POLICY_DEFAULT_OCL, POLICY_SIMD = 0, 1
+
+# every symbol include/versalign_cuda.h declares (tests check the .so exports all of them)
+C_ABI_SYMBOLS = [
+    "va_cuda_abi_version", "va_cuda_last_error", "va_cuda_device_count", "va_cuda_create", "va_cuda_destroy",
+    "va_cuda_set_host_threads", "va_cuda_get_timings", "va_cuda_score_ptrs", "va_cuda_align_ptrs",
+    "va_cuda_score_flat", "va_cuda_align_flat", "va_cuda_score_device", "va_cuda_align_device",
+    "va_cuda_max_resident_pairs", "va_cuda_int_peak",
+]
+PLUGIN_SYMBOLS = ["spawn_alignment_kernel", "delete_alignment_kernel", "set_parameters", "set_logger"]
+
+
+class Scoring(ctypes.Structure):
+    _fields_ = [("match", ctypes.c_int32), ("mismatch", ctypes.c_int32),
+                ("gap_read", ctypes.c_int32), ("gap_ref", ctypes.c_int32)]
+
+
+class Timings(ctypes.Structure):
+    _fields_ = [("total_s", ctypes.c_double), ("gather_s", ctypes.c_double), ("scatter_s", ctypes.c_double),
+                ("kernel_ms", ctypes.c_double), ("cells", ctypes.c_int64), ("h2d_bytes", ctypes.c_int64),
+                ("d2h_bytes", ctypes.c_int64), ("chunks", ctypes.c_int32), ("launches", ctypes.c_int32),
+                ("devices", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+class CudaError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def library_path() -> str:
+    return _build.CUDA_PLUGIN
+
+
+def lib():
+    """Load libCUDAKernel.so (building it in-tree first when sources are newer)."""
+    global _lib
+    if _lib is None:
+        path = _build.build_cuda() if os.path.exists(os.path.join(_build.CSRC, "va_kernels.cu")) else _build.CUDA_PLUGIN
+        if not os.path.exists(path):
+            raise CudaError(f"{path} is missing: run `python -m versalignlib_b200.build`")
+        L = ctypes.CDLL(path)
+        vp, ci = ctypes.c_void_p, ctypes.c_int
+        L.va_cuda_abi_version.restype = ci
+        L.va_cuda_last_error.restype = ctypes.c_char_p
+        L.va_cuda_device_count.argtypes = [ctypes.POINTER(ci)]
+        L.va_cuda_create.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(ci), ci, ci]
+        L.va_cuda_destroy.argtypes = [vp]
+        L.va_cuda_destroy.restype = None
+        L.va_cuda_set_host_threads.argtypes = [vp, ci]
+        L.va_cuda_get_timings.argtypes = [vp, ctypes.POINTER(Timings)]
+        sp = ctypes.POINTER(Scoring)
+        L.va_cuda_score_ptrs.argtypes = [vp, ci, sp, ci, vp, ci, vp, ci, vp]
+        L.va_cuda_align_ptrs.argtypes = [vp, ci, ci, sp, ci, vp, ci, vp, ci, vp, vp, vp, vp]
+        L.va_cuda_score_flat.argtypes = [vp, ci, sp, ci, vp, ci, vp, ci, vp]
+        L.va_cuda_align_flat.argtypes = [vp, ci, ci, sp, ci, vp, ci, vp, ci, vp, vp, vp, vp]
+        L.va_cuda_score_device.argtypes = [vp, ci, sp, ci, vp, ci, vp, ci, vp, vp]
+        L.va_cuda_align_device.argtypes = [vp, ci, ci, sp, ci, vp, ci, vp, ci, vp, vp, vp, vp, vp]
+        L.va_cuda_max_resident_pairs.argtypes = [vp, ci, ci, ci, ctypes.POINTER(ctypes.c_int64)]
+        L.va_cuda_int_peak.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_double), vp]
+        _lib = L
+    return _lib
+
+
+def device_count() -> int:
+    n = ctypes.c_int(0)
+    lib().va_cuda_device_count(ctypes.byref(n))
+    return n.value
+
+
+def _u8(a: np.ndarray) -> np.ndarray:
+    assert a.dtype == np.uint8 and a.ndim == 2
+    return np.ascontiguousarray(a)
+
+
+def _row_pointers(a: np.ndarray) -> np.ndarray:
+    """char* per row of a C-contiguous 2-D array (the reference's char const* const* shape)."""
+    return (a.ctypes.data + np.arange(a.shape[0], dtype=np.uint64) * np.uint64(a.strides[0])).astype(np.uint64)
+
+
+class CudaContext:
+    """va_cuda_ctx: streams, pinned staging and device workspace on one or more GPUs."""
+
+    def __init__(self, devices: list[int] | None = None, host_threads: int = 0):
+        L = lib()
+        self._L = L
+        h = ctypes.c_void_p()
+        if devices:
+            arr = (ctypes.c_int * len(devices))(*devices)
+            rc = L.va_cuda_create(ctypes.byref(h), arr, len(devices), host_threads)
+        else:
+            rc = L.va_cuda_create(ctypes.byref(h), None, 0, host_threads)
+        if rc != 0:
+            raise CudaError(f"va_cuda_create rc={rc}: {L.va_cuda_last_error().decode()}")
+        self._h = h
+
+    def _check(self, rc: int, what: str) -> None:
+        if rc != 0:
+            raise CudaError(f"{what} rc={rc}: {self._L.va_cuda_last_error().decode()}")
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._L.va_cuda_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_host_threads(self, n: int) -> None:
+        self._check(self._L.va_cuda_set_host_threads(self._h, n), "va_cuda_set_host_threads")
+
+    def timings(self) -> dict:
+        t = Timings()
+        self._check(self._L.va_cuda_get_timings(self._h, ctypes.byref(t)), "va_cuda_get_timings")
+        return t.as_dict()
+
+    # ---- host buffers ----------------------------------------------------------------
+    def score_flat(self, opt: int, reads: np.ndarray, refs: np.ndarray, scoring=(2, -1, -3, -3),
+                   out: np.ndarray | None = None) -> np.ndarray:
+        reads, refs = _u8(reads), _u8(refs)
+        n = reads.shape[0]
+        if out is None:
+            out = np.zeros(n, dtype=np.int16)
+        sc = Scoring(*scoring)
+        self._check(self._L.va_cuda_score_flat(self._h, opt, ctypes.byref(sc), n, reads.ctypes.data, reads.shape[1],
+                                               refs.ctypes.data, refs.shape[1], out.ctypes.data), "va_cuda_score_flat")
+        return out
+
+    def score_ptrs(self, opt: int, reads: np.ndarray, refs: np.ndarray, scoring=(2, -1, -3, -3)) -> np.ndarray:
+        reads, refs = _u8(reads), _u8(refs)
+        n = reads.shape[0]
+        out = np.zeros(n, dtype=np.int16)
+        rp, fp = _row_pointers(reads), _row_pointers(refs)
+        sc = Scoring(*scoring)
+        self._check(self._L.va_cuda_score_ptrs(self._h, opt, ctypes.byref(sc), n, rp.ctypes.data, reads.shape[1],
+                                               fp.ctypes.data, refs.shape[1], out.ctypes.data), "va_cuda_score_ptrs")
+        return out
+
+    def align_flat(self, opt: int, policy: int, reads: np.ndarray, refs: np.ndarray, scoring=(2, -1, -3, -3)):
+        """Returns (aln_read[n,L], aln_ref[n,L], start[n], end_cell[n,2])."""
+        reads, refs = _u8(reads), _u8(refs)
+        n, L = reads.shape[0], reads.shape[1] + refs.shape[1]
+        a = np.zeros((n, L), dtype=np.uint8)
+        b = np.zeros((n, L), dtype=np.uint8)
+        start = np.zeros(n, dtype=np.int16)
+        end = np.zeros((n, 2), dtype=np.int16)
+        sc = Scoring(*scoring)
+        self._check(self._L.va_cuda_align_flat(self._h, opt, policy, ctypes.byref(sc), n, reads.ctypes.data,
+                                               reads.shape[1], refs.ctypes.data, refs.shape[1], a.ctypes.data,
+                                               b.ctypes.data, start.ctypes.data, end.ctypes.data), "va_cuda_align_flat")
+        return a, b, start, end
+
+    def align_ptrs(self, opt: int, policy: int, reads: np.ndarray, refs: np.ndarray, scoring=(2, -1, -3, -3)):
+        reads, refs = _u8(reads), _u8(refs)
+        n, L = reads.shape[0], reads.shape[1] + refs.shape[1]
+        a = np.zeros((n, L), dtype=np.uint8)
+        b = np.zeros((n, L), dtype=np.uint8)
+        start = np.zeros(n, dtype=np.int16)
+        end = np.zeros((n, 2), dtype=np.int16)
+        rp, fp, ap, bp = _row_pointers(reads), _row_pointers(refs), _row_pointers(a), _row_pointers(b)
+        sc = Scoring(*scoring)
+        self._check(self._L.va_cuda_align_ptrs(self._h, opt, policy, ctypes.byref(sc), n, rp.ctypes.data, reads.shape[1],
+                                               fp.ctypes.data, refs.shape[1], ap.ctypes.data, bp.ctypes.data,
+                                               start.ctypes.data, end.ctypes.data), "va_cuda_align_ptrs")
+        return a, b, start, end
+
+    # ---- device-resident (torch tensors supply the memory and the stream) --------------
+    def score_device(self, opt: int, d_reads, d_refs, d_scores, scoring=(2, -1, -3, -3), stream: int = 0) -> None:
+        n = d_reads.shape[0]
+        sc = Scoring(*scoring)
+        self._check(self._L.va_cuda_score_device(self._h, opt, ctypes.byref(sc), n, d_reads.data_ptr(), d_reads.shape[1],
+                                                 d_refs.data_ptr(), d_refs.shape[1], d_scores.data_ptr(), stream),
+                    "va_cuda_score_device")
+
+    def align_device(self, opt: int, policy: int, d_reads, d_refs, d_aln_read, d_aln_ref, d_start, d_end_cell=None,
+                     scoring=(2, -1, -3, -3), stream: int = 0) -> None:
+        n = d_reads.shape[0]
+        sc = Scoring(*scoring)
+        self._check(self._L.va_cuda_align_device(self._h, opt, policy, ctypes.byref(sc), n, d_reads.data_ptr(),
+                                                 d_reads.shape[1], d_refs.data_ptr(), d_refs.shape[1],
+                                                 d_aln_read.data_ptr(), d_aln_ref.data_ptr(), d_start.data_ptr(),
+                                                 d_end_cell.data_ptr() if d_end_cell is not None else None, stream),
+                    "va_cuda_align_device")
+
+    def max_resident_pairs(self, align: bool, read_length: int, ref_length: int) -> int:
+        out = ctypes.c_int64(0)
+        self._check(self._L.va_cuda_max_resident_pairs(self._h, 1 if align else 0, read_length, ref_length,
+                                                       ctypes.byref(out)), "va_cuda_max_resident_pairs")
+        return out.value
+
+    def int_peak(self, kind: int, stream: int = 0) -> float:
+        """Measured integer-pipe throughput in lane-ops/s (kind: 0 s32, 1 s16x2, 2 s16x2.relu, 3 vimax3 s16x2)."""
+        out = ctypes.c_double(0)
+        self._check(self._L.va_cuda_int_peak(self._h, kind, ctypes.byref(out), stream), "va_cuda_int_peak")
+        return out.value

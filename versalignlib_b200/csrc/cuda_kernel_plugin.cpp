@@ -1,0 +1,206 @@
+// cuda_kernel_plugin.cpp -- "CUDAKernel": one more AlignmentKernel behind the reference's
+// plug-in boundary, so the reference driver loads libCUDAKernel.so exactly like its Default,
+// SSE, AVX and OpenCL libraries (add { "CUDA", libPathDir + "libCUDAKernel" + libSuffix } to
+// kernel_map, src/impl/main.cpp:61-64).
+//
+//   reference                                              here
+//   DefaultKernel.h:66-81   ctor: six required keys, throws a C string when one is missing   CUDAKernel::CUDAKernel
+//   DefaultKernel.cpp:52-81 score_alignments: opt&0xF dispatch, log, run                     CUDAKernel::score_alignments
+//   DefaultKernel.cpp:21-50 compute_alignments, :441-451 new char[alnLength] + four shorts   CUDAKernel::compute_alignments
+//   DefaultKernel_dllexport.cpp:18-42  the four extern "C" symbols + _parameters/_logger     bottom of this file
+//
+// All device work goes through the flat C ABI (versalign_cuda.h); there is no CPU path.
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "versalign_cuda.h"
+#include "versalign_plugin_abi.h"
+
+#define KERNEL "CUDA"
+
+AlignmentParameters *_parameters = 0;
+AlignmentLogger *_logger = 0;
+
+namespace {
+
+// Optional keys are probed with has_key() first: the reference driver's param_int() throws on
+// unknown keys (CustomParameters.h:25-27).  Environment variables are the fallback so the
+// stock driver can steer the plug-in without code changes.
+int optional_param(const char *key, const char *env, int fallback) {
+    if (_parameters && Parameters.has_key(key)) return Parameters.param_int(key);
+    if (const char *v = getenv(env)) return atoi(v);
+    return fallback;
+}
+
+void log_info(const std::string &msg) {
+    if (_logger) Logger.log(0, KERNEL, msg.c_str());
+}
+
+[[noreturn]] void fatal(const std::string &msg) {
+    // reference convention: log at level 3, then throw (OpenCLKernel.cpp:647-655); we throw a
+    // C string like the constructors do so hosts can catch (const char*)
+    static thread_local std::string keep;
+    keep = msg;
+    if (_logger) Logger.log(3, KERNEL, keep.c_str());
+    throw keep.c_str();
+}
+
+// The library is never dlclose()d by the reference driver (main.cpp:217-225 re-dlopens to find
+// delete_alignment_kernel), and it spawns a fresh kernel per timing run (main.cpp:261-265), so
+// the CUDA context (streams, pinned staging, device workspace) is shared by all instances.
+struct SharedContext {
+    std::mutex mu;
+    va_cuda_ctx *ctx = nullptr;
+    int n_devices = -1;
+};
+SharedContext g_shared;
+
+va_cuda_ctx *acquire_context(int n_devices) {
+    std::lock_guard<std::mutex> lk(g_shared.mu);
+    if (g_shared.ctx && g_shared.n_devices == n_devices) return g_shared.ctx;
+    if (g_shared.ctx) {
+        va_cuda_destroy(g_shared.ctx);
+        g_shared.ctx = nullptr;
+    }
+    int visible = 0;
+    if (va_cuda_device_count(&visible) != VA_OK) fatal(std::string("Cannot instantiate Kernel. ") + va_cuda_last_error());
+    std::vector<int> devs;
+    const int use = (n_devices <= 0 || n_devices > visible) ? visible : n_devices;
+    for (int d = 0; d < use; ++d) devs.push_back(d);
+    va_cuda_ctx *ctx = nullptr;
+    if (va_cuda_create(&ctx, devs.data(), (int)devs.size(), 0) != VA_OK)
+        fatal(std::string("Cannot instantiate Kernel. ") + va_cuda_last_error());
+    g_shared.ctx = ctx;
+    g_shared.n_devices = n_devices;
+    return ctx;
+}
+
+class CUDAKernel : public AlignmentKernel {
+public:
+    CUDAKernel() {
+        bool missing = _parameters == 0;
+        auto need = [&](const char *key) -> int {
+            if (missing || !Parameters.has_key(key)) {
+                missing = true;
+                return 0;
+            }
+            return Parameters.param_int(key);
+        };
+        // values are narrowed to short like the reference's members (DefaultKernel.h:139-142)
+        scoring_.match = (short)need("score_match");
+        scoring_.mismatch = (short)need("score_mismatch");
+        scoring_.gap_read = (short)need("score_gap_read");
+        scoring_.gap_ref = (short)need("score_gap_ref");
+        read_length_ = need("read_length");
+        ref_length_ = need("ref_length");
+        if (missing) throw "Cannot instantiate Kernel. Lacking parameters";
+        aln_length_ = read_length_ + ref_length_;
+        policy_ = optional_param("cuda_traceback_policy", "VERSALIGN_CUDA_POLICY", VA_POLICY_DEFAULT_OCL);
+        if (policy_ != VA_POLICY_DEFAULT_OCL && policy_ != VA_POLICY_SIMD) fatal("cuda_traceback_policy must be 0 (Default/OpenCL) or 1 (SSE/AVX)");
+        const int n_devices = optional_param("cuda_devices", "VERSALIGN_CUDA_DEVICES", 0);
+        ctx_ = acquire_context(n_devices);
+        log_info("Successfully instantiated CUDA Kernel.");
+    }
+
+    ~CUDAKernel() override {}
+
+    void score_alignments(int const &opt, int const &aln_number, char const *const *const reads,
+                          char const *const *const refs, short *const scores) override {
+        const int alg = opt & 0xF;
+        if (alg != VA_OPT_SW && alg != VA_OPT_NW) return;  // unsupported mode: touch nothing
+        apply_threads();
+        log_info("Running CUDAKernel score.");
+        int rc = va_cuda_score_ptrs(ctx_, opt, &scoring_, aln_number, reads, read_length_, refs, ref_length_, scores);
+        if (rc != VA_OK) fatal(std::string("score_alignments failed: ") + va_cuda_last_error());
+    }
+
+    void compute_alignments(int const &opt, int const &aln_number, char const *const *const reads,
+                            char const *const *const refs, Alignment *const alignments) override {
+        const int alg = opt & 0xF;
+        if (alg != VA_OPT_SW && alg != VA_OPT_NW) return;
+        const int threads = apply_threads();
+        log_info("Running CUDAKernel align.");
+        const int n = aln_number;
+        if (n <= 0) return;
+        // Result blocks must be individually delete[]-able (Alignment::~Alignment), so they are
+        // plain array-new blocks; allocate them on several threads.
+        std::vector<char *> out_read(n), out_ref(n);
+        std::vector<short> start(n);
+        const size_t len = (size_t)(aln_length_ > 0 ? aln_length_ : 1);
+        parallel_blocks(n, threads, [&](int b, int e) {
+            for (int i = b; i < e; ++i) {
+                out_read[i] = new char[len];
+                out_ref[i] = new char[len];
+            }
+        });
+        int rc = va_cuda_align_ptrs(ctx_, opt, policy_, &scoring_, n, reads, read_length_, refs, ref_length_,
+                                    out_read.data(), out_ref.data(), start.data(), nullptr);
+        if (rc != VA_OK) {
+            for (int i = 0; i < n; ++i) {
+                delete[] out_read[i];
+                delete[] out_ref[i];
+            }
+            fatal(std::string("compute_alignments failed: ") + va_cuda_last_error());
+        }
+        const short end = (short)(aln_length_ - 1);
+        for (int i = 0; i < n; ++i) {
+            Alignment &a = alignments[i];
+            a.read = out_read[i];  // previous contents are neither freed nor reused (reference semantics)
+            a.ref = out_ref[i];
+            a.readStart = start[i];
+            a.refStart = start[i];
+            a.readEnd = end;
+            a.refEnd = end;
+        }
+    }
+
+private:
+    // num_threads is read on every call like the reference (DefaultKernel.cpp:45); here it sizes
+    // the host staging pool.
+    int apply_threads() {
+        int t = 0;
+        if (_parameters && Parameters.has_key("num_threads")) t = Parameters.param_int("num_threads");
+        const int env = optional_param("cuda_host_threads", "VERSALIGN_CUDA_HOST_THREADS", 0);
+        if (env > 0) t = env;
+        va_cuda_set_host_threads(ctx_, t);
+        int hw = (int)std::thread::hardware_concurrency();
+        if (hw <= 0) hw = 1;
+        return t > 0 ? (t < hw ? t : hw) : (hw < 32 ? hw : 32);
+    }
+
+    template <class F>
+    static void parallel_blocks(int n, int threads, F fn) {
+        if (threads <= 1 || n < 4096) {
+            fn(0, n);
+            return;
+        }
+        std::vector<std::thread> pool;
+        for (int t = 0; t < threads; ++t) {
+            const int b = (int)((long long)n * t / threads), e = (int)((long long)n * (t + 1) / threads);
+            if (e > b) pool.emplace_back([=] { fn(b, e); });
+        }
+        for (auto &th : pool) th.join();
+    }
+
+    va_cuda_scoring scoring_{};
+    int read_length_ = 0, ref_length_ = 0, aln_length_ = 0;
+    int policy_ = VA_POLICY_DEFAULT_OCL;
+    va_cuda_ctx *ctx_ = nullptr;
+};
+
+}  // namespace
+
+extern "C" AlignmentKernel *spawn_alignment_kernel() { return new CUDAKernel(); }
+
+extern "C" void set_parameters(AlignmentParameters *parameters) { _parameters = parameters; }
+
+extern "C" void set_logger(AlignmentLogger *logger) { _logger = logger; }
+
+extern "C" void delete_alignment_kernel(AlignmentKernel *instance) {
+    if (instance != 0) delete instance;
+}

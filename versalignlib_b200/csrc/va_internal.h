@@ -1,0 +1,76 @@
+// va_internal.h -- host-visible declarations shared by the kernel launchers (va_kernels.cu)
+// and the C ABI / staging layer (va_cabi.cu).  Nothing here is exported.
+#ifndef VA_INTERNAL_H
+#define VA_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace va {
+
+// Base codes written by the prep kernel.  0..3 are the four bases that can score;
+// N and "anything else" (including the '\0' pad and bytes >= 0x80) always score 0 but are
+// told apart because the Default/OpenCL kernels count N as a valid character when they
+// look for the end of a sequence (DefaultKernel.cpp:308,348) while SSE/AVX do not
+// (SSEKernel.cpp:514-518,673-677).
+enum : int { CODE_A = 0, CODE_C = 1, CODE_G = 2, CODE_T = 3, CODE_N = 4, CODE_OTHER = 5 };
+
+// direction codes, shared with the traceback kernel (same numbering as SSEKernel.h:28-31)
+enum : int { DIR_START = 0, DIR_UP = 1, DIR_LEFT = 2, DIR_DIAG = 3 };
+
+enum : int { MODE_SW_SCORE = 0, MODE_NW_SCORE = 1, MODE_SW_ALIGN = 2, MODE_NW_ALIGN = 3 };
+
+struct Scoring {
+    int match, mismatch, gap_read, gap_ref;
+};
+
+// Per-pair DP extents and NW end-of-sequence markers, produced by the prep kernel.
+struct __align__(16) PairMeta {
+    int16_t rows;          // DP rows to fill   (<= read_length)
+    int16_t cols;          // DP columns to fill (<= ref_length)
+    int16_t max_read_pos;  // NW align: index of the first invalid read char - 1 (policy dependent)
+    int16_t max_ref_pos;   // NW align: same for the ref
+    int16_t true_rows;     // 1 + index of the last ACGT base of the read
+    int16_t true_cols;     // same for the ref
+    int16_t flags;         // bit 0: a non-ACGT byte inside [0,true_rows) of the read; bit 1: same for ref
+    int16_t pad;
+};
+
+// Geometry of one chunk's device buffers.  "slot" = position of a pair inside the chunk.
+struct ChunkGeom {
+    int n;             // pairs in the chunk
+    int slots;         // n rounded up (multiple of 64): stride of every slot-interleaved array
+    int read_length;   // batch-wide padded lengths (bytes per raw sequence)
+    int ref_length;
+    int read_chunks;   // ceil(read_length/16): uint4 code chunks per read
+    int ref_chunks;
+    int rows_alloc;    // rows of the direction matrix / boundary column that are allocated
+    int segs;          // ceil(ref_length/8): direction half-words per row
+};
+
+struct ChunkBuffers {
+    const uint8_t *raw_reads;  // [n][read_length]
+    const uint8_t *raw_refs;   // [n][ref_length]
+    uint4 *code_reads;         // [read_chunks][slots]
+    uint4 *code_refs;          // [ref_chunks][slots]
+    PairMeta *meta;            // [slots]
+    int32_t *boundary;         // [rows_alloc][slots]   right edge of the previous column strip
+    uint16_t *dirs;            // [segs][rows_alloc][slots]  2 bits per cell, 8 cells per half-word
+    int16_t *scores;           // [n]
+    int16_t *end_cell;         // [n][2]
+    // traceback outputs
+    uint8_t *aln_read;         // [n][read_length+ref_length]
+    uint8_t *aln_ref;
+    int16_t *start;            // [n]
+    unsigned long long *cell_count;  // device counter: DP cells computed
+};
+
+// Launchers (va_kernels.cu).  All asynchronous on `stream`; return the number of kernels launched.
+int launch_prep(const ChunkGeom &g, const ChunkBuffers &b, int mode, int policy, const Scoring &sc, cudaStream_t stream);
+int launch_fill_general(const ChunkGeom &g, const ChunkBuffers &b, int mode, int policy, const Scoring &sc,
+                        cudaStream_t stream);
+int launch_traceback(const ChunkGeom &g, const ChunkBuffers &b, int mode, bool zero_prefix, cudaStream_t stream);
+int launch_int_peak(int kind, int sm_count, int iters, unsigned int *sink, cudaStream_t stream, double *lane_ops);
+
+}  // namespace va
+#endif
