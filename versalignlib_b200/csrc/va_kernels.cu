@@ -96,6 +96,12 @@ __global__ void __launch_bounds__(128) prep_kernel(ChunkGeom g, ChunkBuffers b, 
         // scores are <= 0 (SURVEY.md A.1/A.2 "padding is neutral")
         m.rows = m.true_rows;
         m.cols = m.true_cols;
+        if (mode == MODE_SW_ALIGN) {
+            // with a zero score traceback starts at cell (0,0) (DefaultKernel.cpp:207-208), so that
+            // cell's pointer must exist even when a sequence holds no ACGT base at all
+            m.rows = (int16_t)max((int)m.rows, min(1, g.read_length));
+            m.cols = (int16_t)max((int)m.cols, min(1, g.ref_length));
+        }
     } else {
         m.rows = (int16_t)g.read_length;
         m.cols = (int16_t)g.ref_length;
@@ -242,6 +248,7 @@ __global__ void __launch_bounds__(128) traceback_kernel(ChunkGeom g, ChunkBuffer
     uint8_t *oa = b.aln_read + (size_t)slot * L;
     uint8_t *ob = b.aln_ref + (size_t)slot * L;
     int i = b.end_cell[2 * slot], j = b.end_cell[2 * slot + 1];
+    const int rows = b.meta[slot].rows, cols = b.meta[slot].cols;
     int pos = L - 2;
     if (L >= 1) {
         oa[L - 1] = 0;
@@ -249,7 +256,7 @@ __global__ void __launch_bounds__(128) traceback_kernel(ChunkGeom g, ChunkBuffer
     }
     while (true) {
         int code;
-        if (i < 0) code = DIR_START;                        // matrix row 0
+        if (i < 0 || i >= rows || j >= cols) code = DIR_START;  // matrix row 0 (or nothing was filled)
         else if (j < 0) code = NW ? DIR_UP : DIR_START;     // matrix column 0 (DefaultKernel.cpp:304)
         else code = (b.dirs[((size_t)(j >> 3) * g.rows_alloc + i) * g.slots + slot] >> (2 * (j & 7))) & 3;
         if (code == DIR_START) break;
