@@ -155,6 +155,17 @@ int va_cuda_align_device(va_cuda_ctx *ctx, int opt, int policy, const va_cuda_sc
  * context may allocate (direction matrix for align calls). */
 int va_cuda_max_resident_pairs(va_cuda_ctx *ctx, int align, int read_length, int ref_length, int64_t *max_n);
 
+/* Per-kernel device times of the LAST device-resident call, for roofline accounting:
+ * when profiling is on, CUDA events are recorded on the caller's stream around the prep, fill
+ * and traceback kernels; va_cuda_get_kernel_ms waits for them and returns the elapsed
+ * milliseconds summed over the call's sub-chunks (ms[0] prep, ms[1] fill, ms[2] traceback). */
+int va_cuda_set_profiling(va_cuda_ctx *ctx, int on);
+int va_cuda_get_kernel_ms(va_cuda_ctx *ctx, float ms[3]);
+
+/* Timings of the last host-buffer call made through the plug-in class (the context the
+ * CUDAKernel instances share).  VA_ERR_ARG before the first spawn. */
+int va_cuda_plugin_timings(va_cuda_timings *out);
+
 /* Integer-pipe microbenchmark used for the roofline denominator: runs `iters` dependent
  * rounds of `chains` independent VIADDMNMX chains per thread on every SM and reports
  * lane-operations per second (kind 0: .S32, 1: .S16x2 counted as 2 lanes, 2: .S16x2.RELU,

@@ -20,7 +20,8 @@ C_ABI_SYMBOLS = [
     "va_cuda_abi_version", "va_cuda_last_error", "va_cuda_device_count", "va_cuda_create", "va_cuda_destroy",
     "va_cuda_set_host_threads", "va_cuda_get_timings", "va_cuda_score_ptrs", "va_cuda_align_ptrs",
     "va_cuda_score_flat", "va_cuda_align_flat", "va_cuda_score_device", "va_cuda_align_device",
-    "va_cuda_max_resident_pairs", "va_cuda_int_peak",
+    "va_cuda_max_resident_pairs", "va_cuda_int_peak", "va_cuda_set_profiling", "va_cuda_get_kernel_ms",
+    "va_cuda_plugin_timings",
 ]
 PLUGIN_SYMBOLS = ["spawn_alignment_kernel", "delete_alignment_kernel", "set_parameters", "set_logger"]
 
@@ -77,8 +78,19 @@ def lib():
         L.va_cuda_align_device.argtypes = [vp, ci, ci, sp, ci, vp, ci, vp, ci, vp, vp, vp, vp, vp]
         L.va_cuda_max_resident_pairs.argtypes = [vp, ci, ci, ci, ctypes.POINTER(ctypes.c_int64)]
         L.va_cuda_int_peak.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_double), vp]
+        L.va_cuda_set_profiling.argtypes = [vp, ci]
+        L.va_cuda_get_kernel_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float * 3)]
+        L.va_cuda_plugin_timings.argtypes = [ctypes.POINTER(Timings)]
         _lib = L
     return _lib
+
+
+def plugin_timings() -> dict | None:
+    """Phase timings of the last call made through the CUDAKernel plug-in in this process."""
+    t = Timings()
+    if lib().va_cuda_plugin_timings(ctypes.byref(t)) != 0:
+        return None
+    return t.as_dict()
 
 
 def device_count() -> int:
@@ -215,6 +227,15 @@ class CudaContext:
         self._check(self._L.va_cuda_max_resident_pairs(self._h, 1 if align else 0, read_length, ref_length,
                                                        ctypes.byref(out)), "va_cuda_max_resident_pairs")
         return out.value
+
+    def set_profiling(self, on: bool) -> None:
+        self._check(self._L.va_cuda_set_profiling(self._h, 1 if on else 0), "va_cuda_set_profiling")
+
+    def kernel_ms(self) -> tuple[float, float, float]:
+        """(prep, fill, traceback) milliseconds of the last device-resident call (profiling on)."""
+        ms = (ctypes.c_float * 3)()
+        self._check(self._L.va_cuda_get_kernel_ms(self._h, ctypes.byref(ms)), "va_cuda_get_kernel_ms")
+        return float(ms[0]), float(ms[1]), float(ms[2])
 
     def int_peak(self, kind: int, stream: int = 0) -> float:
         """Measured integer-pipe throughput in lane-ops/s (kind: 0 s32, 1 s16x2, 2 s16x2.relu, 3 vimax3 s16x2)."""

@@ -57,12 +57,13 @@ struct SharedContext {
     std::mutex mu;
     va_cuda_ctx *ctx = nullptr;
     int n_devices = -1;
+    int first = 0;
 };
 SharedContext g_shared;
 
-va_cuda_ctx *acquire_context(int n_devices) {
+va_cuda_ctx *acquire_context(int n_devices, int first) {
     std::lock_guard<std::mutex> lk(g_shared.mu);
-    if (g_shared.ctx && g_shared.n_devices == n_devices) return g_shared.ctx;
+    if (g_shared.ctx && g_shared.n_devices == n_devices && g_shared.first == first) return g_shared.ctx;
     if (g_shared.ctx) {
         va_cuda_destroy(g_shared.ctx);
         g_shared.ctx = nullptr;
@@ -70,13 +71,15 @@ va_cuda_ctx *acquire_context(int n_devices) {
     int visible = 0;
     if (va_cuda_device_count(&visible) != VA_OK) fatal(std::string("Cannot instantiate Kernel. ") + va_cuda_last_error());
     std::vector<int> devs;
-    const int use = (n_devices <= 0 || n_devices > visible) ? visible : n_devices;
-    for (int d = 0; d < use; ++d) devs.push_back(d);
+    if (first < 0 || first >= visible) first = 0;
+    const int use = (n_devices <= 0 || first + n_devices > visible) ? visible - first : n_devices;
+    for (int d = 0; d < use; ++d) devs.push_back(first + d);
     va_cuda_ctx *ctx = nullptr;
     if (va_cuda_create(&ctx, devs.data(), (int)devs.size(), 0) != VA_OK)
         fatal(std::string("Cannot instantiate Kernel. ") + va_cuda_last_error());
     g_shared.ctx = ctx;
     g_shared.n_devices = n_devices;
+    g_shared.first = first;
     return ctx;
 }
 
@@ -103,7 +106,9 @@ public:
         policy_ = optional_param("cuda_traceback_policy", "VERSALIGN_CUDA_POLICY", VA_POLICY_DEFAULT_OCL);
         if (policy_ != VA_POLICY_DEFAULT_OCL && policy_ != VA_POLICY_SIMD) fatal("cuda_traceback_policy must be 0 (Default/OpenCL) or 1 (SSE/AVX)");
         const int n_devices = optional_param("cuda_devices", "VERSALIGN_CUDA_DEVICES", 0);
-        ctx_ = acquire_context(n_devices);
+        // one process per GPU (torchrun): rank r passes cuda_device_first = r, cuda_devices = 1
+        const int first = optional_param("cuda_device_first", "VERSALIGN_CUDA_DEVICE_FIRST", 0);
+        ctx_ = acquire_context(n_devices, first);
         log_info("Successfully instantiated CUDA Kernel.");
     }
 
@@ -194,6 +199,12 @@ private:
 };
 
 }  // namespace
+
+extern "C" int va_cuda_plugin_timings(va_cuda_timings *out) {
+    std::lock_guard<std::mutex> lk(g_shared.mu);
+    if (!g_shared.ctx || !out) return VA_ERR_ARG;
+    return va_cuda_get_timings(g_shared.ctx, out);
+}
 
 extern "C" AlignmentKernel *spawn_alignment_kernel() { return new CUDAKernel(); }
 

@@ -245,6 +245,10 @@ struct Engine {
     ChunkSlot resident;  // workspace of the device-resident entry points (no pinned memory, caller's stream)
     unsigned long long *d_cells = nullptr;
     unsigned int *d_sink = nullptr;
+    // optional per-kernel events of device-resident calls (va_cuda_set_profiling)
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;  // 4 per sub-chunk: before prep, after prep, after fill, after traceback
+    size_t prof_used = 0;
 
     int init(int dev) {
         device = dev;
@@ -270,6 +274,8 @@ struct Engine {
         resident.release();
         if (d_cells) cudaFree(d_cells);
         if (d_sink) cudaFree(d_sink);
+        for (auto ev : prof_events) cudaEventDestroy(ev);
+        prof_events.clear();
         d_cells = nullptr;
         d_sink = nullptr;
     }
@@ -383,7 +389,8 @@ void fill_geom(ChunkGeom &g, const Shape &sh, int n) {
 // the device.  Outputs go to the given device pointers.  Returns kernels launched (or < 0).
 int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int policy, const Scoring &sc, int n,
                         const uint8_t *raw_reads, const uint8_t *raw_refs, int16_t *scores, int16_t *end_cell,
-                        uint8_t *aln_read, uint8_t *aln_ref, int16_t *start, bool zero_prefix, cudaStream_t stream) {
+                        uint8_t *aln_read, uint8_t *aln_ref, int16_t *start, bool zero_prefix, cudaStream_t stream,
+                        bool profile = false) {
     ChunkGeom g;
     fill_geom(g, sh, n);
     ChunkBuffers b{};
@@ -401,9 +408,25 @@ int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int
     b.start = start;
     b.cell_count = e.d_cells;
     int launches = 0;
+    cudaEvent_t *pe = nullptr;
+    if (profile) {
+        if (e.prof_used + 4 > e.prof_events.size()) {
+            for (int k = 0; k < 4; ++k) {
+                cudaEvent_t ev;
+                cudaEventCreate(&ev);
+                e.prof_events.push_back(ev);
+            }
+        }
+        pe = &e.prof_events[e.prof_used];
+        e.prof_used += 4;
+        cudaEventRecord(pe[0], stream);
+    }
     launches += launch_prep(g, b, mode, policy, sc, stream);
+    if (pe) cudaEventRecord(pe[1], stream);
     launches += launch_fill_general(g, b, mode, policy, sc, stream);
+    if (pe) cudaEventRecord(pe[2], stream);
     if (sh.align) launches += launch_traceback(g, b, mode, zero_prefix, stream);
+    if (pe) cudaEventRecord(pe[3], stream);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return set_error(VA_ERR_DEVICE, "kernel launch failed: %s", cudaGetErrorString(err));
     return launches;
@@ -819,6 +842,7 @@ static int resident_call(va_cuda_ctx *ctx, int opt, bool align, int policy, cons
     cudaStream_t st = (cudaStream_t)stream;
     const int L = c.sh.L;
     int launches = 0;
+    e.prof_used = 0;
     for (int64_t first = 0; first < n; first += sub) {
         const int count = (int)std::min<int64_t>(sub, n - first);
         int16_t *scores = d_scores ? (int16_t *)d_scores + first : (int16_t *)ws.scores.p + first;
@@ -828,7 +852,7 @@ static int resident_call(va_cuda_ctx *ctx, int opt, bool align, int policy, cons
                                     (const uint8_t *)d_refs + first * ref_length, scores, endc,
                                     align ? (uint8_t *)d_aln_read + first * L : nullptr,
                                     align ? (uint8_t *)d_aln_ref + first * L : nullptr,
-                                    align ? (int16_t *)d_start + first : nullptr, true, st);
+                                    align ? (int16_t *)d_start + first : nullptr, true, st, e.profiling);
         if (k < 0) return k;
         launches += k;
     }
@@ -849,6 +873,28 @@ int va_cuda_align_device(va_cuda_ctx *ctx, int opt, int policy, const va_cuda_sc
     if (n > 0 && (!d_aln_read || !d_aln_ref || !d_start)) return set_error(VA_ERR_ARG, "null device output buffer");
     return resident_call(ctx, opt, true, policy, sc, n, d_reads, read_length, d_refs, ref_length, nullptr, d_aln_read,
                          d_aln_ref, d_start, d_end_cell, stream);
+}
+
+int va_cuda_set_profiling(va_cuda_ctx *ctx, int on) {
+    if (!ctx) return set_error(VA_ERR_ARG, "context is null");
+    ctx->engines[0].profiling = on != 0;
+    ctx->engines[0].prof_used = 0;
+    return VA_OK;
+}
+
+int va_cuda_get_kernel_ms(va_cuda_ctx *ctx, float ms[3]) {
+    if (!ctx || !ms) return set_error(VA_ERR_ARG, "null argument");
+    Engine &e = ctx->engines[0];
+    ms[0] = ms[1] = ms[2] = 0.f;
+    for (size_t k = 0; k + 4 <= e.prof_used; k += 4) {
+        CUDA_TRY(cudaEventSynchronize(e.prof_events[k + 3]));
+        for (int j = 0; j < 3; ++j) {
+            float t = 0.f;
+            CUDA_TRY(cudaEventElapsedTime(&t, e.prof_events[k + j], e.prof_events[k + j + 1]));
+            ms[j] += t;
+        }
+    }
+    return VA_OK;
 }
 
 int va_cuda_int_peak(va_cuda_ctx *ctx, int kind, double *lane_ops_per_s, void *stream) {
