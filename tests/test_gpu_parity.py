@@ -159,3 +159,40 @@ def test_large_batch_properties(ctx):
     assert np.array_equal(ctx.score_flat(ora.SW, padded_r, padded_f), got)
     same = ctx.score_flat(ora.NW, refs, refs, (3, -2, -5, -5))
     assert np.all(same == 450)
+
+
+def test_general_kernel_only_subprocess():
+    """Same parity deck with the packed kernels switched off (VERSALIGN_CUDA_GENERAL_ONLY=1), in a
+    fresh process because the switch is read once per process."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import numpy as np
+from oracle import binding as ora
+from versalignlib_b200 import capi, synth
+reads, refs = synth.uniform_batch(600, 100, 150, p_sub=0.1, q_indel=0.02, seed=3)
+with capi.CudaContext(devices=[0]) as ctx:
+    for opt in (0, 1):
+        assert np.array_equal(ctx.score_flat(opt, reads, refs), ora.score(opt, reads, refs))
+        for pol in (0, 1):
+            a, b, s, e = ctx.align_flat(opt, pol, reads, refs)
+            oa, ob, os_, oe = ora.align(opt, pol, reads, refs)
+            assert np.array_equal(a, oa) and np.array_equal(b, ob) and np.array_equal(s, os_) and np.array_equal(e, oe)
+print("general-only ok")
+'''
+    env = dict(os.environ, VERSALIGN_CUDA_GENERAL_ONLY="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "general-only ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_wide_scores_fall_back_to_general_kernel(ctx):
+    """Scores that do not fit the packed kernels' 8-bit tables / 16-bit headroom stay exact."""
+    _, reads, refs = BATCHES[0]
+    for sc in [(200, -150, -300, -300), (20, -30, -50, -40)]:
+        for opt in (ora.SW, ora.NW):
+            assert np.array_equal(ctx.score_flat(opt, reads, refs, sc), ora.score(opt, reads, refs, sc)), (sc, opt)
+        a, b, start, end = ctx.align_flat(ora.NW, 0, reads, refs, sc)
+        oa, ob, ostart, oend = ora.align(ora.NW, 0, reads, refs, sc)
+        assert np.array_equal(a, oa) and np.array_equal(b, ob) and np.array_equal(start, ostart)

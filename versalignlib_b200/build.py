@@ -30,8 +30,8 @@ NVCC_FLAGS = [
     "-I", INCLUDE, "-I", CSRC,
 ]
 
-CUDA_SOURCES = ["va_kernels.cu", "va_cabi.cu", "cuda_kernel_plugin.cpp"]
-CUDA_HEADERS = ["va_device.cuh", "va_internal.h"]
+CUDA_SOURCES = ["va_kernels.cu", "va_fast.cu", "va_cabi.cu", "cuda_kernel_plugin.cpp"]
+CUDA_HEADERS = ["va_device.cuh", "va_fast.cuh", "va_internal.h"]
 
 
 def _newer(target: str, deps: list[str]) -> bool:

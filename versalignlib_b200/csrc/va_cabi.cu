@@ -16,6 +16,7 @@
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <mutex>
@@ -212,7 +213,7 @@ struct PinBuf {
 
 // Device workspace of one chunk in flight.
 struct ChunkSlot {
-    DevBuf raw_reads, raw_refs, code_reads, code_refs, meta, boundary, dirs, scores, end_cell, aln_read, aln_ref, start;
+    DevBuf raw_reads, raw_refs, code_reads, code_refs, meta, boundary, dirs, hrow, scores, end_cell, aln_read, aln_ref, start;
     PinBuf h_reads, h_refs, h_scores, h_end_cell, h_aln_read, h_aln_ref, h_start;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_done = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
@@ -222,7 +223,7 @@ struct ChunkSlot {
     bool busy = false;
 
     void release() {
-        DevBuf *d[] = {&raw_reads, &raw_refs, &code_reads, &code_refs, &meta, &boundary, &dirs, &scores, &end_cell, &aln_read, &aln_ref, &start};
+        DevBuf *d[] = {&raw_reads, &raw_refs, &code_reads, &code_refs, &meta, &boundary, &dirs, &hrow, &scores, &end_cell, &aln_read, &aln_ref, &start};
         for (auto *b : d) b->release();
         PinBuf *h[] = {&h_reads, &h_refs, &h_scores, &h_end_cell, &h_aln_read, &h_aln_ref, &h_start};
         for (auto *b : h) b->release();
@@ -286,9 +287,13 @@ struct Shape {
     int read_length, ref_length, L;
     int read_chunks, ref_chunks, segs, rows_alloc;
     bool align;
+    // direction bytes per matrix row and pair: the general and the packed kernel keep separate
+    // regions because one chunk can hold pairs of both kinds
+    size_t gen_dir_row_bytes() const { return (size_t)segs * 2; }
+    size_t dir_row_bytes() const { return gen_dir_row_bytes() + fast_dirs_bytes_per_row_per_slot(ref_length); }
     size_t per_pair_workspace() const {
         size_t b = (size_t)(read_chunks + ref_chunks) * 16 + sizeof(PairMeta) + (size_t)rows_alloc * 4;
-        if (align) b += (size_t)segs * rows_alloc * 2;
+        if (align) b += dir_row_bytes() * rows_alloc + (size_t)ref_length * 2;
         return b;
     }
     size_t per_pair_io() const {
@@ -353,7 +358,8 @@ int reserve_slot(ChunkSlot &s, const Shape &sh, int cap_pairs, bool pinned) {
     if ((rc = s.scores.reserve(slots * 2))) return rc;
     if ((rc = s.end_cell.reserve(slots * 4))) return rc;
     if (sh.align) {
-        if ((rc = s.dirs.reserve(slots * (size_t)sh.segs * sh.rows_alloc * 2))) return rc;
+        if ((rc = s.dirs.reserve(slots * sh.dir_row_bytes() * sh.rows_alloc + 512))) return rc;
+        if ((rc = s.hrow.reserve(slots * (size_t)std::max(sh.ref_length, 1) * 2 + 64))) return rc;
         if (pinned) {
             if ((rc = s.aln_read.reserve((size_t)cap_pairs * sh.L + 16))) return rc;
             if ((rc = s.aln_ref.reserve((size_t)cap_pairs * sh.L + 16))) return rc;
@@ -383,6 +389,8 @@ void fill_geom(ChunkGeom &g, const Shape &sh, int n) {
     g.ref_chunks = sh.ref_chunks;
     g.rows_alloc = sh.rows_alloc;
     g.segs = sh.segs;
+    g.duos = g.slots / 2;
+    g.fast_tw = 0;
 }
 
 // Enqueue prep + fill (+ traceback) for n pairs whose raw bytes are at raw_reads/raw_refs on
@@ -393,6 +401,10 @@ int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int
                         bool profile = false) {
     ChunkGeom g;
     fill_geom(g, sh, n);
+    // VERSALIGN_CUDA_GENERAL_ONLY=1 keeps every pair on the 32-bit kernel (parity tests use it to
+    // cover that kernel on inputs the packed kernels would otherwise take)
+    static const bool general_only = [] { const char *v = getenv("VERSALIGN_CUDA_GENERAL_ONLY"); return v && atoi(v) != 0; }();
+    if (!general_only && fast_scoring_ok(mode, policy, sc, sh.read_length, sh.ref_length)) g.fast_tw = fast_pick_tw(mode, sh.ref_length);
     ChunkBuffers b{};
     b.raw_reads = raw_reads;
     b.raw_refs = raw_refs;
@@ -401,6 +413,8 @@ int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int
     b.meta = (PairMeta *)ws.meta.p;
     b.boundary = (int32_t *)ws.boundary.p;
     b.dirs = (uint16_t *)ws.dirs.p;
+    b.fdirs = (uint2 *)((char *)ws.dirs.p + round_up((size_t)g.slots * sh.gen_dir_row_bytes() * sh.rows_alloc, 256));
+    b.hrow = (uint32_t *)ws.hrow.p;
     b.scores = scores;
     b.end_cell = end_cell;
     b.aln_read = aln_read;
@@ -423,9 +437,10 @@ int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int
     }
     launches += launch_prep(g, b, mode, policy, sc, stream);
     if (pe) cudaEventRecord(pe[1], stream);
+    launches += launch_fill_fast(g, b, mode, sc, stream);
     launches += launch_fill_general(g, b, mode, policy, sc, stream);
     if (pe) cudaEventRecord(pe[2], stream);
-    if (sh.align) launches += launch_traceback(g, b, mode, zero_prefix, stream);
+    if (sh.align) launches += launch_traceback(g, b, mode, zero_prefix, sc.gap_ref, stream);
     if (pe) cudaEventRecord(pe[3], stream);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return set_error(VA_ERR_DEVICE, "kernel launch failed: %s", cudaGetErrorString(err));

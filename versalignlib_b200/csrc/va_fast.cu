@@ -1,0 +1,246 @@
+// va_fast.cu -- the packed inter-task fill kernels: one thread computes TWO pairs at once in the
+// two signed 16-bit lanes of every register, with the Blackwell DPX instructions
+// (VIADDMNMX.S16x2[.RELU], VIMNMX.S16x2 with predicate outputs, VIMNMX3.S16x2).
+//
+// Same recurrences as the reference's kernels (score: DefaultKernel.cpp:83-202,
+// SSEKernel.cpp:1007-1315; NW fill with pointers: DefaultKernel.cpp:282-389), restructured for
+// the GPU instead of translated:
+//   * a strip of TW ref columns lives in registers (previous-row H per column + one PRMT selector
+//     per column); the thread sweeps all read rows of the strip, then moves to the next strip; the
+//     strip's right edge goes through a slot-interleaved boundary array (coalesced 4 B / thread);
+//   * the substitution score of both lanes is ONE prmt: the row supplies two 4-byte tables
+//     (scores of read base A/B against ref A,C,G,T), the column supplies the selector; the
+//     selector's sign-replicate nibbles widen the 8-bit entries to 16-bit lanes;
+//   * per cell: t = max(up+gF, left+gR); H = max(diag+s, t [,0])  -> 3 DPX instructions
+//     (+ 1 prmt, + 1/2 VIMNMX3 for the SW running maximum);
+//   * NW align keeps H+gF per column so that both comparisons the Default/OpenCL pointer rule
+//     needs (diag+s >= max(up,left) -> DIAG, else up >= left -> UP, else LEFT) fall out of the
+//     two max instructions as predicates; the predicates are banked into bit planes with
+//     predicated FADDs (2^23-biased floats: exact integers, runs on the FP pipes and leaves the
+//     integer pipe to the recurrence).  2 bits per cell reach HBM, as coalesced 8-byte stores.
+#include <type_traits>
+
+#include "va_fast.cuh"
+
+namespace va {
+
+namespace {
+
+constexpr uint32_t NEG2 = 0x80008000u;  // (-32768, -32768): identity of the packed max
+
+__device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b) { return __viaddmax_s16x2(a, b, NEG2); }
+
+template <int MODE, int TW>
+__global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuffers b, FastConsts fc) {
+    constexpr bool NWA = MODE == MODE_NW_ALIGN;
+    constexpr bool SWS = MODE == MODE_SW_SCORE;
+    constexpr bool NWS = MODE == MODE_NW_SCORE;
+    constexpr int NG = (TW + 15) / 16;
+
+    __shared__ uint32_t T[8];
+    if (threadIdx.x < 8) T[threadIdx.x] = fc.tab[threadIdx.x];
+    __syncthreads();
+
+    const int duo = blockIdx.x * blockDim.x + threadIdx.x;
+    const int slot_a = 2 * duo, slot_b = slot_a + 1;
+    unsigned long long cells = 0;
+    bool mine = false;
+    PairMeta ma, mb;
+    if (slot_b < g.n) {
+        ma = b.meta[slot_a];
+        mb = b.meta[slot_b];
+        mine = duo_is_fast(g, MODE, slot_a, ma, mb);
+    }
+    if (mine) {
+        const int m = max((int)ma.rows, (int)mb.rows), n = ma.cols;
+        cells = ((unsigned long long)ma.rows + (unsigned long long)mb.rows) * (unsigned long long)n;
+        const uint32_t gF2 = fc.gF2, gR2 = fc.gR2, dFR2 = fc.dFR2;
+        const uint8_t *cread = reinterpret_cast<const uint8_t *>(b.code_reads);
+        const uint8_t *cref = reinterpret_cast<const uint8_t *>(b.code_refs);
+        uint32_t *bnd = reinterpret_cast<uint32_t *>(b.boundary);
+        uint2 *dirs = b.fdirs;
+
+        uint32_t best = 0;  // SW: running max; NW score: max(0, last column, last row)
+        const int nstrips = (n + TW - 1) / TW;
+        for (int s = 0; s < nstrips; ++s) {
+            const int c0 = s * TW;
+            const bool first = s == 0, last = s == nstrips - 1;
+            uint32_t sel[TW], H[TW];
+#pragma unroll
+            for (int k = 0; k < TW; ++k) {
+                const int col = min(c0 + k, n - 1);  // columns past n repeat the last one; their cells are never used
+                const size_t off = ((size_t)(col >> 4) * g.slots) * 16 + (col & 15);
+                const uint32_t fa = cref[off + (size_t)slot_a * 16], fb = cref[off + (size_t)slot_b * 16];
+                // nibbles: lane A low byte <- table a[fa], high byte <- its sign; lane B from table b (bytes 4..7)
+                sel[k] = fa | ((fa | 8u) << 4) | ((fb | 4u) << 8) | ((fb | 12u) << 12);
+                H[k] = NWA ? gF2 : 0u;  // matrix row 0 is 0 (NW align keeps H + gF)
+            }
+            // H[i][c0] feeding the first column's diagonal: 0 for matrix row 0
+            uint32_t diag_next = NWA ? gF2 : 0u;
+            // matrix column 0: 0 in the score modes, (i+1)*gF in NW align; carried as "left + gR"
+            uint32_t col0 = NWA ? add2(gF2, gR2) : gR2;
+            const int kv = min(TW, n - c0);  // valid columns of this strip
+            const bool full = kv == TW;
+
+            const uint8_t *ra = cread + (size_t)slot_a * 16;  // read codes of lane A; lane B is the next uint4
+            const uint32_t chunk_stride = (uint32_t)g.slots * 16u;
+            // One sweep over all read rows of this strip.  PARTIAL (only ever the last strip) guards
+            // the few places that must not see the columns past n; full strips run unguarded.
+            auto sweep = [&](auto partial_tag) {
+                constexpr bool PARTIAL = decltype(partial_tag)::value;
+                uint32_t *bp = bnd + duo;
+                uint2 *dp = dirs + fast_dir_index(g, s, 0, 0, duo);
+                for (int i = 0; i < m; ++i, bp += g.duos, dp += (size_t)NG * g.duos) {
+                    const uint32_t roff = (uint32_t)(i >> 4) * chunk_stride + (uint32_t)(i & 15);
+                    const uint32_t ta = T[ra[roff]], tb = T[ra[roff + 16]];
+                    uint32_t left = first ? col0 : *bp;
+                    if (NWA && first) col0 = add2(col0, gF2);
+                    uint32_t diag = diag_next;
+                    diag_next = add2(left, dFR2);
+                    float p1l[NG], p1h[NG], p2l[NG], p2h[NG];
+#pragma unroll
+                    for (int q = 0; q < NG; ++q) p1l[q] = p1h[q] = p2l[q] = p2h[q] = 8388608.0f;
+#pragma unroll
+                    for (int k = 0; k < TW; ++k) {
+                        const uint32_t sub = prmt(ta, tb, sel[k]);
+                        const uint32_t up = H[k];
+                        if (NWA) {
+                            bool dl, dh, ul, uh;
+                            const uint32_t t = __vibmax_s16x2(up, left, &uh, &ul);  // up+gF >= left+gR : UP before LEFT
+                            const uint32_t d = add2(diag, sub);                     // diag + s (table holds s - gF)
+                            const uint32_t h = __vibmax_s16x2(d, t, &dh, &dl);      // diag+s >= max(up,left) : DIAG first
+                            const float bit = (float)(1u << (k & 15));
+                            if (dl) p1l[k >> 4] += bit;
+                            if (dh) p1h[k >> 4] += bit;
+                            if (ul) p2l[k >> 4] += bit;
+                            if (uh) p2h[k >> 4] += bit;
+                            left = add2(h, gR2);
+                            H[k] = add2(h, gF2);
+                        } else {
+                            const uint32_t t = __viaddmax_s16x2(up, gF2, left);
+                            const uint32_t h = SWS ? __viaddmax_s16x2_relu(diag, sub, t) : __viaddmax_s16x2(diag, sub, t);
+                            left = add2(h, gR2);
+                            H[k] = h;
+                            if (SWS) {
+                                // running maximum: two cells per VIMNMX3; columns past n (repeats of the
+                                // last ref base) stay out of it
+                                if (PARTIAL) {
+                                    if (k < kv) best = __vmaxs2(best, h);
+                                } else if (k & 1) {
+                                    best = __vimax3_s16x2(best, h, H[k - 1]);
+                                }
+                            }
+                            if (NWS && PARTIAL && k == kv - 1) best = __vmaxs2(best, h);  // last column of this row
+                        }
+                        diag = up;
+                    }
+                    if (!last) *bp = left;
+                    if (NWS && !PARTIAL && last) best = __vmaxs2(best, H[TW - 1]);  // last column (SSEKernel.cpp:1285-1291)
+                    if (NWA) {
+#pragma unroll
+                        for (int q = 0; q < NG; ++q) {
+                            uint2 w;
+                            w.x = __byte_perm(__float_as_uint(p1l[q]), __float_as_uint(p1h[q]), 0x5410);
+                            w.y = __byte_perm(__float_as_uint(p2l[q]), __float_as_uint(p2h[q]), 0x5410);
+                            dp[(size_t)q * g.duos] = w;
+                        }
+                    }
+                }
+            };
+            if (NWA || full) sweep(std::false_type{});
+            else sweep(std::true_type{});
+            if (NWS) {  // whole last row (SSEKernel.cpp:1302-1310); column 0 is 0 and `best` starts at 0
+#pragma unroll
+                for (int k = 0; k < TW; ++k)
+                    if (c0 + k < n) best = __vmaxs2(best, H[k]);
+            }
+            if (NWA) {  // the row the end-cell rule scans (DefaultKernel.cpp:352-355,381-387)
+#pragma unroll
+                for (int k = 0; k < TW; ++k)
+                    if (c0 + k < n) b.hrow[(size_t)(c0 + k) * g.duos + duo] = H[k];
+            }
+        }
+        if (!NWA) {
+            b.scores[slot_a] = (int16_t)(best & 0xFFFF);
+            b.scores[slot_b] = (int16_t)(best >> 16);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) cells += __shfl_xor_sync(0xffffffffu, cells, o);
+    if ((threadIdx.x & 31) == 0 && cells) atomicAdd(b.cell_count, cells);
+}
+
+template <int MODE, int TW>
+void launch_one(const ChunkGeom &g, const ChunkBuffers &b, const FastConsts &fc, cudaStream_t stream) {
+    const int threads = 128;
+    const int duos = (g.n + 1) / 2;
+    const int blocks = (duos + threads - 1) / threads;
+    fill_fast_kernel<MODE, TW><<<blocks, threads, 0, stream>>>(g, b, fc);
+}
+
+template <int MODE>
+void launch_tw(const ChunkGeom &g, const ChunkBuffers &b, const FastConsts &fc, cudaStream_t stream) {
+    switch (g.fast_tw) {
+        case 30: launch_one<MODE, 30>(g, b, fc, stream); break;
+        default: launch_one<MODE, 32>(g, b, fc, stream); break;
+    }
+}
+
+uint32_t table_word(int code, int match, int mismatch, int offset) {
+    uint32_t w = 0;
+    for (int f = 0; f < 4; ++f) {
+        const int s = (code < 4 ? (code == f ? match : mismatch) : 0) - offset;
+        w |= ((uint32_t)s & 0xFFu) << (8 * f);
+    }
+    return w;
+}
+
+bool fits8(int v) { return v >= -128 && v <= 127; }
+
+}  // namespace
+
+// The packed kernels are exact only while (a) every table entry fits a signed byte and (b) no
+// cell can leave the int16 range; otherwise the call stays on the general 32-bit kernel.
+bool fast_scoring_ok(int mode, int policy, const Scoring &sc, int read_length, int ref_length) {
+    if (mode == MODE_SW_ALIGN) return false;              // not packed yet: general kernel
+    if (mode == MODE_NW_ALIGN && policy != 0) return false;  // SSE/AVX pointer rule: general kernel
+    const int off = mode == MODE_NW_ALIGN ? sc.gap_ref : 0;
+    if (!fits8(sc.match - off) || !fits8(sc.mismatch - off) || !fits8(-off)) return false;
+    int mx = 1;
+    for (int v : {sc.match, sc.mismatch, sc.gap_read, sc.gap_ref}) mx = max(mx, v < 0 ? -v : v);
+    return (long long)(read_length + ref_length + 4) * mx <= 32000;
+}
+
+int fast_pick_tw(int mode, int ref_length) {
+    (void)mode;
+    // fewest computed columns wins; ties go to the wider strip (fewer passes over the read)
+    const int c32 = (ref_length + 31) / 32 * 32, c30 = (ref_length + 29) / 30 * 30;
+    return c30 < c32 ? 30 : 32;
+}
+
+size_t fast_dirs_bytes_per_row_per_slot(int ref_length) {
+    // per row and duo: strips * groups * 8 bytes; both strip widths use 2 groups
+    const size_t s32 = (size_t)(ref_length + 31) / 32, s30 = (size_t)(ref_length + 29) / 30;
+    return (s32 > s30 ? s32 : s30) * 2 * 8 / 2;
+}
+
+int launch_fill_fast(const ChunkGeom &g, const ChunkBuffers &b, int mode, const Scoring &sc, cudaStream_t stream) {
+    if (g.fast_tw == 0 || g.n < 2) return 0;
+    FastConsts fc{};
+    const int off = mode == MODE_NW_ALIGN ? sc.gap_ref : 0;
+    for (int c = 0; c < 8; ++c) fc.tab[c] = table_word(c, sc.match, sc.mismatch, off);
+    fc.gF = sc.gap_ref;
+    fc.gR = sc.gap_read;
+    fc.gF2 = ((uint32_t)sc.gap_ref & 0xFFFFu) * 0x00010001u;
+    fc.gR2 = ((uint32_t)sc.gap_read & 0xFFFFu) * 0x00010001u;
+    const int d = mode == MODE_NW_ALIGN ? sc.gap_ref - sc.gap_read : -sc.gap_read;
+    fc.dFR2 = ((uint32_t)d & 0xFFFFu) * 0x00010001u;
+    switch (mode) {
+        case MODE_SW_SCORE: launch_tw<MODE_SW_SCORE>(g, b, fc, stream); break;
+        case MODE_NW_SCORE: launch_tw<MODE_NW_SCORE>(g, b, fc, stream); break;
+        case MODE_NW_ALIGN: launch_tw<MODE_NW_ALIGN>(g, b, fc, stream); break;
+        default: return 0;
+    }
+    return 1;
+}
+
+}  // namespace va

@@ -1,0 +1,35 @@
+// va_fast.cuh -- device-side pieces shared by the packed (s16x2) fill kernels and the
+// traceback kernel: which pairs the packed path owns, and how its direction bits are laid out.
+#ifndef VA_FAST_CUH
+#define VA_FAST_CUH
+
+#include "va_device.cuh"
+#include "va_internal.h"
+
+namespace va {
+
+// A "duo" is two neighbouring slots (2u, 2u+1) computed by ONE thread in the two 16-bit lanes
+// of every register.  The packed kernels own a duo iff this predicate holds; otherwise the
+// general kernel computes both pairs.  Both kernels evaluate it, so no flag is exchanged.
+//   - the per-column PRMT selector cannot express "scores 0", so no non-ACGT byte may sit inside
+//     the ref columns that are filled (non-ACGT READ bytes are fine: their row table is all zero);
+//   - both lanes sweep the same columns; rows may differ for the score modes (trailing rows that
+//     can only score 0 are neutral) but not for NW align, whose end-cell rule reads one exact row.
+__device__ __forceinline__ bool duo_is_fast(const ChunkGeom &g, int mode, int slot_a, const PairMeta &a, const PairMeta &b) {
+    if (g.fast_tw == 0 || slot_a + 1 >= g.n) return false;
+    if ((a.flags & 2) || (b.flags & 2)) return false;
+    if (a.cols != b.cols || a.cols <= 0) return false;
+    if (a.cols != a.true_cols || b.cols != b.true_cols) return false;  // no padded / N tail inside the sweep
+    if (mode == MODE_NW_ALIGN || mode == MODE_SW_ALIGN) return a.rows == b.rows && a.rows > 0;
+    return max(a.rows, b.rows) > 0;
+}
+
+__device__ __forceinline__ int fast_groups(int tw) { return (tw + 15) >> 4; }
+
+// index (in uint2 units) of the direction words of (strip, row, group) for duo u
+__device__ __forceinline__ size_t fast_dir_index(const ChunkGeom &g, int strip, int row, int group, int duo) {
+    return (((size_t)strip * g.rows_alloc + row) * fast_groups(g.fast_tw) + group) * g.duos + duo;
+}
+
+}  // namespace va
+#endif

@@ -46,6 +46,16 @@ struct ChunkGeom {
     int ref_chunks;
     int rows_alloc;    // rows of the direction matrix / boundary column that are allocated
     int segs;          // ceil(ref_length/8): direction half-words per row
+    int fast_tw;       // column-strip width of the packed 16-bit kernels for this call, 0 = not eligible
+    int duos;          // slots / 2: stride of the arrays the packed kernels index by pair-of-pairs
+};
+
+// Constants of the packed (two pairs per thread, s16x2) kernels, built on the host per call.
+struct FastConsts {
+    uint32_t tab[8];   // tab[read_code]: four 8-bit substitution scores vs ref A,C,G,T (NW align: minus gap_ref)
+    uint32_t gF2, gR2; // gap scores replicated in both 16-bit lanes
+    uint32_t dFR2;     // NW align: gap_ref - gap_read ; score modes: -gap_read   (boundary -> diagonal conversion)
+    int gF, gR;
 };
 
 struct ChunkBuffers {
@@ -55,7 +65,10 @@ struct ChunkBuffers {
     uint4 *code_refs;          // [ref_chunks][slots]
     PairMeta *meta;            // [slots]
     int32_t *boundary;         // [rows_alloc][slots]   right edge of the previous column strip
-    uint16_t *dirs;            // [segs][rows_alloc][slots]  2 bits per cell, 8 cells per half-word
+    uint16_t *dirs;            // general kernel: [segs][rows_alloc][slots] half-words, 2 bits per cell, 8 cells each
+    uint2 *fdirs;              // packed kernel:  [strip][rows_alloc][group][duos] (DIAG plane, UP plane), 16 cells each
+                               // (separate regions: one chunk can hold pairs of both kinds)
+    uint32_t *hrow;            // packed NW align: [ref_length][duos] last valid row of the matrix (H + gap_ref)
     int16_t *scores;           // [n]
     int16_t *end_cell;         // [n][2]
     // traceback outputs
@@ -69,7 +82,12 @@ struct ChunkBuffers {
 int launch_prep(const ChunkGeom &g, const ChunkBuffers &b, int mode, int policy, const Scoring &sc, cudaStream_t stream);
 int launch_fill_general(const ChunkGeom &g, const ChunkBuffers &b, int mode, int policy, const Scoring &sc,
                         cudaStream_t stream);
-int launch_traceback(const ChunkGeom &g, const ChunkBuffers &b, int mode, bool zero_prefix, cudaStream_t stream);
+// packed kernels (va_fast.cu)
+bool fast_scoring_ok(int mode, int policy, const Scoring &sc, int read_length, int ref_length);
+int fast_pick_tw(int mode, int ref_length);
+size_t fast_dirs_bytes_per_row_per_slot(int ref_length);
+int launch_fill_fast(const ChunkGeom &g, const ChunkBuffers &b, int mode, const Scoring &sc, cudaStream_t stream);
+int launch_traceback(const ChunkGeom &g, const ChunkBuffers &b, int mode, bool zero_prefix, int gap_ref, cudaStream_t stream);
 int launch_int_peak(int kind, int sm_count, int iters, unsigned int *sink, cudaStream_t stream, double *lane_ops);
 
 }  // namespace va

@@ -12,6 +12,7 @@
 //                      (DefaultKernel.cpp:391-525; SSEKernel.cpp:729-1005; alignment_kernels.cl:146-192,370-414)
 #include "va_internal.h"
 #include "va_device.cuh"
+#include "va_fast.cuh"
 
 namespace va {
 
@@ -129,7 +130,8 @@ __global__ void __launch_bounds__(128) fill_general_kernel(ChunkGeom g, ChunkBuf
 
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long cells = 0;
-    if (slot < g.n) {
+    // pairs the packed kernel owns (va_fast.cuh) are skipped here
+    if (slot < g.n && !duo_is_fast(g, MODE, slot & ~1, b.meta[slot & ~1], b.meta[slot | 1])) {
         const PairMeta meta = b.meta[slot];
         const int m = meta.rows, n = meta.cols;
         const int gF = sc.gap_ref, gR = sc.gap_read;
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(128) fill_general_kernel(ChunkGeom g, ChunkBuf
 // ------------------------------------------------------------------------------------------
 
 template <bool NW>
-__global__ void __launch_bounds__(128) traceback_kernel(ChunkGeom g, ChunkBuffers b, int zero_prefix) {
+__global__ void __launch_bounds__(128) traceback_kernel(ChunkGeom g, ChunkBuffers b, int zero_prefix, int gap_ref) {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= g.n) return;
     const int L = g.read_length + g.ref_length;
@@ -247,18 +249,48 @@ __global__ void __launch_bounds__(128) traceback_kernel(ChunkGeom g, ChunkBuffer
     const uint8_t *ref = b.raw_refs + (size_t)slot * g.ref_length;
     uint8_t *oa = b.aln_read + (size_t)slot * L;
     uint8_t *ob = b.aln_ref + (size_t)slot * L;
-    int i = b.end_cell[2 * slot], j = b.end_cell[2 * slot + 1];
-    const int rows = b.meta[slot].rows, cols = b.meta[slot].cols;
+    const PairMeta meta = b.meta[slot];
+    const int rows = meta.rows, cols = meta.cols;
+    const int mode = NW ? MODE_NW_ALIGN : MODE_SW_ALIGN;
+    const bool packed = duo_is_fast(g, mode, slot & ~1, b.meta[slot & ~1], b.meta[slot | 1]);
+    const int duo = slot >> 1, lane_shift = (slot & 1) * 16;
+    int i, j;
+    if (packed && NW) {
+        // end-cell rule on the row the packed fill kernel left behind (values are H + gap_ref):
+        // first strictly greater column of matrix row `rows`, starting from column 0 = rows*gap_ref
+        int best = rows * gap_ref, idx = 0;
+        for (int c = 0; c < cols; ++c) {
+            const int h = (int)(int16_t)(b.hrow[(size_t)c * g.duos + duo] >> lane_shift) - gap_ref;
+            if (h > best) {
+                best = h;
+                idx = c;
+            }
+        }
+        i = rows - 1;
+        j = min((int)meta.max_ref_pos, idx);
+        b.end_cell[2 * slot] = (int16_t)i;
+        b.end_cell[2 * slot + 1] = (int16_t)j;
+        b.scores[slot] = (int16_t)best;
+    } else {
+        i = b.end_cell[2 * slot];
+        j = b.end_cell[2 * slot + 1];
+    }
     int pos = L - 2;
     if (L >= 1) {
         oa[L - 1] = 0;
         ob[L - 1] = 0;
     }
+    const uint2 *planes = b.fdirs;
     while (true) {
         int code;
         if (i < 0 || i >= rows || j >= cols) code = DIR_START;  // matrix row 0 (or nothing was filled)
         else if (j < 0) code = NW ? DIR_UP : DIR_START;     // matrix column 0 (DefaultKernel.cpp:304)
-        else code = (b.dirs[((size_t)(j >> 3) * g.rows_alloc + i) * g.slots + slot] >> (2 * (j & 7))) & 3;
+        else if (packed) {
+            const int strip = j / g.fast_tw, k = j - strip * g.fast_tw;
+            const uint2 w = planes[fast_dir_index(g, strip, i, k >> 4, duo)];
+            const int bit = lane_shift + (k & 15);
+            code = ((w.x >> bit) & 1) ? DIR_DIAG : (((w.y >> bit) & 1) ? DIR_UP : DIR_LEFT);
+        } else code = (b.dirs[((size_t)(j >> 3) * g.rows_alloc + i) * g.slots + slot] >> (2 * (j & 7))) & 3;
         if (code == DIR_START) break;
         uint8_t a = '-', c = '-';
         if (code != DIR_LEFT) a = read[i--];
@@ -340,11 +372,11 @@ int launch_fill_general(const ChunkGeom &g, const ChunkBuffers &b, int mode, int
     return 1;
 }
 
-int launch_traceback(const ChunkGeom &g, const ChunkBuffers &b, int mode, bool zero_prefix, cudaStream_t stream) {
+int launch_traceback(const ChunkGeom &g, const ChunkBuffers &b, int mode, bool zero_prefix, int gap_ref, cudaStream_t stream) {
     if (g.n <= 0) return 0;
     const int threads = 128, blocks = (g.n + threads - 1) / threads;
-    if (mode == MODE_NW_ALIGN) traceback_kernel<true><<<blocks, threads, 0, stream>>>(g, b, zero_prefix ? 1 : 0);
-    else traceback_kernel<false><<<blocks, threads, 0, stream>>>(g, b, zero_prefix ? 1 : 0);
+    if (mode == MODE_NW_ALIGN) traceback_kernel<true><<<blocks, threads, 0, stream>>>(g, b, zero_prefix ? 1 : 0, gap_ref);
+    else traceback_kernel<false><<<blocks, threads, 0, stream>>>(g, b, zero_prefix ? 1 : 0, gap_ref);
     return 1;
 }
 
