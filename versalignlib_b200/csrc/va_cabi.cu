@@ -213,7 +213,7 @@ struct PinBuf {
 
 // Device workspace of one chunk in flight.
 struct ChunkSlot {
-    DevBuf raw_reads, raw_refs, code_reads, code_refs, meta, boundary, dirs, hrow, scores, end_cell, aln_read, aln_ref, start;
+    DevBuf raw_reads, raw_refs, code_reads, code_refs, meta, boundary, dirs, hrow, queue, scores, end_cell, aln_read, aln_ref, start;
     PinBuf h_reads, h_refs, h_scores, h_end_cell, h_aln_read, h_aln_ref, h_start;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_done = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
@@ -223,7 +223,7 @@ struct ChunkSlot {
     bool busy = false;
 
     void release() {
-        DevBuf *d[] = {&raw_reads, &raw_refs, &code_reads, &code_refs, &meta, &boundary, &dirs, &hrow, &scores, &end_cell, &aln_read, &aln_ref, &start};
+        DevBuf *d[] = {&raw_reads, &raw_refs, &code_reads, &code_refs, &meta, &boundary, &dirs, &hrow, &queue, &scores, &end_cell, &aln_read, &aln_ref, &start};
         for (auto *b : d) b->release();
         PinBuf *h[] = {&h_reads, &h_refs, &h_scores, &h_end_cell, &h_aln_read, &h_aln_ref, &h_start};
         for (auto *b : h) b->release();
@@ -293,7 +293,11 @@ struct Shape {
     size_t dir_row_bytes() const { return gen_dir_row_bytes() + fast_dirs_bytes_per_row_per_slot(ref_length); }
     size_t per_pair_workspace() const {
         size_t b = (size_t)(read_chunks + ref_chunks) * 16 + sizeof(PairMeta) + (size_t)rows_alloc * 4;
-        if (align) b += dir_row_bytes() * rows_alloc + (size_t)ref_length * 2;
+        if (align) {
+            b += dir_row_bytes() * rows_alloc + (size_t)ref_length * 2;
+            const size_t qw = traceback_queue_words(read_length, ref_length);
+            if (qw * 128 * 4 > 48 * 1024) b += qw * 4;
+        }
         return b;
     }
     size_t per_pair_io() const {
@@ -360,6 +364,9 @@ int reserve_slot(ChunkSlot &s, const Shape &sh, int cap_pairs, bool pinned) {
     if (sh.align) {
         if ((rc = s.dirs.reserve(slots * sh.dir_row_bytes() * sh.rows_alloc + 512))) return rc;
         if ((rc = s.hrow.reserve(slots * (size_t)std::max(sh.ref_length, 1) * 2 + 64))) return rc;
+        // traceback move queue: shared memory unless the sequences are long
+        const size_t qw = traceback_queue_words(sh.read_length, sh.ref_length);
+        if (qw * 128 * 4 > 48 * 1024 && (rc = s.queue.reserve(slots * qw * 4 + 64))) return rc;
         if (pinned) {
             if ((rc = s.aln_read.reserve((size_t)cap_pairs * sh.L + 16))) return rc;
             if ((rc = s.aln_ref.reserve((size_t)cap_pairs * sh.L + 16))) return rc;
@@ -440,7 +447,13 @@ int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int
     launches += launch_fill_fast(g, b, mode, sc, stream);
     launches += launch_fill_general(g, b, mode, policy, sc, stream);
     if (pe) cudaEventRecord(pe[2], stream);
-    if (sh.align) launches += launch_traceback(g, b, mode, zero_prefix, sc.gap_ref, stream);
+    if (sh.align) {
+        if (zero_prefix) {  // bytes before start[i] are promised to be zero on this path
+            cudaMemsetAsync(aln_read, 0, (size_t)n * sh.L, stream);
+            cudaMemsetAsync(aln_ref, 0, (size_t)n * sh.L, stream);
+        }
+        launches += launch_traceback(g, b, mode, sc.gap_ref, (uint32_t *)ws.queue.p, stream);
+    }
     if (pe) cudaEventRecord(pe[3], stream);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return set_error(VA_ERR_DEVICE, "kernel launch failed: %s", cudaGetErrorString(err));
@@ -508,8 +521,16 @@ void scatter_chunk(va_cuda_ctx *ctx, const HostCall &c, ChunkSlot &s, int64_t fi
     if (c.end_cell) memcpy(c.end_cell + 2 * first, ec, (size_t)count * 2 * sizeof(int16_t));
     if (c.out_read_f) {
         ctx->pool->parallel_for(count, 2048, [&](int64_t b, int64_t e) {
-            memcpy(c.out_read_f + (first + b) * L, ha + b * L, (size_t)(e - b) * L);
-            memcpy(c.out_ref_f + (first + b) * L, hb + b * L, (size_t)(e - b) * L);
+            for (int64_t i = b; i < e; ++i) {
+                int s0 = st[i];
+                if (s0 < 0) s0 = 0;
+                if (s0 > L) s0 = L;
+                char *da = c.out_read_f + (first + i) * L, *db = c.out_ref_f + (first + i) * L;
+                memset(da, 0, (size_t)s0);
+                memset(db, 0, (size_t)s0);
+                memcpy(da + s0, ha + i * L + s0, (size_t)(L - s0));
+                memcpy(db + s0, hb + i * L + s0, (size_t)(L - s0));
+            }
         });
     } else {
         ctx->pool->parallel_for(count, 1024, [&](int64_t b, int64_t e) {
@@ -567,7 +588,7 @@ void run_shard(va_cuda_ctx *ctx, Engine &e, const HostCall &c, int64_t lo, int64
         cudaMemcpyAsync(s.raw_refs.p, s.h_refs.p, (size_t)count * FL, cudaMemcpyHostToDevice, s.stream);
         st.h2d += (int64_t)count * (RL + FL);
         cudaEventRecord(s.ev_k0, s.stream);
-        const bool zero_prefix = c.out_read_f != nullptr;
+        const bool zero_prefix = false;  // the host scatter zero-fills prefixes of the flat outputs itself
         int launches = enqueue_device_work(e, s, c.sh, c.mode, c.policy, c.sc, count, (const uint8_t *)s.raw_reads.p,
                                            (const uint8_t *)s.raw_refs.p, (int16_t *)s.scores.p, (int16_t *)s.end_cell.p,
                                            (uint8_t *)s.aln_read.p, (uint8_t *)s.aln_ref.p, (int16_t *)s.start.p,

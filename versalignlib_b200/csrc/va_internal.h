@@ -87,7 +87,9 @@ bool fast_scoring_ok(int mode, int policy, const Scoring &sc, int read_length, i
 int fast_pick_tw(int mode, int ref_length);
 size_t fast_dirs_bytes_per_row_per_slot(int ref_length);
 int launch_fill_fast(const ChunkGeom &g, const ChunkBuffers &b, int mode, const Scoring &sc, cudaStream_t stream);
-int launch_traceback(const ChunkGeom &g, const ChunkBuffers &b, int mode, bool zero_prefix, int gap_ref, cudaStream_t stream);
+size_t traceback_queue_words(int read_length, int ref_length);
+int launch_traceback(const ChunkGeom &g, const ChunkBuffers &b, int mode, int gap_ref, uint32_t *global_queue,
+                     cudaStream_t stream);
 int launch_int_peak(int kind, int sm_count, int iters, unsigned int *sink, cudaStream_t stream, double *lane_ops);
 
 }  // namespace va

@@ -8,8 +8,7 @@
 //   fill_general       score_alignment_* and calculate_alignment_matrix_* of every reference
 //                      kernel (DefaultKernel.cpp:83-389; SSEKernel.cpp:226-727,1007-1315;
 //                      scoring_kernels.cl, alignment_kernels.cl:38-135,239-364)
-//   traceback_kernel   the serial traceback + output write of calc_alignment_*
-//                      (DefaultKernel.cpp:391-525; SSEKernel.cpp:729-1005; alignment_kernels.cl:146-192,370-414)
+// (the traceback kernel is in va_traceback.cu)
 #include "va_internal.h"
 #include "va_device.cuh"
 #include "va_fast.cuh"
@@ -237,81 +236,6 @@ __global__ void __launch_bounds__(128) fill_general_kernel(ChunkGeom g, ChunkBuf
 }
 
 // ------------------------------------------------------------------------------------------
-// traceback: one thread per pair follows the 2-bit pointers and writes the gapped strings
-// ------------------------------------------------------------------------------------------
-
-template <bool NW>
-__global__ void __launch_bounds__(128) traceback_kernel(ChunkGeom g, ChunkBuffers b, int zero_prefix, int gap_ref) {
-    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= g.n) return;
-    const int L = g.read_length + g.ref_length;
-    const uint8_t *read = b.raw_reads + (size_t)slot * g.read_length;
-    const uint8_t *ref = b.raw_refs + (size_t)slot * g.ref_length;
-    uint8_t *oa = b.aln_read + (size_t)slot * L;
-    uint8_t *ob = b.aln_ref + (size_t)slot * L;
-    const PairMeta meta = b.meta[slot];
-    const int rows = meta.rows, cols = meta.cols;
-    const int mode = NW ? MODE_NW_ALIGN : MODE_SW_ALIGN;
-    const bool packed = duo_is_fast(g, mode, slot & ~1, b.meta[slot & ~1], b.meta[slot | 1]);
-    const int duo = slot >> 1, lane_shift = (slot & 1) * 16;
-    int i, j;
-    if (packed && NW) {
-        // end-cell rule on the row the packed fill kernel left behind (values are H + gap_ref):
-        // first strictly greater column of matrix row `rows`, starting from column 0 = rows*gap_ref
-        int best = rows * gap_ref, idx = 0;
-        for (int c = 0; c < cols; ++c) {
-            const int h = (int)(int16_t)(b.hrow[(size_t)c * g.duos + duo] >> lane_shift) - gap_ref;
-            if (h > best) {
-                best = h;
-                idx = c;
-            }
-        }
-        i = rows - 1;
-        j = min((int)meta.max_ref_pos, idx);
-        b.end_cell[2 * slot] = (int16_t)i;
-        b.end_cell[2 * slot + 1] = (int16_t)j;
-        b.scores[slot] = (int16_t)best;
-    } else {
-        i = b.end_cell[2 * slot];
-        j = b.end_cell[2 * slot + 1];
-    }
-    int pos = L - 2;
-    if (L >= 1) {
-        oa[L - 1] = 0;
-        ob[L - 1] = 0;
-    }
-    const uint2 *planes = b.fdirs;
-    while (true) {
-        int code;
-        if (i < 0 || i >= rows || j >= cols) code = DIR_START;  // matrix row 0 (or nothing was filled)
-        else if (j < 0) code = NW ? DIR_UP : DIR_START;     // matrix column 0 (DefaultKernel.cpp:304)
-        else if (packed) {
-            const int strip = j / g.fast_tw, k = j - strip * g.fast_tw;
-            const uint2 w = planes[fast_dir_index(g, strip, i, k >> 4, duo)];
-            const int bit = lane_shift + (k & 15);
-            code = ((w.x >> bit) & 1) ? DIR_DIAG : (((w.y >> bit) & 1) ? DIR_UP : DIR_LEFT);
-        } else code = (b.dirs[((size_t)(j >> 3) * g.rows_alloc + i) * g.slots + slot] >> (2 * (j & 7))) & 3;
-        if (code == DIR_START) break;
-        uint8_t a = '-', c = '-';
-        if (code != DIR_LEFT) a = read[i--];
-        if (code != DIR_UP) c = ref[j--];
-        if (pos >= 0) {
-            oa[pos] = a;
-            ob[pos] = c;
-        }
-        --pos;
-    }
-    const int start = pos + 1;
-    b.start[slot] = (int16_t)start;
-    if (zero_prefix) {
-        for (int k = 0; k < start && k < L; ++k) {
-            oa[k] = 0;
-            ob[k] = 0;
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
 // integer-pipe peak: dependent VIADDMNMX / VIMNMX3 chains, registers only
 // ------------------------------------------------------------------------------------------
 
@@ -369,14 +293,6 @@ int launch_fill_general(const ChunkGeom &g, const ChunkBuffers &b, int mode, int
         case MODE_SW_ALIGN: launch_fill_mode<MODE_SW_ALIGN>(g, b, policy, sc, stream); break;
         default: launch_fill_mode<MODE_NW_ALIGN>(g, b, policy, sc, stream); break;
     }
-    return 1;
-}
-
-int launch_traceback(const ChunkGeom &g, const ChunkBuffers &b, int mode, bool zero_prefix, int gap_ref, cudaStream_t stream) {
-    if (g.n <= 0) return 0;
-    const int threads = 128, blocks = (g.n + threads - 1) / threads;
-    if (mode == MODE_NW_ALIGN) traceback_kernel<true><<<blocks, threads, 0, stream>>>(g, b, zero_prefix ? 1 : 0, gap_ref);
-    else traceback_kernel<false><<<blocks, threads, 0, stream>>>(g, b, zero_prefix ? 1 : 0, gap_ref);
     return 1;
 }
 

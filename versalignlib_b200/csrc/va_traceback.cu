@@ -1,0 +1,212 @@
+// va_traceback.cu -- per-pair traceback over the 2-bit direction matrix and output of the two
+// gapped strings, right-aligned in read_length+ref_length byte blocks like the reference's
+// calc_alignment_* (DefaultKernel.cpp:391-525; SSEKernel.cpp:729-1005;
+// alignment_kernels.cl:146-192,370-414).
+//
+// One thread per pair, two phases, so that the only dependent chain through HBM is the walk:
+//   walk  follow the pointers from the end cell to START, one direction word per step (L2/HBM
+//         latency bound, hidden by occupancy); the moves go into a per-thread 2-bit queue in
+//         shared memory (global memory when the sequences are too long for that);
+//   emit  replay the queue: fetch the read/ref bytes it names and write both strings backwards,
+//         four characters per 32-bit store, so every output sector is written whole.
+// The packed fill kernel leaves NW's end-cell decision (arg-max of the last valid row,
+// DefaultKernel.cpp:352-355,381-387) to this kernel: `hrow` holds that row.
+#include "va_fast.cuh"
+
+namespace va {
+
+namespace {
+
+constexpr int TB_THREADS = 128;
+
+// 2-bit move queue of one thread: word w lives at q[w * stride]
+struct MoveQueue {
+    uint32_t *q;
+    size_t stride;
+};
+
+template <bool NW>
+__global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, ChunkBuffers b, int gap_ref, uint32_t *gq,
+                                                               int queue_words) {
+    extern __shared__ uint32_t sq[];
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= g.n) return;
+    MoveQueue mq;
+    if (gq) {
+        mq.q = gq + slot;
+        mq.stride = (size_t)g.slots;
+    } else {
+        mq.q = sq + threadIdx.x;
+        mq.stride = TB_THREADS;
+    }
+    (void)queue_words;
+    const int L = g.read_length + g.ref_length;
+    const PairMeta meta = b.meta[slot];
+    const int rows = meta.rows, cols = meta.cols;
+    const int mode = NW ? MODE_NW_ALIGN : MODE_SW_ALIGN;
+    const bool packed = duo_is_fast(g, mode, slot & ~1, b.meta[slot & ~1], b.meta[slot | 1]);
+    const int duo = slot >> 1, lane_shift = (slot & 1) * 16;
+
+    // ---- end cell ----------------------------------------------------------------------
+    int i, j;
+    if (packed && NW) {
+        // first strictly greater column of matrix row `rows`, starting from column 0 = rows*gap_ref;
+        // hrow holds H + gap_ref
+        int best = rows * gap_ref, idx = 0;
+        const uint32_t *hr = b.hrow + duo;
+        for (int c = 0; c < cols; ++c) {
+            const int h = (int)(int16_t)(hr[(size_t)c * g.duos] >> lane_shift) - gap_ref;
+            if (h > best) {
+                best = h;
+                idx = c;
+            }
+        }
+        i = rows - 1;
+        j = min((int)meta.max_ref_pos, idx);
+        b.end_cell[2 * slot] = (int16_t)i;
+        b.end_cell[2 * slot + 1] = (int16_t)j;
+        b.scores[slot] = (int16_t)best;
+    } else {
+        i = b.end_cell[2 * slot];
+        j = b.end_cell[2 * slot + 1];
+    }
+    const int end_i = i, end_j = j;
+
+    // ---- walk ----------------------------------------------------------------------------
+    int n_moves = 0;
+    uint32_t acc = 0;
+    if (packed) {
+        const int tw = g.fast_tw, ng = fast_groups(tw);
+        int strip = j >= 0 ? j / tw : 0, k = j >= 0 ? j - strip * tw : 0;
+        const size_t row_step = (size_t)ng * g.duos, strip_step = (size_t)g.rows_alloc * row_step;
+        const uint2 *p = b.fdirs + (size_t)strip * strip_step + (size_t)max(i, 0) * row_step + duo;
+        int have_row = -1, have_strip = -1, have_grp = -1;
+        uint2 w = make_uint2(0, 0);
+        while (true) {
+            int code;
+            if (i < 0 || i >= rows || j >= cols) code = DIR_START;
+            else if (j < 0) code = NW ? DIR_UP : DIR_START;  // matrix column 0 (DefaultKernel.cpp:304)
+            else {
+                const int grp = k >> 4;
+                if (i != have_row || strip != have_strip || grp != have_grp) {
+                    w = p[(size_t)grp * g.duos];
+                    have_row = i;
+                    have_strip = strip;
+                    have_grp = grp;
+                }
+                const int bit = lane_shift + (k & 15);
+                code = ((w.x >> bit) & 1) ? DIR_DIAG : (((w.y >> bit) & 1) ? DIR_UP : DIR_LEFT);
+            }
+            if (code == DIR_START) break;
+            acc |= (uint32_t)code << (2 * (n_moves & 15));
+            if ((++n_moves & 15) == 0) {
+                mq.q[(size_t)((n_moves >> 4) - 1) * mq.stride] = acc;
+                acc = 0;
+            }
+            if (code != DIR_LEFT) {
+                --i;
+                p -= row_step;
+            }
+            if (code != DIR_UP) {
+                --j;
+                if (--k < 0) {
+                    k += tw;
+                    --strip;
+                    p -= strip_step;
+                }
+            }
+        }
+    } else {
+        while (true) {
+            int code;
+            if (i < 0 || i >= rows || j >= cols) code = DIR_START;
+            else if (j < 0) code = NW ? DIR_UP : DIR_START;
+            else code = (b.dirs[((size_t)(j >> 3) * g.rows_alloc + i) * g.slots + slot] >> (2 * (j & 7))) & 3;
+            if (code == DIR_START) break;
+            acc |= (uint32_t)code << (2 * (n_moves & 15));
+            if ((++n_moves & 15) == 0) {
+                mq.q[(size_t)((n_moves >> 4) - 1) * mq.stride] = acc;
+                acc = 0;
+            }
+            if (code != DIR_LEFT) --i;
+            if (code != DIR_UP) --j;
+        }
+    }
+    if (n_moves & 15) mq.q[(size_t)(n_moves >> 4) * mq.stride] = acc;
+
+    // ---- emit ----------------------------------------------------------------------------
+    const uint8_t *read = b.raw_reads + (size_t)slot * g.read_length;
+    const uint8_t *ref = b.raw_refs + (size_t)slot * g.ref_length;
+    uint8_t *oa = b.aln_read + (size_t)slot * L;
+    uint8_t *ob = b.aln_ref + (size_t)slot * L;
+    const int start = L - 1 - n_moves;  // may be negative only when every move was a gap (never with gap scores < 0)
+    b.start[slot] = (int16_t)start;
+    if (L >= 1) {
+        oa[L - 1] = 0;
+        ob[L - 1] = 0;
+    }
+    i = end_i;
+    j = end_j;
+    int pos = L - 2;
+    int t = 0;
+    uint32_t word = n_moves ? mq.q[0] : 0;
+    auto next_move = [&]() -> int {
+        const int code = (word >> (2 * (t & 15))) & 3;
+        if ((++t & 15) == 0 && t < n_moves) word = mq.q[(size_t)(t >> 4) * mq.stride];
+        return code;
+    };
+    auto one_byte = [&]() {
+        const int code = next_move();
+        uint8_t a = '-', c = '-';
+        if (code != DIR_LEFT) a = read[i--];
+        if (code != DIR_UP) c = ref[j--];
+        if (pos >= 0) {
+            oa[pos] = a;
+            ob[pos] = c;
+        }
+        --pos;
+    };
+    // both output rows start at slot*L, so they share their alignment modulo 4
+    const uintptr_t base_mod = reinterpret_cast<uintptr_t>(oa) & 3, base_mod_b = reinterpret_cast<uintptr_t>(ob) & 3;
+    if (base_mod == base_mod_b) {
+        // bytes until the next byte to write is the top byte of an aligned word
+        while (t < n_moves && pos >= 0 && ((base_mod + pos) & 3) != 3) one_byte();
+        while (n_moves - t >= 4 && pos >= 3) {
+            uint32_t wa = 0, wb = 0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int code = next_move();
+                uint32_t a = '-', c = '-';
+                if (code != DIR_LEFT) a = read[i--];
+                if (code != DIR_UP) c = ref[j--];
+                wa |= a << (8 * (3 - r));
+                wb |= c << (8 * (3 - r));
+            }
+            *reinterpret_cast<uint32_t *>(oa + pos - 3) = wa;
+            *reinterpret_cast<uint32_t *>(ob + pos - 3) = wb;
+            pos -= 4;
+        }
+    }
+    while (t < n_moves) one_byte();
+}
+
+}  // namespace
+
+// Shared-memory move queue while it fits (<= 48 KB per block), else `global_queue`
+// (slots * queue_words words, provided by the caller).
+size_t traceback_queue_words(int read_length, int ref_length) { return (size_t)(read_length + ref_length + 15) / 16 + 1; }
+
+int launch_traceback(const ChunkGeom &g, const ChunkBuffers &b, int mode, int gap_ref, uint32_t *global_queue,
+                     cudaStream_t stream) {
+    if (g.n <= 0) return 0;
+    const int blocks = (g.n + TB_THREADS - 1) / TB_THREADS;
+    const int qw = (int)traceback_queue_words(g.read_length, g.ref_length);
+    const size_t smem = (size_t)qw * TB_THREADS * sizeof(uint32_t);
+    const bool use_shared = smem <= 48 * 1024;
+    uint32_t *gq = use_shared ? nullptr : global_queue;
+    if (mode == MODE_NW_ALIGN) traceback_kernel<true><<<blocks, TB_THREADS, use_shared ? smem : 0, stream>>>(g, b, gap_ref, gq, qw);
+    else traceback_kernel<false><<<blocks, TB_THREADS, use_shared ? smem : 0, stream>>>(g, b, gap_ref, gq, qw);
+    return 1;
+}
+
+}  // namespace va
