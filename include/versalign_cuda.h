@@ -123,6 +123,19 @@ int va_cuda_align_ptrs(va_cuda_ctx *ctx, int opt, int policy, const va_cuda_scor
                        const char *const *refs, int ref_length,
                        char *const *out_read, char *const *out_ref, int16_t *start, int16_t *end_cell);
 
+/* Same, but the result blocks are obtained from the caller's allocator while results stream
+ * back -- on the staging threads, overlapped with device work -- instead of being
+ * pre-allocated: out_read[i] = alloc(L, user), out_ref[i] = alloc(L, user).  This is what the
+ * plug-in class uses with alloc = new char[] (DefaultKernel.cpp:441-442).  alloc must be
+ * thread-safe; a NULL return aborts the call with VA_ERR_MEMORY (blocks handed out so far stay
+ * in out_read/out_ref, untouched entries are NULL). */
+typedef char *(*va_cuda_alloc_fn)(size_t bytes, void *user);
+int va_cuda_align_alloc(va_cuda_ctx *ctx, int opt, int policy, const va_cuda_scoring *sc, int n,
+                        const char *const *reads, int read_length,
+                        const char *const *refs, int ref_length,
+                        va_cuda_alloc_fn alloc, void *user,
+                        char **out_read, char **out_ref, int16_t *start, int16_t *end_cell);
+
 /* ---- host buffers, contiguous (fixed stride) ----------------------------------------- */
 
 /* Same as va_cuda_score_ptrs with reads = n*read_length contiguous bytes (the layout

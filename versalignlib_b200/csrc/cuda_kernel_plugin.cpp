@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -132,19 +133,14 @@ public:
         log_info("Running CUDAKernel align.");
         const int n = aln_number;
         if (n <= 0) return;
-        // Result blocks must be individually delete[]-able (Alignment::~Alignment), so they are
-        // plain array-new blocks; allocate them on several threads.
+        // Result blocks must be individually delete[]-able (Alignment::~Alignment), so each is a
+        // plain array-new block; the C ABI calls this allocator from its staging threads while
+        // results stream back from the device.
         std::vector<char *> out_read(n), out_ref(n);
         std::vector<short> start(n);
-        const size_t len = (size_t)(aln_length_ > 0 ? aln_length_ : 1);
-        parallel_blocks(n, threads, [&](int b, int e) {
-            for (int i = b; i < e; ++i) {
-                out_read[i] = new char[len];
-                out_ref[i] = new char[len];
-            }
-        });
-        int rc = va_cuda_align_ptrs(ctx_, opt, policy_, &scoring_, n, reads, read_length_, refs, ref_length_,
-                                    out_read.data(), out_ref.data(), start.data(), nullptr);
+        int rc = va_cuda_align_alloc(ctx_, opt, policy_, &scoring_, n, reads, read_length_, refs, ref_length_,
+                                     [](size_t bytes, void *) -> char * { return new (std::nothrow) char[bytes]; }, nullptr,
+                                     out_read.data(), out_ref.data(), start.data(), nullptr);
         if (rc != VA_OK) {
             for (int i = 0; i < n; ++i) {
                 delete[] out_read[i];
@@ -153,15 +149,17 @@ public:
             fatal(std::string("compute_alignments failed: ") + va_cuda_last_error());
         }
         const short end = (short)(aln_length_ - 1);
-        for (int i = 0; i < n; ++i) {
-            Alignment &a = alignments[i];
-            a.read = out_read[i];  // previous contents are neither freed nor reused (reference semantics)
-            a.ref = out_ref[i];
-            a.readStart = start[i];
-            a.refStart = start[i];
-            a.readEnd = end;
-            a.refEnd = end;
-        }
+        parallel_blocks(n, threads, [&](int b, int e) {
+            for (int i = b; i < e; ++i) {
+                Alignment &a = alignments[i];
+                a.read = out_read[i];  // previous contents are neither freed nor reused (reference semantics)
+                a.ref = out_ref[i];
+                a.readStart = start[i];
+                a.refStart = start[i];
+                a.readEnd = end;
+                a.refEnd = end;
+            }
+        });
     }
 
 private:
@@ -180,7 +178,7 @@ private:
 
     template <class F>
     static void parallel_blocks(int n, int threads, F fn) {
-        if (threads <= 1 || n < 4096) {
+        if (threads <= 1 || n < 65536) {
             fn(0, n);
             return;
         }

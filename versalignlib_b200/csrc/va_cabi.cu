@@ -190,13 +190,14 @@ struct DevBuf {
 struct PinBuf {
     void *p = nullptr;
     size_t cap = 0;
-    int reserve(size_t bytes) {
+    // write_combined: staging the CPU only ever writes (inputs on their way to the device)
+    int reserve(size_t bytes, bool write_combined = false) {
         if (bytes <= cap) return VA_OK;
         if (p) cudaFreeHost(p);
         p = nullptr;
         cap = 0;
         const size_t want = round_up(bytes + bytes / 8, 1 << 16);
-        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        cudaError_t e = cudaHostAlloc(&p, want, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault);
         if (e != cudaSuccess) {
             cudaGetLastError();
             return set_error(VA_ERR_MEMORY, "cudaHostAlloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
@@ -374,8 +375,9 @@ int reserve_slot(ChunkSlot &s, const Shape &sh, int cap_pairs, bool pinned) {
         }
     }
     if (pinned) {
-        if ((rc = s.h_reads.reserve((size_t)cap_pairs * sh.read_length + 16))) return rc;
-        if ((rc = s.h_refs.reserve((size_t)cap_pairs * sh.ref_length + 16))) return rc;
+        static const bool wc = [] { const char *v = getenv("VERSALIGN_CUDA_WC"); return v && atoi(v) != 0; }();
+        if ((rc = s.h_reads.reserve((size_t)cap_pairs * sh.read_length + 16, wc))) return rc;
+        if ((rc = s.h_refs.reserve((size_t)cap_pairs * sh.ref_length + 16, wc))) return rc;
         if ((rc = s.h_scores.reserve(slots * 2))) return rc;
         if ((rc = s.h_end_cell.reserve(slots * 4))) return rc;
         if (sh.align) {
@@ -475,6 +477,11 @@ struct HostCall {
     int16_t *scores = nullptr;
     char *const *out_read_p = nullptr;
     char *const *out_ref_p = nullptr;
+    va_cuda_alloc_fn alloc = nullptr;  // when set, out_*_w receive freshly allocated blocks
+    void *alloc_user = nullptr;
+    char **out_read_w = nullptr;
+    char **out_ref_w = nullptr;
+    std::atomic<int> *alloc_failed = nullptr;
     char *out_read_f = nullptr;
     char *out_ref_f = nullptr;
     int16_t *start = nullptr;
@@ -528,6 +535,24 @@ void scatter_chunk(va_cuda_ctx *ctx, const HostCall &c, ChunkSlot &s, int64_t fi
                 char *da = c.out_read_f + (first + i) * L, *db = c.out_ref_f + (first + i) * L;
                 memset(da, 0, (size_t)s0);
                 memset(db, 0, (size_t)s0);
+                memcpy(da + s0, ha + i * L + s0, (size_t)(L - s0));
+                memcpy(db + s0, hb + i * L + s0, (size_t)(L - s0));
+            }
+        });
+    } else if (c.alloc) {
+        ctx->pool->parallel_for(count, 1024, [&](int64_t b, int64_t e) {
+            for (int64_t i = b; i < e; ++i) {
+                int s0 = st[i];
+                if (s0 < 0) s0 = 0;
+                if (s0 > L) s0 = L;
+                char *da = c.alloc((size_t)(L > 0 ? L : 1), c.alloc_user);
+                char *db = c.alloc((size_t)(L > 0 ? L : 1), c.alloc_user);
+                c.out_read_w[first + i] = da;
+                c.out_ref_w[first + i] = db;
+                if (!da || !db) {
+                    c.alloc_failed->store(1);
+                    continue;
+                }
                 memcpy(da + s0, ha + i * L + s0, (size_t)(L - s0));
                 memcpy(db + s0, hb + i * L + s0, (size_t)(L - s0));
             }
@@ -823,6 +848,31 @@ int va_cuda_align_ptrs(va_cuda_ctx *ctx, int opt, int policy, const va_cuda_scor
     c.start = start;
     c.end_cell = end_cell;
     return run_host_call(ctx, c);
+}
+
+int va_cuda_align_alloc(va_cuda_ctx *ctx, int opt, int policy, const va_cuda_scoring *sc, int n, const char *const *reads,
+                        int read_length, const char *const *refs, int ref_length, va_cuda_alloc_fn alloc, void *user,
+                        char **out_read, char **out_ref, int16_t *start, int16_t *end_cell) {
+    HostCall c;
+    bool noop;
+    int rc = prepare_call(ctx, c, opt, true, policy, sc, n, read_length, ref_length, &noop);
+    if (rc || noop) return rc;
+    if (!alloc) return set_error(VA_ERR_ARG, "alloc is null");
+    if (n > 0 && (!reads || !refs || !out_read || !out_ref || !start)) return set_error(VA_ERR_ARG, "null buffer");
+    std::atomic<int> failed{0};
+    for (int i = 0; i < n; ++i) out_read[i] = out_ref[i] = nullptr;
+    c.reads_p = reads;
+    c.refs_p = refs;
+    c.alloc = alloc;
+    c.alloc_user = user;
+    c.out_read_w = out_read;
+    c.out_ref_w = out_ref;
+    c.alloc_failed = &failed;
+    c.start = start;
+    c.end_cell = end_cell;
+    rc = run_host_call(ctx, c);
+    if (rc == VA_OK && failed.load()) return set_error(VA_ERR_MEMORY, "the caller's allocator returned NULL");
+    return rc;
 }
 
 int va_cuda_align_flat(va_cuda_ctx *ctx, int opt, int policy, const va_cuda_scoring *sc, int n, const char *reads,
