@@ -30,7 +30,9 @@ constexpr uint32_t NEG2 = 0x80008000u;  // (-32768, -32768): identity of the pac
 
 __device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b) { return __viaddmax_s16x2(a, b, NEG2); }
 
-template <int MODE, int TW>
+// SYM: gap_read == gap_ref, so "H + gR" (what the cell to the right needs) and "H + gF" (what the
+// cell below needs) are the same register: one add less per cell in NW align.
+template <int MODE, int TW, bool SYM>
 __global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuffers b, FastConsts fc) {
     constexpr bool NWA = MODE == MODE_NW_ALIGN;
     constexpr bool SWS = MODE == MODE_SW_SCORE;
@@ -90,10 +92,28 @@ __global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuf
                 constexpr bool PARTIAL = decltype(partial_tag)::value;
                 uint32_t *bp = bnd + duo;
                 uint2 *dp = dirs + fast_dir_index(g, s, 0, 0, duo);
+                // Software pipeline of the per-row inputs so no row starts by waiting on memory: the
+                // read-code bytes are fetched two rows ahead, the row tables (shared-memory look-up by
+                // that code) and the boundary word one row ahead.
+                auto code_off = [&](int r) { return (uint32_t)(r >> 4) * chunk_stride + (uint32_t)(r & 15); };
+                const int mlast = m - 1;
+                uint32_t o1 = code_off(min(1, mlast));
+                uint32_t ca1 = ra[o1], cb1 = ra[o1 + 16];
+                uint32_t o0 = code_off(0);
+                uint32_t nta = T[ra[o0]], ntb = T[ra[o0 + 16]];
+                uint32_t nleft = first ? 0u : *bp;
+#pragma unroll 2
                 for (int i = 0; i < m; ++i, bp += g.duos, dp += (size_t)NG * g.duos) {
-                    const uint32_t roff = (uint32_t)(i >> 4) * chunk_stride + (uint32_t)(i & 15);
-                    const uint32_t ta = T[ra[roff]], tb = T[ra[roff + 16]];
-                    uint32_t left = first ? col0 : *bp;
+                    const uint32_t ta = nta, tb = ntb;
+                    uint32_t left = first ? col0 : nleft;
+                    {
+                        nta = T[ca1];  // tables of row i+1
+                        ntb = T[cb1];
+                        const uint32_t o2 = code_off(min(i + 2, mlast));
+                        ca1 = ra[o2];  // codes of row i+2
+                        cb1 = ra[o2 + 16];
+                        if (!first) nleft = bp[i < mlast ? g.duos : 0];  // boundary of row i+1
+                    }
                     if (NWA && first) col0 = add2(col0, gF2);
                     uint32_t diag = diag_next;
                     diag_next = add2(left, dFR2);
@@ -115,7 +135,7 @@ __global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuf
                             if (ul) p2l[k >> 4] += bit;
                             if (uh) p2h[k >> 4] += bit;
                             left = add2(h, gR2);
-                            H[k] = add2(h, gF2);
+                            H[k] = SYM ? left : add2(h, gF2);
                         } else {
                             const uint32_t t = __viaddmax_s16x2(up, gF2, left);
                             const uint32_t h = SWS ? __viaddmax_s16x2_relu(diag, sub, t) : __viaddmax_s16x2(diag, sub, t);
@@ -174,7 +194,8 @@ void launch_one(const ChunkGeom &g, const ChunkBuffers &b, const FastConsts &fc,
     const int threads = 128;
     const int duos = (g.n + 1) / 2;
     const int blocks = (duos + threads - 1) / threads;
-    fill_fast_kernel<MODE, TW><<<blocks, threads, 0, stream>>>(g, b, fc);
+    if (MODE == MODE_NW_ALIGN && fc.gF == fc.gR) fill_fast_kernel<MODE, TW, true><<<blocks, threads, 0, stream>>>(g, b, fc);
+    else fill_fast_kernel<MODE, TW, false><<<blocks, threads, 0, stream>>>(g, b, fc);
 }
 
 template <int MODE>
