@@ -110,6 +110,23 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def tune_host_malloc() -> str:
+    """Host-application side: keep freed heap pages inside glibc's arenas between calls.  Every
+    kernel behind this boundary (the reference's too) returns 2 heap blocks per pair, and the
+    caller frees them after each call; with the default trim threshold each call then re-faults
+    hundreds of MB.  Applied to BOTH arms (ours and --impl reference)."""
+    import ctypes
+    try:
+        libc = ctypes.CDLL("libc.so.6")
+        M_TRIM_THRESHOLD, M_TOP_PAD, M_MMAP_THRESHOLD = -1, -2, -3
+        libc.mallopt(M_TRIM_THRESHOLD, 1 << 30)
+        libc.mallopt(M_TOP_PAD, 64 << 20)
+        libc.mallopt(M_MMAP_THRESHOLD, 1 << 30)
+        return "mallopt(M_TRIM_THRESHOLD=1GiB, M_TOP_PAD=64MiB, M_MMAP_THRESHOLD=1GiB)"
+    except Exception as e:  # pragma: no cover
+        return f"default ({e})"
+
+
 def measured_peaks() -> dict:
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -159,7 +176,8 @@ def run_reference(args):
         "impl": "reference", "metric": "GCUPS", "value": cb["value"], "unit": "GCUPS", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU reference arm: bounded sample, rank 0 only"},
+        "config": {"workload": WORKLOAD, "note": "CPU reference arm: bounded sample, rank 0 only",
+                   "host_malloc": args.host_malloc},
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -310,7 +328,7 @@ def run_ours(args):
                        "l2": "inputs + direction matrix (5.9 GB/step) exceed the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e_value, "unit": "GCUPS", "ms_per_step": e2e_sec * 1e3,
                     "h2d_bytes_per_step": n * (READ_LEN + REF_LEN), "d2h_bytes_per_step": int(pt.get("d2h_bytes", n * (2 * L + 6))),
-                    "host_threads": host_threads, "phases": pt,
+                    "host_threads": host_threads, "host_malloc": args.host_malloc, "phases": pt,
                     "api": "dlopen(libCUDAKernel.so) -> spawn_alignment_kernel -> AlignmentKernel::compute_alignments, scattered char* in, new char[] out"},
             "gpu_launches": int(launches_per_step) * args.steps,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
@@ -329,7 +347,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_GPU, help="pairs per GPU (default: the C2 workload, 1M)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--tune-malloc", action="store_true", help="host side: keep freed pages in glibc's arenas (mallopt)")
     args = ap.parse_args()
+    args.host_malloc = tune_host_malloc() if args.tune_malloc else "default"
     if args.impl == "reference":
         run_reference(args)
     else:

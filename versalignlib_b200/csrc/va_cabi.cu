@@ -295,7 +295,7 @@ struct Shape {
     size_t per_pair_workspace() const {
         size_t b = (size_t)(read_chunks + ref_chunks) * 16 + sizeof(PairMeta) + (size_t)rows_alloc * 4;
         if (align) {
-            b += dir_row_bytes() * rows_alloc + (size_t)ref_length * 2;
+            b += dir_row_bytes() * (rows_alloc + 1) + (size_t)ref_length * 2;
             const size_t qw = traceback_queue_words(read_length, ref_length);
             if (qw * 128 * 4 > 48 * 1024) b += qw * 4;
         }
@@ -363,7 +363,7 @@ int reserve_slot(ChunkSlot &s, const Shape &sh, int cap_pairs, bool pinned) {
     if ((rc = s.scores.reserve(slots * 2))) return rc;
     if ((rc = s.end_cell.reserve(slots * 4))) return rc;
     if (sh.align) {
-        if ((rc = s.dirs.reserve(slots * sh.dir_row_bytes() * sh.rows_alloc + 512))) return rc;
+        if ((rc = s.dirs.reserve(slots * sh.dir_row_bytes() * (sh.rows_alloc + 1) + 512))) return rc;
         if ((rc = s.hrow.reserve(slots * (size_t)std::max(sh.ref_length, 1) * 2 + 64))) return rc;
         // traceback move queue: shared memory unless the sequences are long
         const size_t qw = traceback_queue_words(sh.read_length, sh.ref_length);
@@ -422,7 +422,7 @@ int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int
     b.meta = (PairMeta *)ws.meta.p;
     b.boundary = (int32_t *)ws.boundary.p;
     b.dirs = (uint16_t *)ws.dirs.p;
-    b.fdirs = (uint2 *)((char *)ws.dirs.p + round_up((size_t)g.slots * sh.gen_dir_row_bytes() * sh.rows_alloc, 256));
+    b.fdirs = (uint4 *)((char *)ws.dirs.p + round_up((size_t)g.slots * sh.gen_dir_row_bytes() * sh.rows_alloc, 256));
     b.hrow = (uint32_t *)ws.hrow.p;
     b.scores = scores;
     b.end_cell = end_cell;

@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuf
         const uint8_t *cread = reinterpret_cast<const uint8_t *>(b.code_reads);
         const uint8_t *cref = reinterpret_cast<const uint8_t *>(b.code_refs);
         uint32_t *bnd = reinterpret_cast<uint32_t *>(b.boundary);
-        uint2 *dirs = b.fdirs;
+        uint4 *dirs = b.fdirs;
 
         uint32_t best = 0;  // SW: running max; NW score: max(0, last column, last row)
         const int nstrips = (n + TW - 1) / TW;
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuf
             auto sweep = [&](auto partial_tag) {
                 constexpr bool PARTIAL = decltype(partial_tag)::value;
                 uint32_t *bp = bnd + duo;
-                uint2 *dp = dirs + fast_dir_index(g, s, 0, 0, duo);
+                uint4 *dp = dirs + fast_dir_index(g, s, 0, 0, duo);
                 // Software pipeline of the per-row inputs so no row starts by waiting on memory: the
                 // read-code bytes are fetched two rows ahead, the row tables (shared-memory look-up by
                 // that code) and the boundary word one row ahead.
@@ -102,8 +102,8 @@ __global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuf
                 uint32_t o0 = code_off(0);
                 uint32_t nta = T[ra[o0]], ntb = T[ra[o0 + 16]];
                 uint32_t nleft = first ? 0u : *bp;
-#pragma unroll 2
-                for (int i = 0; i < m; ++i, bp += g.duos, dp += (size_t)NG * g.duos) {
+                // one matrix row of this strip; NW align returns the row's two direction planes per group
+                auto do_row = [&](int i, uint2(&w)[NG]) {
                     const uint32_t ta = nta, tb = ntb;
                     uint32_t left = first ? col0 : nleft;
                     {
@@ -155,15 +155,33 @@ __global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuf
                         diag = up;
                     }
                     if (!last) *bp = left;
+                    bp += g.duos;
                     if (NWS && !PARTIAL && last) best = __vmaxs2(best, H[TW - 1]);  // last column (SSEKernel.cpp:1285-1291)
                     if (NWA) {
 #pragma unroll
                         for (int q = 0; q < NG; ++q) {
-                            uint2 w;
-                            w.x = __byte_perm(__float_as_uint(p1l[q]), __float_as_uint(p1h[q]), 0x5410);
-                            w.y = __byte_perm(__float_as_uint(p2l[q]), __float_as_uint(p2h[q]), 0x5410);
-                            dp[(size_t)q * g.duos] = w;
+                            w[q].x = __byte_perm(__float_as_uint(p1l[q]), __float_as_uint(p1h[q]), 0x5410);
+                            w[q].y = __byte_perm(__float_as_uint(p2l[q]), __float_as_uint(p2h[q]), 0x5410);
                         }
+                    }
+                };
+                // two rows per iteration: their direction words leave as one 16-byte store per group
+                int i = 0;
+                for (; i + 1 < m; i += 2, dp += (size_t)NG * g.duos) {
+                    uint2 w0[NG], w1[NG];
+                    do_row(i, w0);
+                    do_row(i + 1, w1);
+                    if (NWA) {
+#pragma unroll
+                        for (int q = 0; q < NG; ++q) dp[(size_t)q * g.duos] = make_uint4(w0[q].x, w0[q].y, w1[q].x, w1[q].y);
+                    }
+                }
+                if (i < m) {
+                    uint2 w0[NG];
+                    do_row(i, w0);
+                    if (NWA) {
+#pragma unroll
+                        for (int q = 0; q < NG; ++q) dp[(size_t)q * g.duos] = make_uint4(w0[q].x, w0[q].y, 0u, 0u);
                     }
                 }
             };
@@ -239,7 +257,8 @@ int fast_pick_tw(int mode, int ref_length) {
 }
 
 size_t fast_dirs_bytes_per_row_per_slot(int ref_length) {
-    // per row and duo: strips * groups * 8 bytes; both strip widths use 2 groups
+    // per row and duo: strips * groups * 8 bytes; both strip widths use 2 groups.  (Rows are stored
+    // in pairs; the caller rounds the row count up to even.)
     const size_t s32 = (size_t)(ref_length + 31) / 32, s30 = (size_t)(ref_length + 29) / 30;
     return (s32 > s30 ? s32 : s30) * 2 * 8 / 2;
 }

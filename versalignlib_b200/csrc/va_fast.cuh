@@ -26,9 +26,16 @@ __device__ __forceinline__ bool duo_is_fast(const ChunkGeom &g, int mode, int sl
 
 __device__ __forceinline__ int fast_groups(int tw) { return (tw + 15) >> 4; }
 
-// index (in uint2 units) of the direction words of (strip, row, group) for duo u
+// Direction words of the packed kernel: one uint4 per (strip, ROW PAIR, group of 16 columns, duo)
+//   .x/.y = DIAG plane / UP plane of the even row, .z/.w = the same for the odd row;
+//   in each 32-bit plane the low half belongs to lane A (slot 2u), the high half to lane B.
+// Two rows per word keep the fill kernel's stores 16 bytes wide and fully coalesced and halve
+// the number of dependent loads of the traceback walk.
+__device__ __forceinline__ int fast_row_pairs(const ChunkGeom &g) { return (g.rows_alloc + 1) >> 1; }
+
+// index (in uint4 units) of the word holding `row`
 __device__ __forceinline__ size_t fast_dir_index(const ChunkGeom &g, int strip, int row, int group, int duo) {
-    return (((size_t)strip * g.rows_alloc + row) * fast_groups(g.fast_tw) + group) * g.duos + duo;
+    return (((size_t)strip * fast_row_pairs(g) + (row >> 1)) * fast_groups(g.fast_tw) + group) * g.duos + duo;
 }
 
 }  // namespace va

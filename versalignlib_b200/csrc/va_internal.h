@@ -66,7 +66,7 @@ struct ChunkBuffers {
     PairMeta *meta;            // [slots]
     int32_t *boundary;         // [rows_alloc][slots]   right edge of the previous column strip
     uint16_t *dirs;            // general kernel: [segs][rows_alloc][slots] half-words, 2 bits per cell, 8 cells each
-    uint2 *fdirs;              // packed kernel:  [strip][rows_alloc][group][duos] (DIAG plane, UP plane), 16 cells each
+    uint4 *fdirs;              // packed kernel:  [strip][row pair][group][duos], see va_fast.cuh
                                // (separate regions: one chunk can hold pairs of both kinds)
     uint32_t *hrow;            // packed NW align: [ref_length][duos] last valid row of the matrix (H + gap_ref)
     int16_t *scores;           // [n]

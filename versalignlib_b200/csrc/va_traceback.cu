@@ -78,24 +78,25 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
     if (packed) {
         const int tw = g.fast_tw, ng = fast_groups(tw);
         int strip = j >= 0 ? j / tw : 0, k = j >= 0 ? j - strip * tw : 0;
-        const size_t row_step = (size_t)ng * g.duos, strip_step = (size_t)g.rows_alloc * row_step;
-        const uint2 *p = b.fdirs + (size_t)strip * strip_step + (size_t)max(i, 0) * row_step + duo;
-        int have_row = -1, have_strip = -1, have_grp = -1;
-        uint2 w = make_uint2(0, 0);
+        const size_t pair_step = (size_t)ng * g.duos, strip_step = (size_t)fast_row_pairs(g) * pair_step;
+        const uint4 *p = b.fdirs + (size_t)strip * strip_step + (size_t)(max(i, 0) >> 1) * pair_step + duo;
+        int have_pair = -1, have_strip = -1, have_grp = -1;
+        uint4 w = make_uint4(0, 0, 0, 0);
         while (true) {
             int code;
             if (i < 0 || i >= rows || j >= cols) code = DIR_START;
             else if (j < 0) code = NW ? DIR_UP : DIR_START;  // matrix column 0 (DefaultKernel.cpp:304)
             else {
                 const int grp = k >> 4;
-                if (i != have_row || strip != have_strip || grp != have_grp) {
-                    w = p[(size_t)grp * g.duos];
-                    have_row = i;
+                if ((i >> 1) != have_pair || strip != have_strip || grp != have_grp) {
+                    w = p[(size_t)grp * g.duos];  // two rows x 16 columns x both lanes
+                    have_pair = i >> 1;
                     have_strip = strip;
                     have_grp = grp;
                 }
                 const int bit = lane_shift + (k & 15);
-                code = ((w.x >> bit) & 1) ? DIR_DIAG : (((w.y >> bit) & 1) ? DIR_UP : DIR_LEFT);
+                const uint32_t diag_plane = (i & 1) ? w.z : w.x, up_plane = (i & 1) ? w.w : w.y;
+                code = ((diag_plane >> bit) & 1) ? DIR_DIAG : (((up_plane >> bit) & 1) ? DIR_UP : DIR_LEFT);
             }
             if (code == DIR_START) break;
             acc |= (uint32_t)code << (2 * (n_moves & 15));
@@ -104,8 +105,8 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
                 acc = 0;
             }
             if (code != DIR_LEFT) {
+                if ((i & 1) == 0) p -= pair_step;  // leaving an even row: the row above is in the previous word
                 --i;
-                p -= row_step;
             }
             if (code != DIR_UP) {
                 --j;
