@@ -196,3 +196,21 @@ def test_wide_scores_fall_back_to_general_kernel(ctx):
         a, b, start, end = ctx.align_flat(ora.NW, 0, reads, refs, sc)
         oa, ob, ostart, oend = ora.align(ora.NW, 0, reads, refs, sc)
         assert np.array_equal(a, oa) and np.array_equal(b, ob) and np.array_equal(start, ostart)
+
+
+def test_c5_adversarial_parameter_grid(ctx):
+    """BASELINE config 5: high-mismatch random pairs over the whole scoring grid, asymmetric gaps
+    included -- scores and alignments (both pointer policies) bit-exact against the oracle."""
+    decks = [synth.uniform_batch(192, 64, 96, independent=True, seed=synth.BASE_SEED + 5),
+             synth.uniform_batch(128, 150, 150, p_sub=0.5, seed=synth.BASE_SEED + 55)]
+    combos = [(m, x, gr, gf) for m in (1, 2, 5) for x in (0, -1, -4) for gr in (-1, -3, -7) for gf in (-1, -3, -7)]
+    assert len(combos) == 81
+    for reads, refs in decks:
+        for ci, sc in enumerate(combos):
+            for opt in (ora.SW, ora.NW):
+                assert np.array_equal(ctx.score_flat(opt, reads, refs, sc), ora.score(opt, reads, refs, sc)), (sc, opt)
+                pol = ci & 1  # alternate policies over the grid; both are covered for every gap pair
+                a, b, start, end = ctx.align_flat(opt, pol, reads, refs, sc)
+                oa, ob, ostart, oend = ora.align(opt, pol, reads, refs, sc)
+                assert np.array_equal(start, ostart) and np.array_equal(end, oend), (sc, opt, pol)
+                assert np.array_equal(a, oa) and np.array_equal(b, ob), (sc, opt, pol)

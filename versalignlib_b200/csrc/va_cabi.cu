@@ -214,7 +214,7 @@ struct PinBuf {
 
 // Device workspace of one chunk in flight.
 struct ChunkSlot {
-    DevBuf raw_reads, raw_refs, code_reads, code_refs, meta, boundary, dirs, hrow, queue, scores, end_cell, aln_read, aln_ref, start;
+    DevBuf raw_reads, raw_refs, code_reads, code_refs, meta, pair_of, prep_scratch, boundary, dirs, hrow, queue, scores, end_cell, aln_read, aln_ref, start;
     PinBuf h_reads, h_refs, h_scores, h_end_cell, h_aln_read, h_aln_ref, h_start;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_done = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
@@ -224,7 +224,7 @@ struct ChunkSlot {
     bool busy = false;
 
     void release() {
-        DevBuf *d[] = {&raw_reads, &raw_refs, &code_reads, &code_refs, &meta, &boundary, &dirs, &hrow, &queue, &scores, &end_cell, &aln_read, &aln_ref, &start};
+        DevBuf *d[] = {&raw_reads, &raw_refs, &code_reads, &code_refs, &meta, &pair_of, &prep_scratch, &boundary, &dirs, &hrow, &queue, &scores, &end_cell, &aln_read, &aln_ref, &start};
         for (auto *b : d) b->release();
         PinBuf *h[] = {&h_reads, &h_refs, &h_scores, &h_end_cell, &h_aln_read, &h_aln_ref, &h_start};
         for (auto *b : h) b->release();
@@ -293,7 +293,7 @@ struct Shape {
     size_t gen_dir_row_bytes() const { return (size_t)segs * 2; }
     size_t dir_row_bytes() const { return gen_dir_row_bytes() + fast_dirs_bytes_per_row_per_slot(ref_length); }
     size_t per_pair_workspace() const {
-        size_t b = (size_t)(read_chunks + ref_chunks) * 16 + sizeof(PairMeta) + (size_t)rows_alloc * 4;
+        size_t b = (size_t)(read_chunks + ref_chunks) * 32 + 2 * sizeof(PairMeta) + 40 + (size_t)rows_alloc * 4;
         if (align) {
             b += dir_row_bytes() * (rows_alloc + 1) + (size_t)ref_length * 2;
             const size_t qw = traceback_queue_words(read_length, ref_length);
@@ -359,6 +359,8 @@ int reserve_slot(ChunkSlot &s, const Shape &sh, int cap_pairs, bool pinned) {
     if ((rc = s.code_reads.reserve(slots * sh.read_chunks * 16 + 16))) return rc;
     if ((rc = s.code_refs.reserve(slots * sh.ref_chunks * 16 + 16))) return rc;
     if ((rc = s.meta.reserve(slots * sizeof(PairMeta)))) return rc;
+    if ((rc = s.pair_of.reserve(slots * 4))) return rc;
+    if ((rc = s.prep_scratch.reserve(prep_scratch_bytes((int)slots, sh.read_length, sh.ref_length)))) return rc;
     if ((rc = s.boundary.reserve(slots * sh.rows_alloc * 4))) return rc;
     if ((rc = s.scores.reserve(slots * 2))) return rc;
     if ((rc = s.end_cell.reserve(slots * 4))) return rc;
@@ -420,6 +422,7 @@ int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int
     b.code_reads = (uint4 *)ws.code_reads.p;
     b.code_refs = (uint4 *)ws.code_refs.p;
     b.meta = (PairMeta *)ws.meta.p;
+    b.pair_of = (int32_t *)ws.pair_of.p;
     b.boundary = (int32_t *)ws.boundary.p;
     b.dirs = (uint16_t *)ws.dirs.p;
     b.fdirs = (uint4 *)((char *)ws.dirs.p + round_up((size_t)g.slots * sh.gen_dir_row_bytes() * sh.rows_alloc, 256));
@@ -444,7 +447,7 @@ int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int
         e.prof_used += 4;
         cudaEventRecord(pe[0], stream);
     }
-    launches += launch_prep(g, b, mode, policy, sc, stream);
+    launches += launch_prep(g, b, mode, policy, sc, ws.prep_scratch.p, ws.prep_scratch.cap, stream);
     if (pe) cudaEventRecord(pe[1], stream);
     launches += launch_fill_fast(g, b, mode, sc, stream);
     launches += launch_fill_general(g, b, mode, policy, sc, stream);

@@ -199,8 +199,8 @@ __global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuf
             }
         }
         if (!NWA) {
-            b.scores[slot_a] = (int16_t)(best & 0xFFFF);
-            b.scores[slot_b] = (int16_t)(best >> 16);
+            b.scores[b.pair_of[slot_a]] = (int16_t)(best & 0xFFFF);
+            b.scores[b.pair_of[slot_b]] = (int16_t)(best >> 16);
         }
     }
     for (int o = 16; o > 0; o >>= 1) cells += __shfl_xor_sync(0xffffffffu, cells, o);

@@ -64,6 +64,7 @@ struct ChunkBuffers {
     uint4 *code_reads;         // [read_chunks][slots]
     uint4 *code_refs;          // [ref_chunks][slots]
     PairMeta *meta;            // [slots]
+    int32_t *pair_of;          // [slots] pair (position in the caller's batch) computed in this slot, -1 = padding
     int32_t *boundary;         // [rows_alloc][slots]   right edge of the previous column strip
     uint16_t *dirs;            // general kernel: [segs][rows_alloc][slots] half-words, 2 bits per cell, 8 cells each
     uint4 *fdirs;              // packed kernel:  [strip][row pair][group][duos], see va_fast.cuh
@@ -79,7 +80,10 @@ struct ChunkBuffers {
 };
 
 // Launchers (va_kernels.cu).  All asynchronous on `stream`; return the number of kernels launched.
-int launch_prep(const ChunkGeom &g, const ChunkBuffers &b, int mode, int policy, const Scoring &sc, cudaStream_t stream);
+// staging (va_prep.cu)
+size_t prep_scratch_bytes(int slots, int read_length, int ref_length);
+int launch_prep(const ChunkGeom &g, const ChunkBuffers &b, int mode, int policy, const Scoring &sc, void *scratch,
+                size_t scratch_bytes, cudaStream_t stream);
 int launch_fill_general(const ChunkGeom &g, const ChunkBuffers &b, int mode, int policy, const Scoring &sc,
                         cudaStream_t stream);
 // packed kernels (va_fast.cu)

@@ -2,9 +2,7 @@
 // launchers.  The packed 16-bit fast path lives in va_fast.cuh and is launched from here too.
 //
 // What each kernel stands in for in the reference:
-//   prep_kernel        the per-cell char_to_score[] look-ups (DefaultKernel.h:43-60) and the
-//                      first-invalid-character scans (DefaultKernel.cpp:308-310,348-350;
-//                      SSEKernel.cpp:514-518,673-677), hoisted out of the DP loop
+// (staging kernels: va_prep.cu)
 //   fill_general       score_alignment_* and calculate_alignment_matrix_* of every reference
 //                      kernel (DefaultKernel.cpp:83-389; SSEKernel.cpp:226-727,1007-1315;
 //                      scoring_kernels.cl, alignment_kernels.cl:38-135,239-364)
@@ -14,100 +12,6 @@
 #include "va_fast.cuh"
 
 namespace va {
-
-// ------------------------------------------------------------------------------------------
-// prep: raw bytes -> base codes (slot-interleaved uint4 chunks) + per-pair extents
-// ------------------------------------------------------------------------------------------
-
-__device__ __forceinline__ int base_code(unsigned c) {
-    c &= 0xDFu;  // fold case; bytes >= 0x80 keep bit 7 and fall through to OTHER
-    return c == 'A' ? CODE_A : c == 'C' ? CODE_C : c == 'G' ? CODE_G : c == 'T' ? CODE_T : c == 'N' ? CODE_N : CODE_OTHER;
-}
-
-struct SeqScan {
-    int last_acgt;     // index of the last ACGT base, -1 if none
-    int first_other;   // first byte that is neither ACGT nor N (Default/OpenCL "invalid"), L if none
-    int first_nonacgt; // first byte that is not ACGT (SSE/AVX "invalid"), L if none
-    int n_acgt;
-};
-
-// One thread walks one sequence.  16 bases per uint4, written to [chunk][slot].
-__device__ __forceinline__ SeqScan encode_sequence(const uint8_t *__restrict__ raw, int L, int chunks, uint4 *__restrict__ out,
-                                                   int slots, int slot, bool live) {
-    SeqScan s;
-    s.last_acgt = -1;
-    s.first_other = L;
-    s.first_nonacgt = L;
-    s.n_acgt = 0;
-    for (int c = 0; c < chunks; ++c) {
-        uint32_t w[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            uint32_t word = 0;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int pos = c * 16 + q * 4 + b;
-                int code = CODE_OTHER;
-                if (live && pos < L) {
-                    code = base_code(raw[pos]);
-                    if (code < 4) {
-                        s.last_acgt = pos;
-                        s.n_acgt++;
-                    } else {
-                        if (pos < s.first_nonacgt) s.first_nonacgt = pos;
-                        if (code == CODE_OTHER && pos < s.first_other) s.first_other = pos;
-                    }
-                }
-                word |= (uint32_t)code << (8 * b);
-            }
-            w[q] = word;
-        }
-        out[(size_t)c * slots + slot] = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-    return s;
-}
-
-__global__ void __launch_bounds__(128) prep_kernel(ChunkGeom g, ChunkBuffers b, int mode, int policy, int trim) {
-    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= g.slots) return;
-    const bool live = slot < g.n;
-    SeqScan rd = encode_sequence(b.raw_reads + (size_t)slot * g.read_length, g.read_length, g.read_chunks, b.code_reads,
-                                 g.slots, slot, live);
-    SeqScan rf = encode_sequence(b.raw_refs + (size_t)slot * g.ref_length, g.ref_length, g.ref_chunks, b.code_refs,
-                                 g.slots, slot, live);
-    PairMeta m;
-    m.true_rows = (int16_t)(rd.last_acgt + 1);
-    m.true_cols = (int16_t)(rf.last_acgt + 1);
-    m.flags = (int16_t)((rd.n_acgt != rd.last_acgt + 1 ? 1 : 0) | (rf.n_acgt != rf.last_acgt + 1 ? 2 : 0));
-    const int inv_r = policy == 1 ? rd.first_nonacgt : rd.first_other;
-    const int inv_f = policy == 1 ? rf.first_nonacgt : rf.first_other;
-    m.max_read_pos = (int16_t)(inv_r - 1);
-    m.max_ref_pos = (int16_t)(inv_f - 1);
-    m.pad = 0;
-    if (!live) {
-        m.rows = m.cols = 0;
-    } else if (mode == MODE_NW_ALIGN) {
-        // rows below the first invalid read character are never consulted; the end-cell rule
-        // scans the whole padded width of the last valid row
-        m.rows = (int16_t)(m.max_read_pos + 1);
-        m.cols = (int16_t)g.ref_length;
-    } else if (trim) {
-        // trailing rows/columns that can only score 0 never change the result while both gap
-        // scores are <= 0 (SURVEY.md A.1/A.2 "padding is neutral")
-        m.rows = m.true_rows;
-        m.cols = m.true_cols;
-        if (mode == MODE_SW_ALIGN) {
-            // with a zero score traceback starts at cell (0,0) (DefaultKernel.cpp:207-208), so that
-            // cell's pointer must exist even when a sequence holds no ACGT base at all
-            m.rows = (int16_t)max((int)m.rows, min(1, g.read_length));
-            m.cols = (int16_t)max((int)m.cols, min(1, g.ref_length));
-        }
-    } else {
-        m.rows = (int16_t)g.read_length;
-        m.cols = (int16_t)g.ref_length;
-    }
-    b.meta[slot] = m;
-}
 
 // ------------------------------------------------------------------------------------------
 // general fill: one thread per pair, 32-bit lanes, 16-column register strip
@@ -215,19 +119,20 @@ __global__ void __launch_bounds__(128) fill_general_kernel(ChunkGeom g, ChunkBuf
                 }
             }
         }
+        const int pair = b.pair_of[slot];  // results go back in the caller's pair order
         if (MODE == MODE_SW_SCORE) {
-            b.scores[slot] = (int16_t)best;
+            b.scores[pair] = (int16_t)best;
         } else if (MODE == MODE_NW_SCORE) {
-            b.scores[slot] = (int16_t)border;
+            b.scores[pair] = (int16_t)border;
         } else if (MODE == MODE_SW_ALIGN) {
-            b.end_cell[2 * slot] = (int16_t)best_i;
-            b.end_cell[2 * slot + 1] = (int16_t)best_j;
-            b.scores[slot] = (int16_t)best;
+            b.end_cell[2 * pair] = (int16_t)best_i;
+            b.end_cell[2 * pair + 1] = (int16_t)best_j;
+            b.scores[pair] = (int16_t)best;
         } else {
             // DefaultKernel.cpp:381-387: (max_read_pos, min(max_ref_pos, arg-max of that row))
-            b.end_cell[2 * slot] = (int16_t)(m - 1);
-            b.end_cell[2 * slot + 1] = (int16_t)min((int)meta.max_ref_pos, row_idx);
-            b.scores[slot] = (int16_t)row_max;
+            b.end_cell[2 * pair] = (int16_t)(m - 1);
+            b.end_cell[2 * pair + 1] = (int16_t)min((int)meta.max_ref_pos, row_idx);
+            b.scores[pair] = (int16_t)row_max;
         }
     }
     // one atomic per warp for the cell counter
@@ -269,13 +174,6 @@ __global__ void __launch_bounds__(256) int_peak_kernel(int iters, unsigned int s
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
-
-int launch_prep(const ChunkGeom &g, const ChunkBuffers &b, int mode, int policy, const Scoring &sc, cudaStream_t stream) {
-    const int trim = (sc.gap_read <= 0 && sc.gap_ref <= 0) ? 1 : 0;
-    const int threads = 128, blocks = (g.slots + threads - 1) / threads;
-    prep_kernel<<<blocks, threads, 0, stream>>>(g, b, mode, policy, trim);
-    return 1;
-}
 
 template <int MODE>
 static void launch_fill_mode(const ChunkGeom &g, const ChunkBuffers &b, int policy, const Scoring &sc, cudaStream_t stream) {

@@ -1,0 +1,236 @@
+// va_prep.cu -- staging on the device: raw bytes -> per-pair extents -> length-bucketed slot order
+// -> base codes in slot order.
+//
+// What it replaces in the reference: the per-cell char_to_score[] look-ups
+// (DefaultKernel.h:43-60 == opencl_definitions.cl:25-42) and the first-invalid-character scans of
+// the NW fill (DefaultKernel.cpp:308-310,348-350; SSEKernel.cpp:514-518,673-677) are hoisted out
+// of the DP loop; and where the reference's OpenCL host cuts the batch into equal pieces in input
+// order (OpenCLKernel.cpp:517-568), pairs are first sorted by the DP extents they need, so that
+// the threads of a warp -- and the two lanes of a packed pair-of-pairs -- sweep the same number of
+// rows and columns on mixed-length batches.
+//
+//   meta_kernel    one thread per pair: word loads, table look-up per byte -> codes (pair order),
+//                  last ACGT base / first invalid byte of each sequence -> PairMeta + sort key
+//   radix sort     (cub) key = [dirty ref | cols | rows], value = pair index; stable, so a uniform
+//                  batch keeps its order
+//   encode_kernel  pair = order[slot]: codes and meta move to slot order, 16 bytes per thread
+#include <algorithm>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "va_internal.h"
+
+namespace va {
+
+namespace {
+
+// byte -> code table (DefaultKernel.h:43-60 regrouped: A,C,G,T = 0..3, N = 4, everything else 5)
+__device__ __forceinline__ void fill_lut(uint8_t *lut) {
+    for (int c = threadIdx.x; c < 256; c += blockDim.x) {
+        const int u = c & 0xDF;  // fold case; bytes >= 0x80 keep bit 7 and stay OTHER
+        lut[c] = (uint8_t)(u == 'A' ? CODE_A : u == 'C' ? CODE_C : u == 'G' ? CODE_G : u == 'T' ? CODE_T : u == 'N' ? CODE_N : CODE_OTHER);
+    }
+}
+
+struct SeqScan {
+    int last_acgt;      // index of the last ACGT base, -1 if none
+    int first_other;    // first byte that is neither ACGT nor N (Default/OpenCL "invalid"), L if none
+    int first_nonacgt;  // first byte that is not ACGT (SSE/AVX "invalid"), L if none
+    int n_acgt;
+};
+
+// One thread translates and scans one sequence, 16 bases per step: aligned 32-bit loads (the
+// sequence starts at an arbitrary byte, so neighbouring words are funnel-shifted into place), one
+// shared-memory look-up per byte, and one coalesced uint4 store of 16 codes to the pair-interleaved
+// scratch array codes[chunk][pair].  Bytes past L become OTHER.
+__device__ __forceinline__ SeqScan scan_sequence(const uint8_t *__restrict__ raw, int L, int chunks, uint4 *__restrict__ codes,
+                                                 size_t chunk_stride, const uint8_t *lut, bool last_pair) {
+    SeqScan s{-1, L, L, 0};
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(raw);
+    const uint32_t *words = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
+    const int shift = (int)(addr & 3) * 8;
+    const int nwords_safe = last_pair ? 0 : (L + 3) / 4;  // the last pair of the buffer reads byte-wise: no overrun
+    uint32_t carry = nwords_safe ? words[0] : 0;
+    for (int c = 0; c < chunks; ++c) {
+        uint32_t out[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int wi = c * 4 + q;  // sequence word: bytes 4*wi .. 4*wi+3
+            uint32_t v;
+            if (wi < nwords_safe) {
+                const uint32_t next = words[wi + 1];
+                v = __funnelshift_r(carry, next, shift);
+                carry = next;
+            } else {
+                v = 0;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int pos = wi * 4 + t;
+                    if (pos < L) v |= (uint32_t)raw[pos] << (8 * t);
+                }
+            }
+            uint32_t o = 0;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int pos = wi * 4 + t;
+                int code = CODE_OTHER;
+                if (pos < L) {
+                    code = lut[(v >> (8 * t)) & 0xFF];
+                    if (code < 4) {
+                        s.last_acgt = pos;
+                        s.n_acgt++;
+                    } else {
+                        s.first_nonacgt = min(s.first_nonacgt, pos);
+                        if (code == CODE_OTHER) s.first_other = min(s.first_other, pos);
+                    }
+                }
+                o |= (uint32_t)code << (8 * t);
+            }
+            out[q] = o;
+        }
+        codes[(size_t)c * chunk_stride] = make_uint4(out[0], out[1], out[2], out[3]);
+    }
+    return s;
+}
+
+__global__ void __launch_bounds__(128) meta_kernel(ChunkGeom g, const uint8_t *__restrict__ raw_reads,
+                                                   const uint8_t *__restrict__ raw_refs, PairMeta *__restrict__ meta_pair,
+                                                   uint4 *__restrict__ codes_pair_reads, uint4 *__restrict__ codes_pair_refs,
+                                                   uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, int mode,
+                                                   int policy, int trim, int key_row_bits) {
+    __shared__ uint8_t lut[256];
+    fill_lut(lut);
+    __syncthreads();
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair >= g.n) return;
+    {
+        const bool last_pair = pair == g.n - 1;
+        const SeqScan rd = scan_sequence(raw_reads + (size_t)pair * g.read_length, g.read_length, g.read_chunks,
+                                         codes_pair_reads + pair, (size_t)g.slots, lut, last_pair);
+        const SeqScan rf = scan_sequence(raw_refs + (size_t)pair * g.ref_length, g.ref_length, g.ref_chunks,
+                                         codes_pair_refs + pair, (size_t)g.slots, lut, last_pair);
+        PairMeta m;
+        m.true_rows = (int16_t)(rd.last_acgt + 1);
+        m.true_cols = (int16_t)(rf.last_acgt + 1);
+        m.flags = (int16_t)((rd.n_acgt != rd.last_acgt + 1 ? 1 : 0) | (rf.n_acgt != rf.last_acgt + 1 ? 2 : 0));
+        m.max_read_pos = (int16_t)((policy == 1 ? rd.first_nonacgt : rd.first_other) - 1);
+        m.max_ref_pos = (int16_t)((policy == 1 ? rf.first_nonacgt : rf.first_other) - 1);
+        m.pad = 0;
+        if (mode == MODE_NW_ALIGN) {
+            // rows below the first invalid read character are never consulted; the end-cell rule scans
+            // the whole padded width of the last valid row
+            m.rows = (int16_t)(m.max_read_pos + 1);
+            m.cols = (int16_t)g.ref_length;
+        } else if (trim) {
+            // trailing rows/columns that can only score 0 never change the result while both gap
+            // scores are <= 0 (SURVEY.md A.1/A.2 "padding is neutral")
+            m.rows = m.true_rows;
+            m.cols = m.true_cols;
+            if (mode == MODE_SW_ALIGN) {
+                // with a zero score traceback starts at cell (0,0) (DefaultKernel.cpp:207-208): that
+                // cell's pointer must exist even when a sequence holds no ACGT base at all
+                m.rows = (int16_t)max((int)m.rows, min(1, g.read_length));
+                m.cols = (int16_t)max((int)m.cols, min(1, g.ref_length));
+            }
+        } else {
+            m.rows = (int16_t)g.read_length;
+            m.cols = (int16_t)g.ref_length;
+        }
+        meta_pair[pair] = m;
+        // pairs the packed kernels cannot take (padding / non-ACGT inside the swept ref columns) sort last
+        const uint32_t dirty = ((m.flags & 2) || m.cols != m.true_cols) ? 1u : 0u;
+        keys[pair] = (((dirty << 15) | (uint32_t)m.cols) << key_row_bits) | (uint32_t)m.rows;
+        vals[pair] = (uint32_t)pair;
+    }
+}
+
+// Pair order -> slot order: one thread moves one 16-base chunk (uint4) of one sequence into the
+// slot-interleaved arrays; thread 0 of a slot also moves the meta record.
+__global__ void __launch_bounds__(256) encode_kernel(ChunkGeom g, ChunkBuffers b, const PairMeta *__restrict__ meta_pair,
+                                                     const uint4 *__restrict__ codes_pair_reads,
+                                                     const uint4 *__restrict__ codes_pair_refs,
+                                                     const uint32_t *__restrict__ order) {
+    const int per_slot = g.read_chunks + g.ref_chunks;
+    const size_t total = (size_t)g.slots * per_slot;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        // consecutive threads = consecutive slots of the same chunk: coalesced 16-byte stores
+        const int c = (int)(t / g.slots), slot = (int)(t - (size_t)c * g.slots);
+        if (slot >= g.n) {  // padding slots: only their meta is ever looked at (as a duo partner)
+            if (c == 0) {
+                PairMeta z{};
+                b.meta[slot] = z;
+                b.pair_of[slot] = -1;
+            }
+            continue;
+        }
+        const int pair = (int)order[slot];
+        if (c == 0) {
+            b.meta[slot] = meta_pair[pair];
+            b.pair_of[slot] = pair;
+        }
+        // scratch is [chunk][pair]: for a batch that keeps its order both sides are coalesced
+        if (c < g.read_chunks) b.code_reads[(size_t)c * g.slots + slot] = codes_pair_reads[(size_t)c * g.slots + pair];
+        else b.code_refs[(size_t)(c - g.read_chunks) * g.slots + slot] = codes_pair_refs[(size_t)(c - g.read_chunks) * g.slots + pair];
+    }
+}
+
+int bits_for(int v) {
+    int b = 1;
+    while ((1 << b) <= v) ++b;
+    return b;
+}
+
+}  // namespace
+
+size_t prep_temp_bytes(int n) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint32_t *)nullptr,
+                                    (uint32_t *)nullptr, n > 0 ? n : 1, 0, 32);
+    return bytes + 256;
+}
+
+// scratch layout (all sized for `slots`): meta_pair | codes in pair order (reads, refs) | keys_in |
+// keys_out | vals_in | vals_out | cub temp
+size_t prep_scratch_bytes(int slots, int read_length, int ref_length) {
+    const size_t rpad = (size_t)((read_length + 15) / 16) * 16, fpad = (size_t)((ref_length + 15) / 16) * 16;
+    return (size_t)slots * (sizeof(PairMeta) + rpad + fpad + 4 * sizeof(uint32_t)) + prep_temp_bytes(slots) + 4096;
+}
+
+int launch_prep(const ChunkGeom &g, const ChunkBuffers &b, int mode, int policy, const Scoring &sc, void *scratch,
+                size_t scratch_bytes, cudaStream_t stream) {
+    if (g.n <= 0) return 0;
+    auto align256 = [](char *q) { return (char *)(((uintptr_t)q + 255) & ~(uintptr_t)255); };
+    char *p = (char *)scratch;
+    PairMeta *meta_pair = (PairMeta *)p;
+    p = align256(p + (size_t)g.slots * sizeof(PairMeta));
+    uint4 *codes_reads = (uint4 *)p;
+    p = align256(p + (size_t)g.slots * g.read_chunks * 16);
+    uint4 *codes_refs = (uint4 *)p;
+    p = align256(p + (size_t)g.slots * g.ref_chunks * 16);
+    uint32_t *keys_in = (uint32_t *)p;
+    p += (size_t)g.slots * 4;
+    uint32_t *keys_out = (uint32_t *)p;
+    p += (size_t)g.slots * 4;
+    uint32_t *vals_in = (uint32_t *)p;
+    p += (size_t)g.slots * 4;
+    uint32_t *vals_out = (uint32_t *)p;
+    p = align256(p + (size_t)g.slots * 4);
+    size_t temp_bytes = scratch_bytes - (size_t)(p - (char *)scratch);
+
+    const int trim = (sc.gap_read <= 0 && sc.gap_ref <= 0) ? 1 : 0;
+    const int row_bits = bits_for(g.read_length);
+    const int threads = 256;
+    const int grid_cap = 148 * 8;
+    const int meta_blocks = (g.n + 127) / 128;
+    const size_t enc_items = (size_t)g.slots * (g.read_chunks + g.ref_chunks);
+    const int enc_blocks = (int)std::min<size_t>((enc_items + threads - 1) / threads, grid_cap * 4);
+    meta_kernel<<<meta_blocks, 128, 0, stream>>>(g, b.raw_reads, b.raw_refs, meta_pair, codes_reads, codes_refs, keys_in,
+                                                     vals_in, mode, policy, trim, row_bits);
+    // only the bits that can differ are sorted: rows, cols and the "dirty" flag above them
+    cub::DeviceRadixSort::SortPairs(p, temp_bytes, keys_in, keys_out, vals_in, vals_out, g.n, 0, row_bits + 16, stream);
+    encode_kernel<<<enc_blocks, threads, 0, stream>>>(g, b, meta_pair, codes_reads, codes_refs,
+                                                      vals_out);
+    return 2;  // our kernels; the sort is the library's
+}
+
+}  // namespace va

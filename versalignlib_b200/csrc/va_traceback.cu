@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
     const int mode = NW ? MODE_NW_ALIGN : MODE_SW_ALIGN;
     const bool packed = duo_is_fast(g, mode, slot & ~1, b.meta[slot & ~1], b.meta[slot | 1]);
     const int duo = slot >> 1, lane_shift = (slot & 1) * 16;
+    const int pair = b.pair_of[slot];  // raw bytes and results are indexed in the caller's pair order
 
     // ---- end cell ----------------------------------------------------------------------
     int i, j;
@@ -63,12 +64,12 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
         }
         i = rows - 1;
         j = min((int)meta.max_ref_pos, idx);
-        b.end_cell[2 * slot] = (int16_t)i;
-        b.end_cell[2 * slot + 1] = (int16_t)j;
-        b.scores[slot] = (int16_t)best;
+        b.end_cell[2 * pair] = (int16_t)i;
+        b.end_cell[2 * pair + 1] = (int16_t)j;
+        b.scores[pair] = (int16_t)best;
     } else {
-        i = b.end_cell[2 * slot];
-        j = b.end_cell[2 * slot + 1];
+        i = b.end_cell[2 * pair];
+        j = b.end_cell[2 * pair + 1];
     }
     const int end_i = i, end_j = j;
 
@@ -136,12 +137,12 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
     if (n_moves & 15) mq.q[(size_t)(n_moves >> 4) * mq.stride] = acc;
 
     // ---- emit ----------------------------------------------------------------------------
-    const uint8_t *read = b.raw_reads + (size_t)slot * g.read_length;
-    const uint8_t *ref = b.raw_refs + (size_t)slot * g.ref_length;
-    uint8_t *oa = b.aln_read + (size_t)slot * L;
-    uint8_t *ob = b.aln_ref + (size_t)slot * L;
+    const uint8_t *read = b.raw_reads + (size_t)pair * g.read_length;
+    const uint8_t *ref = b.raw_refs + (size_t)pair * g.ref_length;
+    uint8_t *oa = b.aln_read + (size_t)pair * L;
+    uint8_t *ob = b.aln_ref + (size_t)pair * L;
     const int start = L - 1 - n_moves;  // may be negative only when every move was a gap (never with gap scores < 0)
-    b.start[slot] = (int16_t)start;
+    b.start[pair] = (int16_t)start;
     if (L >= 1) {
         oa[L - 1] = 0;
         ob[L - 1] = 0;
