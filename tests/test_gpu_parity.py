@@ -214,3 +214,17 @@ def test_c5_adversarial_parameter_grid(ctx):
                 oa, ob, ostart, oend = ora.align(opt, pol, reads, refs, sc)
                 assert np.array_equal(start, ostart) and np.array_equal(end, oend), (sc, opt, pol)
                 assert np.array_equal(a, oa) and np.array_equal(b, ob), (sc, opt, pol)
+
+
+def test_long_pairs_intra_task_kernel(ctx):
+    """Few, long pairs take the warp-per-pair wavefront kernel (va_intra.cu); the oracle is the only
+    reference for it (the reference library has no intra-task kernel)."""
+    for n, rl, fl, seed in [(40, 1000, 1200, 31), (6, 3000, 3500, 32), (9, 700, 2049, 33)]:
+        reads, refs = synth.uniform_batch(n, rl, fl, p_sub=0.10, q_indel=0.03, seed=seed)
+        for sc in [(2, -1, -3, -3), (3, -2, -1, -4)]:
+            got = ctx.score_flat(ora.SW, reads, refs, sc)
+            want = ora.score(ora.SW, reads, refs, sc)
+            assert np.array_equal(got, want), (n, rl, fl, sc, np.nonzero(got != want)[0][:5])
+    # mixed lengths + an odd pair count: partial last pass, general-kernel tail
+    reads, refs, _, _ = synth.mixed_batch(33, 900, 1500, p_sub=0.1, q_indel=0.02, seed=34)
+    assert np.array_equal(ctx.score_flat(ora.SW, reads, refs), ora.score(ora.SW, reads, refs))

@@ -449,7 +449,11 @@ int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int
     }
     launches += launch_prep(g, b, mode, policy, sc, ws.prep_scratch.p, ws.prep_scratch.cap, stream);
     if (pe) cudaEventRecord(pe[1], stream);
-    launches += launch_fill_fast(g, b, mode, sc, stream);
+    static const bool no_intra = [] { const char *v = getenv("VERSALIGN_CUDA_NO_INTRA"); return v && atoi(v) != 0; }();
+    if (g.fast_tw && !no_intra && intra_preferred(mode, n, sh.read_length, sh.ref_length, e.sm_count))
+        launches += launch_fill_intra(g, b, mode, make_fast_consts(mode, sc), stream);
+    else
+        launches += launch_fill_fast(g, b, mode, sc, stream);
     launches += launch_fill_general(g, b, mode, policy, sc, stream);
     if (pe) cudaEventRecord(pe[2], stream);
     if (sh.align) {

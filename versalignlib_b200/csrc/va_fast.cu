@@ -246,6 +246,11 @@ bool fast_scoring_ok(int mode, int policy, const Scoring &sc, int read_length, i
     if (!fits8(sc.match - off) || !fits8(sc.mismatch - off) || !fits8(-off)) return false;
     int mx = 1;
     for (int v : {sc.match, sc.mismatch, sc.gap_read, sc.gap_ref}) mx = max(mx, v < 0 ? -v : v);
+    if (mode == MODE_SW_SCORE || mode == MODE_SW_ALIGN) {
+        // every cell is floored at 0: values stay within [-mx, match * min(rows, cols)]
+        const long long top = (long long)(sc.match > 0 ? sc.match : 0) * (read_length < ref_length ? read_length : ref_length);
+        return top + mx <= 32000 && mx <= 8000;
+    }
     return (long long)(read_length + ref_length + 4) * mx <= 32000;
 }
 
@@ -263,8 +268,7 @@ size_t fast_dirs_bytes_per_row_per_slot(int ref_length) {
     return (s32 > s30 ? s32 : s30) * 2 * 8 / 2;
 }
 
-int launch_fill_fast(const ChunkGeom &g, const ChunkBuffers &b, int mode, const Scoring &sc, cudaStream_t stream) {
-    if (g.fast_tw == 0 || g.n < 2) return 0;
+FastConsts make_fast_consts(int mode, const Scoring &sc) {
     FastConsts fc{};
     const int off = mode == MODE_NW_ALIGN ? sc.gap_ref : 0;
     for (int c = 0; c < 8; ++c) fc.tab[c] = table_word(c, sc.match, sc.mismatch, off);
@@ -274,6 +278,12 @@ int launch_fill_fast(const ChunkGeom &g, const ChunkBuffers &b, int mode, const 
     fc.gR2 = ((uint32_t)sc.gap_read & 0xFFFFu) * 0x00010001u;
     const int d = mode == MODE_NW_ALIGN ? sc.gap_ref - sc.gap_read : -sc.gap_read;
     fc.dFR2 = ((uint32_t)d & 0xFFFFu) * 0x00010001u;
+    return fc;
+}
+
+int launch_fill_fast(const ChunkGeom &g, const ChunkBuffers &b, int mode, const Scoring &sc, cudaStream_t stream) {
+    if (g.fast_tw == 0 || g.n < 2) return 0;
+    const FastConsts fc = make_fast_consts(mode, sc);
     switch (mode) {
         case MODE_SW_SCORE: launch_tw<MODE_SW_SCORE>(g, b, fc, stream); break;
         case MODE_NW_SCORE: launch_tw<MODE_NW_SCORE>(g, b, fc, stream); break;

@@ -90,7 +90,11 @@ int launch_fill_general(const ChunkGeom &g, const ChunkBuffers &b, int mode, int
 bool fast_scoring_ok(int mode, int policy, const Scoring &sc, int read_length, int ref_length);
 int fast_pick_tw(int mode, int ref_length);
 size_t fast_dirs_bytes_per_row_per_slot(int ref_length);
+FastConsts make_fast_consts(int mode, const Scoring &sc);
 int launch_fill_fast(const ChunkGeom &g, const ChunkBuffers &b, int mode, const Scoring &sc, cudaStream_t stream);
+// intra-task (warp per pair-of-pairs) kernel for few, long pairs (va_intra.cu)
+bool intra_preferred(int mode, int n_pairs, int read_length, int ref_length, int sm_count);
+int launch_fill_intra(const ChunkGeom &g, const ChunkBuffers &b, int mode, const FastConsts &fc, cudaStream_t stream);
 size_t traceback_queue_words(int read_length, int ref_length);
 int launch_traceback(const ChunkGeom &g, const ChunkBuffers &b, int mode, int gap_ref, uint32_t *global_queue,
                      cudaStream_t stream);
