@@ -461,7 +461,7 @@ int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int
             cudaMemsetAsync(aln_read, 0, (size_t)n * sh.L, stream);
             cudaMemsetAsync(aln_ref, 0, (size_t)n * sh.L, stream);
         }
-        launches += launch_traceback(g, b, mode, sc.gap_ref, (uint32_t *)ws.queue.p, stream);
+        launches += launch_traceback(g, b, mode, sc, (uint32_t *)ws.queue.p, stream);
     }
     if (pe) cudaEventRecord(pe[3], stream);
     cudaError_t err = cudaGetLastError();

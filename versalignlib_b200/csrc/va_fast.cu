@@ -18,6 +18,8 @@
 //     two max instructions as predicates; the predicates are banked into bit planes with
 //     predicated FADDs (2^23-biased floats: exact integers, runs on the FP pipes and leaves the
 //     integer pipe to the recurrence).  2 bits per cell reach HBM, as coalesced 8-byte stores.
+#include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 #include "va_fast.cuh"
@@ -34,7 +36,8 @@ __device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b) { return __viad
 // cell below needs) are the same register: one add less per cell in NW align.
 template <int MODE, int TW, bool SYM>
 __global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuffers b, FastConsts fc) {
-    constexpr bool NWA = MODE == MODE_NW_ALIGN;
+    constexpr bool SWA = MODE == MODE_SW_ALIGN;
+    constexpr bool NWA = MODE == MODE_NW_ALIGN || SWA;  // both align modes keep H + gF and emit direction planes
     constexpr bool SWS = MODE == MODE_SW_SCORE;
     constexpr bool NWS = MODE == MODE_NW_SCORE;
     constexpr int NG = (TW + 15) / 16;
@@ -63,6 +66,8 @@ __global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuf
         uint4 *dirs = b.fdirs;
 
         uint32_t best = 0;  // SW: running max; NW score: max(0, last column, last row)
+        // SW align: best cell so far, per lane (first strictly greater in row-major order)
+        int gbest_a = 0, gbest_b = 0, gi_a = 0, gi_b = 0, gj_a = 0, gj_b = 0;
         const int nstrips = (n + TW - 1) / TW;
         for (int s = 0; s < nstrips; ++s) {
             const int c0 = s * TW;
@@ -75,12 +80,21 @@ __global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuf
                 const uint32_t fa = cref[off + (size_t)slot_a * 16], fb = cref[off + (size_t)slot_b * 16];
                 // nibbles: lane A low byte <- table a[fa], high byte <- its sign; lane B from table b (bytes 4..7)
                 sel[k] = fa | ((fa | 8u) << 4) | ((fb | 4u) << 8) | ((fb | 12u) << 12);
-                H[k] = NWA ? gF2 : 0u;  // matrix row 0 is 0 (NW align keeps H + gF)
+                // matrix row 0 is 0 (the align modes keep H + gF; SW align adds its bias, see below)
+                H[k] = SWA ? fc.swa_g0 : NWA ? gF2 : 0u;
             }
             // H[i][c0] feeding the first column's diagonal: 0 for matrix row 0
-            uint32_t diag_next = NWA ? gF2 : 0u;
-            // matrix column 0: 0 in the score modes, (i+1)*gF in NW align; carried as "left + gR"
-            uint32_t col0 = NWA ? add2(gF2, gR2) : gR2;
+            uint32_t diag_next = SWA ? fc.swa_g0 : NWA ? gF2 : 0u;
+            // matrix column 0: 0 in the score modes and SW align, (i+1)*gF in NW align; carried as "left + gR"
+            uint32_t col0 = SWA ? fc.swa_l0 : NWA ? add2(gF2, gR2) : gR2;
+            // SW align runs the whole recurrence with a constant bias B on every stored value, so that
+            //  - the zero floor folds into the two adds:  left = max(h+gR, 0+gR)  (one VIADDMNMX each), and
+            //  - "left" is never negative, so  key = left*32 + (31-k)  is one IMAD on the FMA pipe and the
+            //    packed maximum of the keys of a row is its best value together with its FIRST column.
+            // Per row the key is compared once (value part only) with the strip's best so far.
+            int sval_a = fc.swa_off, sval_b = fc.swa_off;  // best (biased) value so far in this strip; swa_off = value 0
+            uint32_t skey_a = 0, skey_b = 0;     // key that first exceeded it (gives the column)
+            int srow_a = -1, srow_b = -1;        // and its row
             const int kv = min(TW, n - c0);  // valid columns of this strip
             const bool full = kv == TW;
 
@@ -114,10 +128,12 @@ __global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuf
                         cb1 = ra[o2 + 16];
                         if (!first) nleft = bp[i < mlast ? g.duos : 0];  // boundary of row i+1
                     }
-                    if (NWA && first) col0 = add2(col0, gF2);
+                    if (NWA && !SWA && first) col0 = add2(col0, gF2);
+                    uint32_t rowkey = 0;
                     uint32_t diag = diag_next;
                     diag_next = add2(left, dFR2);
                     float p1l[NG], p1h[NG], p2l[NG], p2h[NG];
+                    uint32_t prev_key = 0;
 #pragma unroll
                     for (int q = 0; q < NG; ++q) p1l[q] = p1h[q] = p2l[q] = p2h[q] = 8388608.0f;
 #pragma unroll
@@ -128,14 +144,30 @@ __global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuf
                             bool dl, dh, ul, uh;
                             const uint32_t t = __vibmax_s16x2(up, left, &uh, &ul);  // up+gF >= left+gR : UP before LEFT
                             const uint32_t d = add2(diag, sub);                     // diag + s (table holds s - gF)
-                            const uint32_t h = __vibmax_s16x2(d, t, &dh, &dl);      // diag+s >= max(up,left) : DIAG first
+                            uint32_t h = __vibmax_s16x2(d, t, &dh, &dl);            // diag+s >= max(up,left) : DIAG first
                             const float bit = (float)(1u << (k & 15));
                             if (dl) p1l[k >> 4] += bit;
                             if (dh) p1h[k >> 4] += bit;
                             if (ul) p2l[k >> 4] += bit;
                             if (uh) p2h[k >> 4] += bit;
-                            left = add2(h, gR2);
-                            H[k] = SYM ? left : add2(h, gF2);
+                            if (SWA) {
+                                // the pointer of a positive cell is the NW rule; a zero cell is START, which the
+                                // traceback recognises by tracking the score (DefaultKernel.cpp:238-248)
+                                left = __viaddmax_s16x2(h, gR2, fc.swa_l0);           // max(h, 0) + gR   (biased)
+                                H[k] = SYM ? left : __viaddmax_s16x2(h, gF2, fc.swa_g0);
+                                const uint32_t key = left * 32u + (uint32_t)(31 - k) * 0x00010001u;
+                                if (PARTIAL) {  // columns past n must not win
+                                    if (k < kv) rowkey = __vmaxs2(rowkey, key);
+                                } else if (k & 1) {
+                                    rowkey = __vimax3_s16x2(rowkey, key, prev_key);
+                                } else if (k == TW - 1) {
+                                    rowkey = __vmaxs2(rowkey, key);
+                                }
+                                prev_key = key;
+                            } else {
+                                left = add2(h, gR2);
+                                H[k] = SYM ? left : add2(h, gF2);
+                            }
                         } else {
                             const uint32_t t = __viaddmax_s16x2(up, gF2, left);
                             const uint32_t h = SWS ? __viaddmax_s16x2_relu(diag, sub, t) : __viaddmax_s16x2(diag, sub, t);
@@ -156,6 +188,20 @@ __global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuf
                     }
                     if (!last) *bp = left;
                     bp += g.duos;
+                    if (SWA) {
+                        // strictly greater VALUE than anything seen before in this strip (rows above): new best cell
+                        const int ra_ = (int)((rowkey & 0xFFFFu) >> 5), rb_ = (int)(rowkey >> 21);
+                        if (ra_ > sval_a) {
+                            sval_a = ra_;
+                            srow_a = i;
+                            skey_a = rowkey & 0xFFFFu;
+                        }
+                        if (rb_ > sval_b) {
+                            sval_b = rb_;
+                            srow_b = i;
+                            skey_b = rowkey >> 16;
+                        }
+                    }
                     if (NWS && !PARTIAL && last) best = __vmaxs2(best, H[TW - 1]);  // last column (SSEKernel.cpp:1285-1291)
                     if (NWA) {
 #pragma unroll
@@ -166,33 +212,41 @@ __global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuf
                     }
                 };
                 // two rows per iteration: their direction words leave as one 16-byte store per group
-                int i = 0;
-                for (; i + 1 < m; i += 2, dp += (size_t)NG * g.duos) {
+                for (int i = 0; i < m; i += 2, dp += (size_t)NG * g.duos) {
                     uint2 w0[NG], w1[NG];
+#pragma unroll
+                    for (int q = 0; q < NG; ++q) w1[q] = make_uint2(0u, 0u);
                     do_row(i, w0);
-                    do_row(i + 1, w1);
+                    if (i + 1 < m) do_row(i + 1, w1);
                     if (NWA) {
 #pragma unroll
                         for (int q = 0; q < NG; ++q) dp[(size_t)q * g.duos] = make_uint4(w0[q].x, w0[q].y, w1[q].x, w1[q].y);
                     }
                 }
-                if (i < m) {
-                    uint2 w0[NG];
-                    do_row(i, w0);
-                    if (NWA) {
-#pragma unroll
-                        for (int q = 0; q < NG; ++q) dp[(size_t)q * g.duos] = make_uint4(w0[q].x, w0[q].y, 0u, 0u);
-                    }
-                }
             };
-            if (NWA || full) sweep(std::false_type{});
+            if ((NWA && !SWA) || full) sweep(std::false_type{});
             else sweep(std::true_type{});
+            if (SWA) {
+                // fold this strip into the pair's best cell: greater wins; equal wins only from an earlier row
+                // (an equal value further right in the same row, or below, comes later in row-major order)
+                const int va = sval_a - fc.swa_off, vb = sval_b - fc.swa_off;
+                if (srow_a >= 0 && (va > gbest_a || (va == gbest_a && srow_a < gi_a))) {
+                    gbest_a = va;
+                    gi_a = srow_a;
+                    gj_a = c0 + 31 - (int)(skey_a & 31u);
+                }
+                if (srow_b >= 0 && (vb > gbest_b || (vb == gbest_b && srow_b < gi_b))) {
+                    gbest_b = vb;
+                    gi_b = srow_b;
+                    gj_b = c0 + 31 - (int)(skey_b & 31u);
+                }
+            }
             if (NWS) {  // whole last row (SSEKernel.cpp:1302-1310); column 0 is 0 and `best` starts at 0
 #pragma unroll
                 for (int k = 0; k < TW; ++k)
                     if (c0 + k < n) best = __vmaxs2(best, H[k]);
             }
-            if (NWA) {  // the row the end-cell rule scans (DefaultKernel.cpp:352-355,381-387)
+            if (NWA && !SWA) {  // the row the end-cell rule scans (DefaultKernel.cpp:352-355,381-387)
 #pragma unroll
                 for (int k = 0; k < TW; ++k)
                     if (c0 + k < n) b.hrow[(size_t)(c0 + k) * g.duos + duo] = H[k];
@@ -201,6 +255,15 @@ __global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuf
         if (!NWA) {
             b.scores[b.pair_of[slot_a]] = (int16_t)(best & 0xFFFF);
             b.scores[b.pair_of[slot_b]] = (int16_t)(best >> 16);
+        }
+        if (SWA) {
+            const int pa = b.pair_of[slot_a], pb = b.pair_of[slot_b];
+            b.scores[pa] = (int16_t)gbest_a;
+            b.end_cell[2 * pa] = (int16_t)gi_a;
+            b.end_cell[2 * pa + 1] = (int16_t)gj_a;
+            b.scores[pb] = (int16_t)gbest_b;
+            b.end_cell[2 * pb] = (int16_t)gi_b;
+            b.end_cell[2 * pb + 1] = (int16_t)gj_b;
         }
     }
     for (int o = 16; o > 0; o >>= 1) cells += __shfl_xor_sync(0xffffffffu, cells, o);
@@ -212,15 +275,27 @@ void launch_one(const ChunkGeom &g, const ChunkBuffers &b, const FastConsts &fc,
     const int threads = 128;
     const int duos = (g.n + 1) / 2;
     const int blocks = (duos + threads - 1) / threads;
-    if (MODE == MODE_NW_ALIGN && fc.gF == fc.gR) fill_fast_kernel<MODE, TW, true><<<blocks, threads, 0, stream>>>(g, b, fc);
-    else fill_fast_kernel<MODE, TW, false><<<blocks, threads, 0, stream>>>(g, b, fc);
+    if constexpr (MODE == MODE_NW_ALIGN || MODE == MODE_SW_ALIGN) {
+        if (fc.gF == fc.gR) {
+            fill_fast_kernel<MODE, TW, true><<<blocks, threads, 0, stream>>>(g, b, fc);
+            return;
+        }
+    }
+    fill_fast_kernel<MODE, TW, false><<<blocks, threads, 0, stream>>>(g, b, fc);
 }
 
 template <int MODE>
 void launch_tw(const ChunkGeom &g, const ChunkBuffers &b, const FastConsts &fc, cudaStream_t stream) {
-    switch (g.fast_tw) {
-        case 30: launch_one<MODE, 30>(g, b, fc, stream); break;
-        default: launch_one<MODE, 32>(g, b, fc, stream); break;
+    if constexpr (MODE == MODE_SW_ALIGN) {  // more live state per cell: narrower strips keep it in registers
+        switch (g.fast_tw) {
+            case 16: launch_one<MODE, 16>(g, b, fc, stream); break;
+            default: launch_one<MODE, 20>(g, b, fc, stream); break;
+        }
+    } else {
+        switch (g.fast_tw) {
+            case 30: launch_one<MODE, 30>(g, b, fc, stream); break;
+            default: launch_one<MODE, 32>(g, b, fc, stream); break;
+        }
     }
 }
 
@@ -240,22 +315,38 @@ bool fits8(int v) { return v >= -128 && v <= 127; }
 // The packed kernels are exact only while (a) every table entry fits a signed byte and (b) no
 // cell can leave the int16 range; otherwise the call stays on the general 32-bit kernel.
 bool fast_scoring_ok(int mode, int policy, const Scoring &sc, int read_length, int ref_length) {
-    if (mode == MODE_SW_ALIGN) return false;              // not packed yet: general kernel
-    if (mode == MODE_NW_ALIGN && policy != 0) return false;  // SSE/AVX pointer rule: general kernel
-    const int off = mode == MODE_NW_ALIGN ? sc.gap_ref : 0;
+    const bool align = mode == MODE_NW_ALIGN || mode == MODE_SW_ALIGN;
+    if (align && policy != 0) return false;  // SSE/AVX pointer rule: general kernel
+    const int off = align ? sc.gap_ref : 0;
     if (!fits8(sc.match - off) || !fits8(sc.mismatch - off) || !fits8(-off)) return false;
     int mx = 1;
     for (int v : {sc.match, sc.mismatch, sc.gap_read, sc.gap_ref}) mx = max(mx, v < 0 ? -v : v);
     if (mode == MODE_SW_SCORE || mode == MODE_SW_ALIGN) {
         // every cell is floored at 0: values stay within [-mx, match * min(rows, cols)]
         const long long top = (long long)(sc.match > 0 ? sc.match : 0) * (read_length < ref_length ? read_length : ref_length);
+        // SW align packs (value + bias) * 32 + column into a 16-bit lane: value + 128 + gap must stay below 1024
+        if (mode == MODE_SW_ALIGN) return top + 2 * 128 < 1024 && mx <= 100;
         return top + mx <= 32000 && mx <= 8000;
     }
     return (long long)(read_length + ref_length + 4) * mx <= 32000;
 }
 
 int fast_pick_tw(int mode, int ref_length) {
-    (void)mode;
+    if (mode == MODE_SW_ALIGN) {
+        if (const char *v = getenv("VERSALIGN_CUDA_SWA_TW")) {
+            const int t = atoi(v);
+            if (t == 16 || t == 20) return t;
+        }
+        int best_tw = 20, best_cols = 1 << 30;
+        for (int t : {20, 16}) {
+            const int c = (ref_length + t - 1) / t * t;
+            if (c < best_cols) {
+                best_cols = c;
+                best_tw = t;
+            }
+        }
+        return best_tw;
+    }
     // fewest computed columns wins; ties go to the wider strip (fewer passes over the read)
     const int c32 = (ref_length + 31) / 32 * 32, c30 = (ref_length + 29) / 30 * 30;
     return c30 < c32 ? 30 : 32;
@@ -265,19 +356,34 @@ size_t fast_dirs_bytes_per_row_per_slot(int ref_length) {
     // per row and duo: strips * groups * 8 bytes; both strip widths use 2 groups.  (Rows are stored
     // in pairs; the caller rounds the row count up to even.)
     const size_t s32 = (size_t)(ref_length + 31) / 32, s30 = (size_t)(ref_length + 29) / 30;
-    return (s32 > s30 ? s32 : s30) * 2 * 8 / 2;
+    size_t per_duo = (s32 > s30 ? s32 : s30) * 2 * 8;
+    // SW align strips: 24 and 20 columns use two groups, 16 columns one
+    per_duo = std::max(per_duo, (size_t)((ref_length + 19) / 20) * 2 * 8);
+    per_duo = std::max(per_duo, (size_t)((ref_length + 23) / 24) * 2 * 8);
+    per_duo = std::max(per_duo, (size_t)((ref_length + 15) / 16) * 1 * 8);
+    return per_duo / 2;
 }
 
 FastConsts make_fast_consts(int mode, const Scoring &sc) {
     FastConsts fc{};
-    const int off = mode == MODE_NW_ALIGN ? sc.gap_ref : 0;
+    const bool align = mode == MODE_NW_ALIGN || mode == MODE_SW_ALIGN;
+    const int off = align ? sc.gap_ref : 0;
     for (int c = 0; c < 8; ++c) fc.tab[c] = table_word(c, sc.match, sc.mismatch, off);
     fc.gF = sc.gap_ref;
     fc.gR = sc.gap_read;
     fc.gF2 = ((uint32_t)sc.gap_ref & 0xFFFFu) * 0x00010001u;
     fc.gR2 = ((uint32_t)sc.gap_read & 0xFFFFu) * 0x00010001u;
-    const int d = mode == MODE_NW_ALIGN ? sc.gap_ref - sc.gap_read : -sc.gap_read;
+    const int d = align ? sc.gap_ref - sc.gap_read : -sc.gap_read;
     fc.dFR2 = ((uint32_t)d & 0xFFFFu) * 0x00010001u;
+    if (mode == MODE_SW_ALIGN) {
+        // bias B: every stored value is shifted by it so that "left" = max(h,0)+gR+B is never negative
+        const int B = 128;
+        auto pk = [](int v) { return ((uint32_t)v & 0xFFFFu) * 0x00010001u; };
+        fc.swa_l0 = pk(sc.gap_read + B);   // matrix column 0 / zero floor, as "left"
+        fc.swa_g0 = pk(sc.gap_ref + B);    // matrix row 0 / zero floor, as "H + gF"
+        fc.swa_off = sc.gap_read + B;      // key>>5 minus this is the cell value
+        fc.swa_key0 = pk(((sc.gap_read + B) << 5) | 31);
+    }
     return fc;
 }
 
@@ -288,6 +394,7 @@ int launch_fill_fast(const ChunkGeom &g, const ChunkBuffers &b, int mode, const 
         case MODE_SW_SCORE: launch_tw<MODE_SW_SCORE>(g, b, fc, stream); break;
         case MODE_NW_SCORE: launch_tw<MODE_NW_SCORE>(g, b, fc, stream); break;
         case MODE_NW_ALIGN: launch_tw<MODE_NW_ALIGN>(g, b, fc, stream); break;
+        case MODE_SW_ALIGN: launch_tw<MODE_SW_ALIGN>(g, b, fc, stream); break;
         default: return 0;
     }
     return 1;

@@ -20,7 +20,7 @@ __device__ __forceinline__ bool duo_is_fast(const ChunkGeom &g, int mode, int sl
     if ((a.flags & 2) || (b.flags & 2)) return false;
     if (a.cols != b.cols || a.cols <= 0) return false;
     if (a.cols != a.true_cols || b.cols != b.true_cols) return false;  // no padded / N tail inside the sweep
-    if (mode == MODE_NW_ALIGN || mode == MODE_SW_ALIGN) return a.rows == b.rows && a.rows > 0;
+    if (mode == MODE_NW_ALIGN) return a.rows == b.rows && a.rows > 0;
     return max(a.rows, b.rows) > 0;
 }
 

@@ -56,6 +56,9 @@ struct FastConsts {
     uint32_t gF2, gR2; // gap scores replicated in both 16-bit lanes
     uint32_t dFR2;     // NW align: gap_ref - gap_read ; score modes: -gap_read   (boundary -> diagonal conversion)
     int gF, gR;
+    // SW align only (see va_fast.cu): biased initial values and key constants
+    uint32_t swa_l0, swa_g0, swa_key0;
+    int swa_off;
 };
 
 struct ChunkBuffers {
@@ -96,7 +99,7 @@ int launch_fill_fast(const ChunkGeom &g, const ChunkBuffers &b, int mode, const 
 bool intra_preferred(int mode, int n_pairs, int read_length, int ref_length, int sm_count);
 int launch_fill_intra(const ChunkGeom &g, const ChunkBuffers &b, int mode, const FastConsts &fc, cudaStream_t stream);
 size_t traceback_queue_words(int read_length, int ref_length);
-int launch_traceback(const ChunkGeom &g, const ChunkBuffers &b, int mode, int gap_ref, uint32_t *global_queue,
+int launch_traceback(const ChunkGeom &g, const ChunkBuffers &b, int mode, const Scoring &sc, uint32_t *global_queue,
                      cudaStream_t stream);
 int launch_int_peak(int kind, int sm_count, int iters, unsigned int *sink, cudaStream_t stream, double *lane_ops);
 

@@ -26,8 +26,9 @@ struct MoveQueue {
 };
 
 template <bool NW>
-__global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, ChunkBuffers b, int gap_ref, uint32_t *gq,
+__global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, ChunkBuffers b, Scoring sc, uint32_t *gq,
                                                                int queue_words) {
+    const int gap_ref = sc.gap_ref;
     extern __shared__ uint32_t sq[];
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= g.n) return;
@@ -83,10 +84,17 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
         const uint4 *p = b.fdirs + (size_t)strip * strip_step + (size_t)(max(i, 0) >> 1) * pair_step + duo;
         int have_pair = -1, have_strip = -1, have_grp = -1;
         uint4 w = make_uint4(0, 0, 0, 0);
+        // SW: the packed fill stores the pointer a cell would have in NW; a cell whose value is 0 is
+        // START (DefaultKernel.cpp:240-241).  The value is known along the path: it starts at the best
+        // score and every move gives back what it added.
+        int hval = NW ? 1 : (int)b.scores[pair];
+        const uint8_t *wread = b.raw_reads + (size_t)pair * g.read_length;
+        const uint8_t *wref = b.raw_refs + (size_t)pair * g.ref_length;
         while (true) {
             int code;
             if (i < 0 || i >= rows || j >= cols) code = DIR_START;
             else if (j < 0) code = NW ? DIR_UP : DIR_START;  // matrix column 0 (DefaultKernel.cpp:304)
+            else if (!NW && hval <= 0) code = DIR_START;
             else {
                 const int grp = k >> 4;
                 if ((i >> 1) != have_pair || strip != have_strip || grp != have_grp) {
@@ -104,6 +112,15 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
             if ((++n_moves & 15) == 0) {
                 mq.q[(size_t)((n_moves >> 4) - 1) * mq.stride] = acc;
                 acc = 0;
+            }
+            if (!NW) {
+                if (code == DIR_UP) hval -= sc.gap_ref;
+                else if (code == DIR_LEFT) hval -= sc.gap_read;
+                else {
+                    const unsigned ca = wread[i] & 0xDFu, cb = wref[j] & 0xDFu;
+                    const bool va = ca == 'A' || ca == 'C' || ca == 'G' || ca == 'T', vb = cb == 'A' || cb == 'C' || cb == 'G' || cb == 'T';
+                    hval -= (va && vb) ? (ca == cb ? sc.match : sc.mismatch) : 0;
+                }
             }
             if (code != DIR_LEFT) {
                 if ((i & 1) == 0) p -= pair_step;  // leaving an even row: the row above is in the previous word
@@ -198,7 +215,7 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
 // (slots * queue_words words, provided by the caller).
 size_t traceback_queue_words(int read_length, int ref_length) { return (size_t)(read_length + ref_length + 15) / 16 + 1; }
 
-int launch_traceback(const ChunkGeom &g, const ChunkBuffers &b, int mode, int gap_ref, uint32_t *global_queue,
+int launch_traceback(const ChunkGeom &g, const ChunkBuffers &b, int mode, const Scoring &sc, uint32_t *global_queue,
                      cudaStream_t stream) {
     if (g.n <= 0) return 0;
     const int blocks = (g.n + TB_THREADS - 1) / TB_THREADS;
@@ -206,8 +223,8 @@ int launch_traceback(const ChunkGeom &g, const ChunkBuffers &b, int mode, int ga
     const size_t smem = (size_t)qw * TB_THREADS * sizeof(uint32_t);
     const bool use_shared = smem <= 48 * 1024;
     uint32_t *gq = use_shared ? nullptr : global_queue;
-    if (mode == MODE_NW_ALIGN) traceback_kernel<true><<<blocks, TB_THREADS, use_shared ? smem : 0, stream>>>(g, b, gap_ref, gq, qw);
-    else traceback_kernel<false><<<blocks, TB_THREADS, use_shared ? smem : 0, stream>>>(g, b, gap_ref, gq, qw);
+    if (mode == MODE_NW_ALIGN) traceback_kernel<true><<<blocks, TB_THREADS, use_shared ? smem : 0, stream>>>(g, b, sc, gq, qw);
+    else traceback_kernel<false><<<blocks, TB_THREADS, use_shared ? smem : 0, stream>>>(g, b, sc, gq, qw);
     return 1;
 }
 
