@@ -212,15 +212,22 @@ __global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuf
                     }
                 };
                 // two rows per iteration: their direction words leave as one 16-byte store per group
-                for (int i = 0; i < m; i += 2, dp += (size_t)NG * g.duos) {
+                int i = 0;
+                for (; i + 1 < m; i += 2, dp += (size_t)NG * g.duos) {
                     uint2 w0[NG], w1[NG];
-#pragma unroll
-                    for (int q = 0; q < NG; ++q) w1[q] = make_uint2(0u, 0u);
                     do_row(i, w0);
-                    if (i + 1 < m) do_row(i + 1, w1);
+                    do_row(i + 1, w1);
                     if (NWA) {
 #pragma unroll
                         for (int q = 0; q < NG; ++q) dp[(size_t)q * g.duos] = make_uint4(w0[q].x, w0[q].y, w1[q].x, w1[q].y);
+                    }
+                }
+                if (i < m) {  // odd row count: the last word holds one row
+                    uint2 w0[NG];
+                    do_row(i, w0);
+                    if (NWA) {
+#pragma unroll
+                        for (int q = 0; q < NG; ++q) dp[(size_t)q * g.duos] = make_uint4(w0[q].x, w0[q].y, 0u, 0u);
                     }
                 }
             };
