@@ -19,6 +19,33 @@ namespace {
 
 constexpr int TB_THREADS = 128;
 
+// Backwards byte reader over one raw sequence: keeps the aligned 16 bytes around the last position in
+// registers, so a walk that visits every base costs one 16-byte load per 16 bases instead of one
+// sector-sized L2 request per base (with full occupancy the L1 is too small to hold every thread's
+// window).  The window never reaches past `limit` (end of the whole raw buffer): there it falls back
+// to byte loads.
+struct ByteWindow {
+    const uint8_t *base;
+    const uint8_t *limit;
+    uintptr_t have;
+    uint4 w;
+    __device__ __forceinline__ ByteWindow(const uint8_t *b, const uint8_t *lim) : base(b), limit(lim), have(~(uintptr_t)0) {
+        w = make_uint4(0, 0, 0, 0);
+    }
+    __device__ __forceinline__ unsigned get(int idx) {
+        const uint8_t *p = base + idx;
+        const uintptr_t a16 = reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)15;
+        if (a16 + 16 > reinterpret_cast<uintptr_t>(limit)) return *p;
+        if (a16 != have) {
+            w = *reinterpret_cast<const uint4 *>(a16);
+            have = a16;
+        }
+        const unsigned k = (unsigned)(reinterpret_cast<uintptr_t>(p) & 15);
+        const uint32_t word = k < 8 ? (k < 4 ? w.x : w.y) : (k < 12 ? w.z : w.w);
+        return (word >> (8 * (k & 3))) & 0xFFu;
+    }
+};
+
 // 2-bit move queue of one thread: word w lives at q[w * stride]
 struct MoveQueue {
     uint32_t *q;
@@ -88,8 +115,8 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
         // START (DefaultKernel.cpp:240-241).  The value is known along the path: it starts at the best
         // score and every move gives back what it added.
         int hval = NW ? 1 : (int)b.scores[pair];
-        const uint8_t *wread = b.raw_reads + (size_t)pair * g.read_length;
-        const uint8_t *wref = b.raw_refs + (size_t)pair * g.ref_length;
+        ByteWindow wread(b.raw_reads + (size_t)pair * g.read_length, b.raw_reads + (size_t)g.n * g.read_length);
+        ByteWindow wref(b.raw_refs + (size_t)pair * g.ref_length, b.raw_refs + (size_t)g.n * g.ref_length);
         while (true) {
             int code;
             if (i < 0 || i >= rows || j >= cols) code = DIR_START;
@@ -117,7 +144,7 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
                 if (code == DIR_UP) hval -= sc.gap_ref;
                 else if (code == DIR_LEFT) hval -= sc.gap_read;
                 else {
-                    const unsigned ca = wread[i] & 0xDFu, cb = wref[j] & 0xDFu;
+                    const unsigned ca = wread.get(i) & 0xDFu, cb = wref.get(j) & 0xDFu;
                     const bool va = ca == 'A' || ca == 'C' || ca == 'G' || ca == 'T', vb = cb == 'A' || cb == 'C' || cb == 'G' || cb == 'T';
                     hval -= (va && vb) ? (ca == cb ? sc.match : sc.mismatch) : 0;
                 }
@@ -154,8 +181,8 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
     if (n_moves & 15) mq.q[(size_t)(n_moves >> 4) * mq.stride] = acc;
 
     // ---- emit ----------------------------------------------------------------------------
-    const uint8_t *read = b.raw_reads + (size_t)pair * g.read_length;
-    const uint8_t *ref = b.raw_refs + (size_t)pair * g.ref_length;
+    ByteWindow read(b.raw_reads + (size_t)pair * g.read_length, b.raw_reads + (size_t)g.n * g.read_length);
+    ByteWindow ref(b.raw_refs + (size_t)pair * g.ref_length, b.raw_refs + (size_t)g.n * g.ref_length);
     uint8_t *oa = b.aln_read + (size_t)pair * L;
     uint8_t *ob = b.aln_ref + (size_t)pair * L;
     const int start = L - 1 - n_moves;  // may be negative only when every move was a gap (never with gap scores < 0)
@@ -177,34 +204,50 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
     auto one_byte = [&]() {
         const int code = next_move();
         uint8_t a = '-', c = '-';
-        if (code != DIR_LEFT) a = read[i--];
-        if (code != DIR_UP) c = ref[j--];
+        if (code != DIR_LEFT) a = (uint8_t)read.get(i--);
+        if (code != DIR_UP) c = (uint8_t)ref.get(j--);
         if (pos >= 0) {
             oa[pos] = a;
             ob[pos] = c;
         }
         --pos;
     };
-    // both output rows start at slot*L, so they share their alignment modulo 4
-    const uintptr_t base_mod = reinterpret_cast<uintptr_t>(oa) & 3, base_mod_b = reinterpret_cast<uintptr_t>(ob) & 3;
-    if (base_mod == base_mod_b) {
-        // bytes until the next byte to write is the top byte of an aligned word
-        while (t < n_moves && pos >= 0 && ((base_mod + pos) & 3) != 3) one_byte();
-        while (n_moves - t >= 4 && pos >= 3) {
-            uint32_t wa = 0, wb = 0;
+    // Both output rows start at pair*L from (at least 256-byte aligned) buffers, so they share their
+    // alignment: bytes down to a 4-byte boundary, words down to a 16-byte boundary, then 16 moves
+    // per pair of 16-byte stores, then the remainder the same way back down.
+    const uintptr_t base_a = reinterpret_cast<uintptr_t>(oa), base_b = reinterpret_cast<uintptr_t>(ob);
+    auto four_moves = [&](uint32_t &wa, uint32_t &wb) {
+        wa = 0;
+        wb = 0;
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int code = next_move();
-                uint32_t a = '-', c = '-';
-                if (code != DIR_LEFT) a = read[i--];
-                if (code != DIR_UP) c = ref[j--];
-                wa |= a << (8 * (3 - r));
-                wb |= c << (8 * (3 - r));
-            }
-            *reinterpret_cast<uint32_t *>(oa + pos - 3) = wa;
-            *reinterpret_cast<uint32_t *>(ob + pos - 3) = wb;
-            pos -= 4;
+        for (int r = 0; r < 4; ++r) {
+            const int code = next_move();
+            uint32_t a = '-', c = '-';
+            if (code != DIR_LEFT) a = read.get(i--);
+            if (code != DIR_UP) c = ref.get(j--);
+            wa |= a << (8 * (3 - r));
+            wb |= c << (8 * (3 - r));
         }
+    };
+    auto one_word = [&]() {
+        uint32_t wa, wb;
+        four_moves(wa, wb);
+        *reinterpret_cast<uint32_t *>(oa + pos - 3) = wa;
+        *reinterpret_cast<uint32_t *>(ob + pos - 3) = wb;
+        pos -= 4;
+    };
+    if ((base_a & 15) == (base_b & 15)) {
+        while (t < n_moves && pos >= 0 && ((base_a + pos) & 3) != 3) one_byte();
+        while (n_moves - t >= 4 && pos >= 3 && ((base_a + pos) & 15) != 15) one_word();
+        while (n_moves - t >= 16 && pos >= 15) {
+            uint32_t wa[4], wb[4];
+#pragma unroll
+            for (int q = 3; q >= 0; --q) four_moves(wa[q], wb[q]);  // highest addresses first
+            *reinterpret_cast<uint4 *>(oa + pos - 15) = make_uint4(wa[0], wa[1], wa[2], wa[3]);
+            *reinterpret_cast<uint4 *>(ob + pos - 15) = make_uint4(wb[0], wb[1], wb[2], wb[3]);
+            pos -= 16;
+        }
+        while (n_moves - t >= 4 && pos >= 3) one_word();
     }
     while (t < n_moves) one_byte();
 }
