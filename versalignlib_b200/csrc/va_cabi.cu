@@ -293,9 +293,9 @@ struct Shape {
     size_t gen_dir_row_bytes() const { return (size_t)segs * 2; }
     size_t dir_row_bytes() const { return gen_dir_row_bytes() + fast_dirs_bytes_per_row_per_slot(ref_length); }
     size_t per_pair_workspace() const {
-        size_t b = (size_t)(read_chunks + ref_chunks) * 32 + 2 * sizeof(PairMeta) + 40 + (size_t)rows_alloc * 4;
+        size_t b = (size_t)(read_chunks + ref_chunks) * 32 + 2 * sizeof(PairMeta) + 40 + (size_t)rows_alloc * 6;
         if (align) {
-            b += dir_row_bytes() * (rows_alloc + 1) + (size_t)ref_length * 2;
+            b += dir_row_bytes() * (rows_alloc + 1) + (size_t)ref_length * 4;
             const size_t qw = traceback_queue_words(read_length, ref_length);
             if (qw * 128 * 4 > 48 * 1024) b += qw * 4;
         }
@@ -361,12 +361,13 @@ int reserve_slot(ChunkSlot &s, const Shape &sh, int cap_pairs, bool pinned) {
     if ((rc = s.meta.reserve(slots * sizeof(PairMeta)))) return rc;
     if ((rc = s.pair_of.reserve(slots * 4))) return rc;
     if ((rc = s.prep_scratch.reserve(prep_scratch_bytes((int)slots, sh.read_length, sh.ref_length)))) return rc;
-    if ((rc = s.boundary.reserve(slots * sh.rows_alloc * 4))) return rc;
+    // general region [rows][slots] + packed region [rows][duos] (kept apart: one chunk can hold both kinds)
+    if ((rc = s.boundary.reserve(slots * sh.rows_alloc * 6 + 512))) return rc;
     if ((rc = s.scores.reserve(slots * 2))) return rc;
     if ((rc = s.end_cell.reserve(slots * 4))) return rc;
     if (sh.align) {
         if ((rc = s.dirs.reserve(slots * sh.dir_row_bytes() * (sh.rows_alloc + 1) + 512))) return rc;
-        if ((rc = s.hrow.reserve(slots * (size_t)std::max(sh.ref_length, 1) * 2 + 64))) return rc;
+        if ((rc = s.hrow.reserve(slots * (size_t)std::max(sh.ref_length, 1) * 4 + 64))) return rc;
         // traceback move queue: shared memory unless the sequences are long
         const size_t qw = traceback_queue_words(sh.read_length, sh.ref_length);
         if (qw * 128 * 4 > 48 * 1024 && (rc = s.queue.reserve(slots * qw * 4 + 64))) return rc;
@@ -424,6 +425,7 @@ int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int
     b.meta = (PairMeta *)ws.meta.p;
     b.pair_of = (int32_t *)ws.pair_of.p;
     b.boundary = (int32_t *)ws.boundary.p;
+    b.fboundary = (uint32_t *)((char *)ws.boundary.p + round_up((size_t)g.slots * sh.rows_alloc * 4, 256));
     b.dirs = (uint16_t *)ws.dirs.p;
     b.fdirs = (uint4 *)((char *)ws.dirs.p + round_up((size_t)g.slots * sh.gen_dir_row_bytes() * sh.rows_alloc, 256));
     b.hrow = (uint32_t *)ws.hrow.p;

@@ -34,7 +34,11 @@ __device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b) { return __viad
 
 // SYM: gap_read == gap_ref, so "H + gR" (what the cell to the right needs) and "H + gF" (what the
 // cell below needs) are the same register: one add less per cell in NW align.
-template <int MODE, int TW, bool SYM>
+// EDGE (NW align only): the duo's ref is padded (cols < ref_length), so the last true column is kept
+// for the traceback kernel's pad-column rule.  It is a separate instantiation -- launched next to the
+// plain one, each taking only its own kind of duo -- because the plain kernel sits right at its
+// register budget and the extra state costs it spills.
+template <int MODE, int TW, bool SYM, bool EDGE>
 __global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuffers b, FastConsts fc) {
     constexpr bool SWA = MODE == MODE_SW_ALIGN;
     constexpr bool NWA = MODE == MODE_NW_ALIGN || SWA;  // both align modes keep H + gF and emit direction planes
@@ -55,6 +59,7 @@ __global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuf
         ma = b.meta[slot_a];
         mb = b.meta[slot_b];
         mine = duo_is_fast(g, MODE, slot_a, ma, mb);
+        if (MODE == MODE_NW_ALIGN) mine = mine && (EDGE == (g.ref_length > ma.cols));
     }
     if (mine) {
         const int m = max((int)ma.rows, (int)mb.rows), n = ma.cols;
@@ -62,7 +67,7 @@ __global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuf
         const uint32_t gF2 = fc.gF2, gR2 = fc.gR2, dFR2 = fc.dFR2;
         const uint8_t *cread = reinterpret_cast<const uint8_t *>(b.code_reads);
         const uint8_t *cref = reinterpret_cast<const uint8_t *>(b.code_refs);
-        uint32_t *bnd = reinterpret_cast<uint32_t *>(b.boundary);
+        uint32_t *bnd = b.fboundary;
         uint4 *dirs = b.fdirs;
 
         uint32_t best = 0;  // SW: running max; NW score: max(0, last column, last row)
@@ -130,6 +135,7 @@ __global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuf
                     }
                     if (NWA && !SWA && first) col0 = add2(col0, gF2);
                     uint32_t rowkey = 0;
+                    uint32_t edge = 0;
                     uint32_t diag = diag_next;
                     diag_next = add2(left, dFR2);
                     float p1l[NG], p1h[NG], p2l[NG], p2h[NG];
@@ -167,6 +173,7 @@ __global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuf
                             } else {
                                 left = add2(h, gR2);
                                 H[k] = SYM ? left : add2(h, gF2);
+                                if (EDGE && PARTIAL && k == kv - 1) edge = left;  // last true column of a partial last strip
                             }
                         } else {
                             const uint32_t t = __viaddmax_s16x2(up, gF2, left);
@@ -186,7 +193,10 @@ __global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuf
                         }
                         diag = up;
                     }
+                    // right edge of the strip for the next strip; NW align also keeps the LAST true column
+                    // (the traceback kernel needs it to decide whether the padded arg-max lands in a pad column)
                     if (!last) *bp = left;
+                    else if (EDGE) *bp = PARTIAL ? edge : left;
                     bp += g.duos;
                     if (SWA) {
                         // strictly greater VALUE than anything seen before in this strip (rows above): new best cell
@@ -231,7 +241,7 @@ __global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuf
                     }
                 }
             };
-            if ((NWA && !SWA) || full) sweep(std::false_type{});
+            if (full || (NWA && !SWA && !EDGE)) sweep(std::false_type{});
             else sweep(std::true_type{});
             if (SWA) {
                 // fold this strip into the pair's best cell: greater wins; equal wins only from an earlier row
@@ -248,15 +258,15 @@ __global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuf
                     gj_b = c0 + 31 - (int)(skey_b & 31u);
                 }
             }
-            if (NWS) {  // whole last row (SSEKernel.cpp:1302-1310); column 0 is 0 and `best` starts at 0
-#pragma unroll
-                for (int k = 0; k < TW; ++k)
-                    if (c0 + k < n) best = __vmaxs2(best, H[k]);
-            }
             if (NWA && !SWA) {  // the row the end-cell rule scans (DefaultKernel.cpp:352-355,381-387)
 #pragma unroll
                 for (int k = 0; k < TW; ++k)
                     if (c0 + k < n) b.hrow[(size_t)(c0 + k) * g.duos + duo] = H[k];
+            }
+            if (NWS) {  // whole last row (SSEKernel.cpp:1302-1310); column 0 is 0 and `best` starts at 0
+#pragma unroll
+                for (int k = 0; k < TW; ++k)
+                    if (c0 + k < n) best = __vmaxs2(best, H[k]);
             }
         }
         if (!NWA) {
@@ -282,13 +292,24 @@ void launch_one(const ChunkGeom &g, const ChunkBuffers &b, const FastConsts &fc,
     const int threads = 128;
     const int duos = (g.n + 1) / 2;
     const int blocks = (duos + threads - 1) / threads;
-    if constexpr (MODE == MODE_NW_ALIGN || MODE == MODE_SW_ALIGN) {
+    if constexpr (MODE == MODE_NW_ALIGN) {
+        // plain duos, then (nothing to do on an unpadded batch) the padded-ref duos
         if (fc.gF == fc.gR) {
-            fill_fast_kernel<MODE, TW, true><<<blocks, threads, 0, stream>>>(g, b, fc);
+            fill_fast_kernel<MODE, TW, true, false><<<blocks, threads, 0, stream>>>(g, b, fc);
+            fill_fast_kernel<MODE, TW, true, true><<<blocks, threads, 0, stream>>>(g, b, fc);
+        } else {
+            fill_fast_kernel<MODE, TW, false, false><<<blocks, threads, 0, stream>>>(g, b, fc);
+            fill_fast_kernel<MODE, TW, false, true><<<blocks, threads, 0, stream>>>(g, b, fc);
+        }
+        return;
+    }
+    if constexpr (MODE == MODE_SW_ALIGN) {
+        if (fc.gF == fc.gR) {
+            fill_fast_kernel<MODE, TW, true, false><<<blocks, threads, 0, stream>>>(g, b, fc);
             return;
         }
     }
-    fill_fast_kernel<MODE, TW, false><<<blocks, threads, 0, stream>>>(g, b, fc);
+    fill_fast_kernel<MODE, TW, false, false><<<blocks, threads, 0, stream>>>(g, b, fc);
 }
 
 template <int MODE>

@@ -68,11 +68,13 @@ struct ChunkBuffers {
     uint4 *code_refs;          // [ref_chunks][slots]
     PairMeta *meta;            // [slots]
     int32_t *pair_of;          // [slots] pair (position in the caller's batch) computed in this slot, -1 = padding
-    int32_t *boundary;         // [rows_alloc][slots]   right edge of the previous column strip
+    int32_t *boundary;         // general kernel: [rows_alloc][slots] right edge of the previous column strip
+    uint32_t *fboundary;       // packed kernels: [rows_alloc][duos] (inter-task) or [duos][rows_alloc] (intra-task);
+                               // after a packed NW-align fill it holds the last true column (read by the traceback)
     uint16_t *dirs;            // general kernel: [segs][rows_alloc][slots] half-words, 2 bits per cell, 8 cells each
     uint4 *fdirs;              // packed kernel:  [strip][row pair][group][duos], see va_fast.cuh
                                // (separate regions: one chunk can hold pairs of both kinds)
-    uint32_t *hrow;            // packed NW align: [ref_length][duos] last valid row of the matrix (H + gap_ref)
+    uint32_t *hrow;            // packed NW align: [ref_length][duos] last valid matrix row (H + gap_ref)
     int16_t *scores;           // [n]
     int16_t *end_cell;         // [n][2]
     // traceback outputs

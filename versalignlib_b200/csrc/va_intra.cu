@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(128) fill_intra_sw_score_kernel(ChunkGeom g, C
     const uint8_t *cread = reinterpret_cast<const uint8_t *>(b.code_reads) + (size_t)slot_a * 16;
     const uint8_t *cref = reinterpret_cast<const uint8_t *>(b.code_refs);
     const uint32_t chunk_stride = (uint32_t)g.slots * 16u;
-    uint32_t *bnd = reinterpret_cast<uint32_t *>(b.boundary) + (size_t)duo * g.rows_alloc;  // this warp's boundary column
+    uint32_t *bnd = b.fboundary + (size_t)duo * g.rows_alloc;  // this warp's boundary column
 
     uint32_t best = 0;
     const int pass_cols = 32 * TW;

@@ -7,6 +7,8 @@
 //                      kernel (DefaultKernel.cpp:83-389; SSEKernel.cpp:226-727,1007-1315;
 //                      scoring_kernels.cl, alignment_kernels.cl:38-135,239-364)
 // (the traceback kernel is in va_traceback.cu)
+#include <climits>
+
 #include "va_internal.h"
 #include "va_device.cuh"
 #include "va_fast.cuh"
@@ -43,6 +45,15 @@ __global__ void __launch_bounds__(128) fill_general_kernel(ChunkGeom g, ChunkBuf
         int best = 0, best_i = 0, best_j = 0;  // SW: first strictly greater cell in row-major order
         int border = 0;                        // NW score: max(0, last column, last row)
         int row_max = m * gF, row_idx = 0;     // NW align: arg-max of the last valid row, column 0 first
+        // NW align on a trimmed ref (columns past n are pad columns that only score 0, not filled):
+        // the end-cell rule scans them too (DefaultKernel.cpp:352-355).  While both gaps are <= 0 a pad
+        // cell of the last valid row can exceed the best true cell only by carrying a value of the last
+        // true column down a zero-score diagonal, so it is enough to know the maximum of that column over
+        // the min(pad columns, rows) matrix rows above the last one ("NW end cell").
+        const int pad_cols = MODE == MODE_NW_ALIGN ? g.ref_length - n : 0;
+        const int pad_reach = min(pad_cols, m);           // matrix rows m-1 .. m-pad_reach feed the pad cells
+        int col_max = (pad_reach == m && m > 0) ? 0 : INT_MIN;  // matrix row 0 is 0 when it is in reach
+        if (MODE == MODE_NW_ALIGN && n == 0 && pad_reach > 0) col_max = max(col_max, (m - pad_reach) * gF);  // column 0 is i*gF
         const uint32_t *rcodes = reinterpret_cast<const uint32_t *>(b.code_reads);
 
         for (int c0 = 0; c0 < n; c0 += GEN_TW) {
@@ -105,6 +116,8 @@ __global__ void __launch_bounds__(128) fill_general_kernel(ChunkGeom g, ChunkBuf
                             row_max = h;
                             row_idx = c0 + k;
                         }
+                        // last true column, matrix rows m-pad_reach .. m-1  (DP rows i = matrix row - 1)
+                        if (c0 + k == n - 1 && i < m - 1 && i >= m - 1 - pad_reach) col_max = max(col_max, h);
                     }
                     diag = up;
                     H[k] = h;
@@ -131,7 +144,8 @@ __global__ void __launch_bounds__(128) fill_general_kernel(ChunkGeom g, ChunkBuf
         } else {
             // DefaultKernel.cpp:381-387: (max_read_pos, min(max_ref_pos, arg-max of that row))
             b.end_cell[2 * pair] = (int16_t)(m - 1);
-            b.end_cell[2 * pair + 1] = (int16_t)min((int)meta.max_ref_pos, row_idx);
+            const bool pad_wins = pad_cols > 0 && col_max > row_max;  // arg-max lies past max_ref_pos: clipped to it
+            b.end_cell[2 * pair + 1] = (int16_t)(pad_wins ? (int)meta.max_ref_pos : min((int)meta.max_ref_pos, row_idx));
             b.scores[pair] = (int16_t)row_max;
         }
     }

@@ -120,7 +120,10 @@ __global__ void __launch_bounds__(128) meta_kernel(ChunkGeom g, const uint8_t *_
             // rows below the first invalid read character are never consulted; the end-cell rule scans
             // the whole padded width of the last valid row
             m.rows = (int16_t)(m.max_read_pos + 1);
-            m.cols = (int16_t)g.ref_length;
+            // With both gaps <= 0 the pad columns need not be filled: the fill/traceback kernels derive
+            // whether the padded arg-max would land in them.  Trailing N of the ref stay inside the
+            // sweep when the policy counts them as valid (max_ref_pos points past the last ACGT base).
+            m.cols = trim ? (int16_t)max((int)m.true_cols, (int)m.max_ref_pos + 1) : (int16_t)g.ref_length;
         } else if (trim) {
             // trailing rows/columns that can only score 0 never change the result while both gap
             // scores are <= 0 (SURVEY.md A.1/A.2 "padding is neutral")

@@ -11,6 +11,8 @@
 //         four characters per 32-bit store, so every output sector is written whole.
 // The packed fill kernel leaves NW's end-cell decision (arg-max of the last valid row,
 // DefaultKernel.cpp:352-355,381-387) to this kernel: `hrow` holds that row.
+#include <climits>
+
 #include "va_fast.cuh"
 
 namespace va {
@@ -91,7 +93,18 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
             }
         }
         i = rows - 1;
-        j = min((int)meta.max_ref_pos, idx);
+        // Pad columns (past `cols`, never filled) take part in the arg-max of the reference.  With both
+        // gaps <= 0 one of them beats the best true cell exactly when a value of the last true column in
+        // one of the min(pad columns, rows) matrix rows above comes down a zero-score diagonal; the
+        // arg-max is then past max_ref_pos and gets clipped to it (DefaultKernel.cpp:387).
+        const int pad_cols = g.ref_length - cols, reach = min(pad_cols, rows);
+        int col_max = (reach == rows && rows > 0) ? 0 : INT_MIN;  // matrix row 0
+        if (reach > 0) {
+            const uint32_t *bl = b.fboundary + duo;  // last true column, H + gap_read
+            for (int r = rows - 2; r >= rows - 1 - reach && r >= 0; --r)
+                col_max = max(col_max, (int)(int16_t)(bl[(size_t)r * g.duos] >> lane_shift) - sc.gap_read);
+        }
+        j = (pad_cols > 0 && col_max > best) ? (int)meta.max_ref_pos : min((int)meta.max_ref_pos, idx);
         b.end_cell[2 * pair] = (int16_t)i;
         b.end_cell[2 * pair + 1] = (int16_t)j;
         b.scores[pair] = (int16_t)best;
