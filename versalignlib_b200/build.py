@@ -30,7 +30,7 @@ NVCC_FLAGS = [
     "-I", INCLUDE, "-I", CSRC,
 ]
 
-CUDA_SOURCES = ["va_prep.cu", "va_kernels.cu", "va_fast.cu", "va_intra.cu", "va_traceback.cu", "va_cabi.cu", "cuda_kernel_plugin.cpp"]
+CUDA_SOURCES = ["va_prep.cu", "va_kernels.cu", "va_fast.cu", "va_nw.cu", "va_intra.cu", "va_traceback.cu", "va_cabi.cu", "cuda_kernel_plugin.cpp"]
 CUDA_HEADERS = ["va_device.cuh", "va_fast.cuh", "va_internal.h"]
 
 

@@ -214,7 +214,7 @@ struct PinBuf {
 
 // Device workspace of one chunk in flight.
 struct ChunkSlot {
-    DevBuf raw_reads, raw_refs, code_reads, code_refs, meta, pair_of, prep_scratch, boundary, dirs, hrow, queue, scores, end_cell, aln_read, aln_ref, start;
+    DevBuf raw_reads, raw_refs, code_reads, code_refs, row_idx, meta, pair_of, prep_scratch, boundary, dirs, hrow, queue, scores, end_cell, aln_read, aln_ref, start;
     PinBuf h_reads, h_refs, h_scores, h_end_cell, h_aln_read, h_aln_ref, h_start;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_done = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
@@ -224,7 +224,7 @@ struct ChunkSlot {
     bool busy = false;
 
     void release() {
-        DevBuf *d[] = {&raw_reads, &raw_refs, &code_reads, &code_refs, &meta, &pair_of, &prep_scratch, &boundary, &dirs, &hrow, &queue, &scores, &end_cell, &aln_read, &aln_ref, &start};
+        DevBuf *d[] = {&raw_reads, &raw_refs, &code_reads, &code_refs, &row_idx, &meta, &pair_of, &prep_scratch, &boundary, &dirs, &hrow, &queue, &scores, &end_cell, &aln_read, &aln_ref, &start};
         for (auto *b : d) b->release();
         PinBuf *h[] = {&h_reads, &h_refs, &h_scores, &h_end_cell, &h_aln_read, &h_aln_ref, &h_start};
         for (auto *b : h) b->release();
@@ -293,7 +293,7 @@ struct Shape {
     size_t gen_dir_row_bytes() const { return (size_t)segs * 2; }
     size_t dir_row_bytes() const { return gen_dir_row_bytes() + fast_dirs_bytes_per_row_per_slot(ref_length); }
     size_t per_pair_workspace() const {
-        size_t b = (size_t)(read_chunks + ref_chunks) * 32 + 2 * sizeof(PairMeta) + 40 + (size_t)rows_alloc * 6;
+        size_t b = (size_t)(read_chunks + ref_chunks) * 32 + (size_t)read_chunks * 8 + 2 * sizeof(PairMeta) + 40 + (size_t)rows_alloc * 6;
         if (align) {
             b += dir_row_bytes() * (rows_alloc + 1) + (size_t)ref_length * 4;
             const size_t qw = traceback_queue_words(read_length, ref_length);
@@ -358,6 +358,7 @@ int reserve_slot(ChunkSlot &s, const Shape &sh, int cap_pairs, bool pinned) {
     if ((rc = s.raw_refs.reserve((size_t)cap_pairs * sh.ref_length + 16))) return rc;
     if ((rc = s.code_reads.reserve(slots * sh.read_chunks * 16 + 16))) return rc;
     if ((rc = s.code_refs.reserve(slots * sh.ref_chunks * 16 + 16))) return rc;
+    if ((rc = s.row_idx.reserve(slots / 2 * sh.read_chunks * 16 + 16))) return rc;
     if ((rc = s.meta.reserve(slots * sizeof(PairMeta)))) return rc;
     if ((rc = s.pair_of.reserve(slots * 4))) return rc;
     if ((rc = s.prep_scratch.reserve(prep_scratch_bytes((int)slots, sh.read_length, sh.ref_length)))) return rc;
@@ -422,6 +423,7 @@ int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int
     b.raw_refs = raw_refs;
     b.code_reads = (uint4 *)ws.code_reads.p;
     b.code_refs = (uint4 *)ws.code_refs.p;
+    b.row_idx = (uint4 *)ws.row_idx.p;
     b.meta = (PairMeta *)ws.meta.p;
     b.pair_of = (int32_t *)ws.pair_of.p;
     b.boundary = (int32_t *)ws.boundary.p;

@@ -345,18 +345,25 @@ bool fits8(int v) { return v >= -128 && v <= 127; }
 bool fast_scoring_ok(int mode, int policy, const Scoring &sc, int read_length, int ref_length) {
     const bool align = mode == MODE_NW_ALIGN || mode == MODE_SW_ALIGN;
     if (align && policy != 0) return false;  // SSE/AVX pointer rule: general kernel
-    const int off = align ? sc.gap_ref : 0;
-    if (!fits8(sc.match - off) || !fits8(sc.mismatch - off) || !fits8(-off)) return false;
     int mx = 1;
     for (int v : {sc.match, sc.mismatch, sc.gap_read, sc.gap_ref}) mx = max(mx, v < 0 ? -v : v);
-    if (mode == MODE_SW_SCORE || mode == MODE_SW_ALIGN) {
-        // every cell is floored at 0: values stay within [-mx, match * min(rows, cols)]
-        const long long top = (long long)(sc.match > 0 ? sc.match : 0) * (read_length < ref_length ? read_length : ref_length);
-        // SW align packs (value + bias) * 32 + column into a 16-bit lane: value + 128 + gap must stay below 1024
-        if (mode == MODE_SW_ALIGN) return top + 2 * 128 < 1024 && mx <= 100;
-        return top + mx <= 32000 && mx <= 8000;
+    if (mode == MODE_NW_SCORE || mode == MODE_NW_ALIGN) {
+        // shifted recurrence (va_nw.cu): gap scores <= 0, table entries s - gap_ref - gap_read, and
+        // 0 <= V <= match*min(rows,cols) + |gap_ref|*rows + |gap_read|*cols
+        if (sc.gap_read > 0 || sc.gap_ref > 0) return false;
+        const int off = sc.gap_ref + sc.gap_read;
+        if (!fits8(sc.match - off) || !fits8(sc.mismatch - off) || !fits8(-off)) return false;
+        const long long top = (long long)(sc.match > 0 ? sc.match : 0) * (read_length < ref_length ? read_length : ref_length) -
+                              (long long)sc.gap_ref * (read_length + 2) - (long long)sc.gap_read * (ref_length + 2);
+        return top + 256 <= 32000;
     }
-    return (long long)(read_length + ref_length + 4) * mx <= 32000;
+    const int off = align ? sc.gap_ref : 0;
+    if (!fits8(sc.match - off) || !fits8(sc.mismatch - off) || !fits8(-off)) return false;
+    // every cell is floored at 0: values stay within [-mx, match * min(rows, cols)]
+    const long long top = (long long)(sc.match > 0 ? sc.match : 0) * (read_length < ref_length ? read_length : ref_length);
+    // SW align packs (value + bias) * 32 + column into a 16-bit lane: value + 128 + gap must stay below 1024
+    if (mode == MODE_SW_ALIGN) return top + 2 * 128 < 1024 && mx <= 100;
+    return top + mx <= 32000 && mx <= 8000;
 }
 
 int fast_pick_tw(int mode, int ref_length) {
@@ -395,7 +402,8 @@ size_t fast_dirs_bytes_per_row_per_slot(int ref_length) {
 FastConsts make_fast_consts(int mode, const Scoring &sc) {
     FastConsts fc{};
     const bool align = mode == MODE_NW_ALIGN || mode == MODE_SW_ALIGN;
-    const int off = align ? sc.gap_ref : 0;
+    const bool nw = mode == MODE_NW_SCORE || mode == MODE_NW_ALIGN;  // shifted recurrence, va_nw.cu
+    const int off = nw ? sc.gap_ref + sc.gap_read : align ? sc.gap_ref : 0;
     for (int c = 0; c < 8; ++c) fc.tab[c] = table_word(c, sc.match, sc.mismatch, off);
     fc.gF = sc.gap_ref;
     fc.gR = sc.gap_read;
@@ -420,8 +428,8 @@ int launch_fill_fast(const ChunkGeom &g, const ChunkBuffers &b, int mode, const 
     const FastConsts fc = make_fast_consts(mode, sc);
     switch (mode) {
         case MODE_SW_SCORE: launch_tw<MODE_SW_SCORE>(g, b, fc, stream); break;
-        case MODE_NW_SCORE: launch_tw<MODE_NW_SCORE>(g, b, fc, stream); break;
-        case MODE_NW_ALIGN: launch_tw<MODE_NW_ALIGN>(g, b, fc, stream); break;
+        case MODE_NW_SCORE:
+        case MODE_NW_ALIGN: return launch_fill_nw(g, b, mode, fc, stream);
         case MODE_SW_ALIGN: launch_tw<MODE_SW_ALIGN>(g, b, fc, stream); break;
         default: return 0;
     }

@@ -66,6 +66,8 @@ struct ChunkBuffers {
     const uint8_t *raw_refs;   // [n][ref_length]
     uint4 *code_reads;         // [read_chunks][slots]
     uint4 *code_refs;          // [ref_chunks][slots]
+    uint4 *row_idx;            // [read_chunks][duos]: per matrix row 6*code(slot 2u) + code(slot 2u+1), 16 rows per word
+                               // (the packed NW kernels' index into their table of score-table pairs)
     PairMeta *meta;            // [slots]
     int32_t *pair_of;          // [slots] pair (position in the caller's batch) computed in this slot, -1 = padding
     int32_t *boundary;         // general kernel: [rows_alloc][slots] right edge of the previous column strip
@@ -97,6 +99,8 @@ int fast_pick_tw(int mode, int ref_length);
 size_t fast_dirs_bytes_per_row_per_slot(int ref_length);
 FastConsts make_fast_consts(int mode, const Scoring &sc);
 int launch_fill_fast(const ChunkGeom &g, const ChunkBuffers &b, int mode, const Scoring &sc, cudaStream_t stream);
+// packed kernels of the NW modes, shifted recurrence (va_nw.cu); reached through launch_fill_fast
+int launch_fill_nw(const ChunkGeom &g, const ChunkBuffers &b, int mode, const FastConsts &fc, cudaStream_t stream);
 // intra-task (warp per pair-of-pairs) kernel for few, long pairs (va_intra.cu)
 bool intra_preferred(int mode, int n_pairs, int read_length, int ref_length, int sm_count);
 int launch_fill_intra(const ChunkGeom &g, const ChunkBuffers &b, int mode, const FastConsts &fc, cudaStream_t stream);

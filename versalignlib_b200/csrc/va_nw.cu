@@ -1,0 +1,284 @@
+// va_nw.cu -- the packed inter-task fill kernels of the library's "Needleman-Wunsch" modes
+// (score: DefaultKernel.cpp:140-202, SSEKernel.cpp:1152-1315; fill with pointers:
+// DefaultKernel.cpp:282-389), two pairs per thread in the two s16 lanes like va_fast.cu.
+//
+// What is different from the SW kernels: nothing in these modes clamps a cell at 0, so the whole
+// matrix can be computed in SHIFTED coordinates
+//        V(I,J) = H(I,J) - gap_ref*I - gap_read*J          (I,J = matrix row / column, 0-based)
+// in which both gap moves cost nothing:
+//        V(I,J) = max( V(I-1,J-1) + (s - gap_ref - gap_read),  V(I-1,J),  V(I,J-1) ).
+// The three candidates of a cell carry the same shift, so every comparison the reference makes
+// (and with it every traceback pointer) is unchanged, while the cell update shrinks to
+//        score:  t = max(up, left);  V = max(diag + s', t)                 2 DPX instructions
+//        align:  t = max(up, left) -> UP>=LEFT;  d = diag + s';  V = max(d, t) -> DIAG>=rest   3
+// (+ 1 PRMT for s'), against 3 and 4 for the unshifted recurrence: "H + gap" never has to be
+// formed, and the value a cell hands to its right neighbour and to the row below is one register.
+// With both gap scores <= 0 (required here; otherwise the general kernel runs) V is non-negative and
+// non-decreasing along rows and columns, which bounds the 16-bit range check.
+// The matrix borders un-shift what they hand out: NW score's last row / last column maxima, the
+// `hrow` row and the last-true-column values the traceback kernel reads (va_traceback.cu).
+#include <type_traits>
+
+#include "va_fast.cuh"
+
+namespace va {
+
+namespace {
+
+constexpr uint32_t NEG2 = 0x80008000u;  // (-32768, -32768): identity of the packed max
+
+__device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b) { return __viaddmax_s16x2(a, b, NEG2); }
+__device__ __forceinline__ uint32_t pk(int v) { return ((uint32_t)v & 0xFFFFu) * 0x00010001u; }
+
+// Ampere-style asynchronous global -> shared copies (LDGSTS): the data never passes through a register.
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// EDGE (align only): the duo's ref is padded (cols < ref_length); the last true column is kept for the
+// traceback kernel's pad-column rule.  Separate instantiation, launched next to the plain one, each
+// taking only its own kind of duo.
+template <bool ALIGN, int TW, bool EDGE>
+__global__ void __launch_bounds__(128, 4) fill_nw_kernel(ChunkGeom g, ChunkBuffers b, FastConsts fc) {
+    constexpr int NG = (TW + 15) / 16;
+    constexpr int MODE = ALIGN ? MODE_NW_ALIGN : MODE_NW_SCORE;
+
+    __shared__ uint2 s_T2[256];              // [6*code_a + code_b] -> the two lanes' 4-entry score tables (36 used)
+    __shared__ uint4 s_idx[3][128];           // staged row indices: 16 rows per thread and buffer
+    __shared__ uint32_t s_bnd[3][16][128];    // staged right edge of the previous strip, [row][thread]
+    for (int t = threadIdx.x; t < 256; t += 128) s_T2[t] = t < 36 ? make_uint2(fc.tab[t / 6], fc.tab[t % 6]) : make_uint2(0u, 0u);
+    __syncthreads();
+
+    const int duo = blockIdx.x * blockDim.x + threadIdx.x;
+    const int slot_a = 2 * duo, slot_b = slot_a + 1;
+    unsigned long long cells = 0;
+    bool mine = false;
+    PairMeta ma, mb;
+    if (slot_b < g.n) {
+        ma = b.meta[slot_a];
+        mb = b.meta[slot_b];
+        mine = duo_is_fast(g, MODE, slot_a, ma, mb);
+        if (ALIGN) mine = mine && (EDGE == (g.ref_length > ma.cols));
+    }
+    if (mine) {
+        const int m = max((int)ma.rows, (int)mb.rows), n = ma.cols;
+        cells = ((unsigned long long)ma.rows + (unsigned long long)mb.rows) * (unsigned long long)n;
+        const int ngF = -fc.gF, ngR = -fc.gR;  // both >= 0
+        const uint32_t gF2 = fc.gF2, ngF2 = pk(ngF);
+        const uint8_t *cref = reinterpret_cast<const uint8_t *>(b.code_refs);
+        uint32_t *bnd = b.fboundary;
+        uint4 *dirs = b.fdirs;
+
+        uint32_t best = 0;  // score mode: max(0, last column, last row) of H
+        const int nstrips = (n + TW - 1) / TW;
+        for (int s = 0; s < nstrips; ++s) {
+            const int c0 = s * TW;
+            const bool first = s == 0, last = s == nstrips - 1;
+            uint32_t sel[TW], H[TW];
+#pragma unroll
+            for (int k = 0; k < TW; ++k) {
+                const int col = min(c0 + k, n - 1);  // columns past n repeat the last one; their cells are never used
+                const size_t off = ((size_t)(col >> 4) * g.slots) * 16 + (col & 15);
+                const uint32_t fa = cref[off + (size_t)slot_a * 16], fb = cref[off + (size_t)slot_b * 16];
+                // nibbles: lane A low byte <- table a[fa], high byte <- its sign; lane B from table b (bytes 4..7)
+                sel[k] = fa | ((fa | 8u) << 4) | ((fb | 4u) << 8) | ((fb | 12u) << 12);
+                H[k] = pk(ngR * (c0 + k + 1));  // V(0,J) = -gap_read*J: matrix row 0 is 0
+            }
+            uint32_t diag_next = pk(ngR * c0);  // V(0, c0)
+            // matrix column 0 in shifted form: H(I,0) = I*gap_ref -> 0 (align); H(I,0) = 0 -> -gap_ref*I (score)
+            uint32_t col0 = ALIGN ? 0u : ngF2;
+            // score mode, last strip: un-shift of the last column, gap_ref*I + gap_read*n
+            uint32_t corr = pk(fc.gR * n + fc.gF);
+            const int kv = min(TW, n - c0);  // valid columns of this strip
+            const bool full = kv == TW;
+
+            // One sweep over all read rows of this strip.  PARTIAL (only ever the last strip) guards the
+            // few places that must tell the columns past n apart; full strips run unguarded.
+            //
+            // Per-row inputs (the row's pair of substitution tables, the previous strip's right edge) never
+            // make a row wait on HBM: they are staged 16 rows ahead with cp.async into this thread's own
+            // shared-memory slots -- no registers held across the loop, nothing for the scheduler to sink
+            // next to the consumer -- one commit group per 16-row chunk, double buffered.
+            auto sweep = [&](auto partial_tag) {
+                constexpr bool PARTIAL = decltype(partial_tag)::value;
+                uint32_t *bp = bnd + duo;
+                uint4 *dp = dirs + fast_dir_index(g, s, 0, 0, duo);
+                const int nchunks = (m + 15) >> 4;
+                auto stage = [&](int c, int buf) {
+                    cp_async16(&s_idx[buf][threadIdx.x], b.row_idx + (size_t)c * g.duos + duo);
+                    if (!first) {
+                        const uint32_t *src = bnd + (size_t)(c * 16) * g.duos + duo;
+#pragma unroll
+                        for (int r = 0; r < 16; ++r)
+                            if (c * 16 + r < m) cp_async4(&s_bnd[buf][r][threadIdx.x], src + (size_t)r * g.duos);
+                    }
+                    cp_async_commit();
+                };
+                // one matrix row of this strip; align returns the row's two direction planes per group
+                auto do_row = [&](const uint2 tt, uint32_t left_in, uint2(&w)[NG]) {
+                    const uint32_t ta = tt.x, tb = tt.y;
+                    uint32_t left = first ? col0 : left_in;
+                    if (!ALIGN && first) col0 = add2(col0, ngF2);
+                    uint32_t edge = 0;
+                    uint32_t diag = diag_next;
+                    diag_next = left;  // V(I, c0) is the next row's diagonal
+                    float p1l[NG], p1h[NG], p2l[NG], p2h[NG];
+#pragma unroll
+                    for (int q = 0; q < NG; ++q) p1l[q] = p1h[q] = p2l[q] = p2h[q] = 8388608.0f;
+#pragma unroll
+                    for (int k = 0; k < TW; ++k) {
+                        const uint32_t sub = prmt(ta, tb, sel[k]);  // s - gap_ref - gap_read
+                        const uint32_t up = H[k];
+                        uint32_t h;
+                        if (ALIGN) {
+                            bool dl, dh, ul, uh;
+                            const uint32_t t = __vibmax_s16x2(up, left, &uh, &ul);  // up >= left : UP before LEFT
+                            const uint32_t d = add2(diag, sub);
+                            h = __vibmax_s16x2(d, t, &dh, &dl);                     // diag >= max(up,left) : DIAG first
+                            const float bit = (float)(1u << (k & 15));
+                            if (dl) p1l[k >> 4] += bit;
+                            if (dh) p1h[k >> 4] += bit;
+                            if (ul) p2l[k >> 4] += bit;
+                            if (uh) p2h[k >> 4] += bit;
+                        } else {
+                            h = __viaddmax_s16x2(diag, sub, __vmaxs2(up, left));
+                        }
+                        if (PARTIAL && k == kv - 1) edge = h;  // last true column of a partial last strip
+                        left = h;
+                        H[k] = h;
+                        diag = up;
+                    }
+                    // right edge of the strip for the next strip; align also keeps the LAST true column (the
+                    // traceback kernel needs it to decide whether the padded arg-max lands in a pad column)
+                    if (!last) *bp = left;
+                    else if (ALIGN && EDGE) *bp = PARTIAL ? edge : left;
+                    bp += g.duos;
+                    if (!ALIGN && last) {  // last column of this row, un-shifted (SSEKernel.cpp:1285-1291)
+                        best = __viaddmax_s16x2(PARTIAL ? edge : left, corr, best);
+                        corr = add2(corr, gF2);
+                    }
+                    if (ALIGN) {
+#pragma unroll
+                        for (int q = 0; q < NG; ++q) {
+                            w[q].x = __byte_perm(__float_as_uint(p1l[q]), __float_as_uint(p1h[q]), 0x5410);
+                            w[q].y = __byte_perm(__float_as_uint(p2l[q]), __float_as_uint(p2h[q]), 0x5410);
+                        }
+                    }
+                };
+                // Software pipeline on top of the staging: the tables and the left edge of the two rows of an
+                // iteration are fetched from shared memory during the iteration before, so chunks c and c+1
+                // must both have landed while chunk c is swept (three buffers, chunk c+2 in flight).
+                stage(0, 0);
+                if (nchunks > 1) stage(1, 1);
+                else cp_async_commit();
+                cp_async_wait<1>();  // chunk 0
+                const uint8_t *ib = reinterpret_cast<const uint8_t *>(&s_idx[0][threadIdx.x]);
+                const uint32_t *lb = &s_bnd[0][0][threadIdx.x];
+                uint2 nt0 = s_T2[ib[0]], nt1 = s_T2[ib[1]];
+                uint32_t nl0 = lb[0], nl1 = lb[128];
+                int buf = 0;
+                for (int c = 0; c < nchunks; ++c) {
+                    const int buf1 = buf == 2 ? 0 : buf + 1, buf2 = buf1 == 2 ? 0 : buf1 + 1;
+                    if (c + 2 < nchunks) stage(c + 2, buf2);
+                    else cp_async_commit();
+                    cp_async_wait<1>();  // chunk c+1 has landed; only the chunk just requested may be in flight
+                    const uint8_t *ip = reinterpret_cast<const uint8_t *>(&s_idx[buf][threadIdx.x]) + 2;
+                    const uint32_t *lp = &s_bnd[buf][2][threadIdx.x];
+                    const uint8_t *ip_next = reinterpret_cast<const uint8_t *>(&s_idx[buf1][threadIdx.x]);
+                    const uint32_t *lp_next = &s_bnd[buf1][0][threadIdx.x];
+                    const int rend = min(16, m - c * 16);
+                    // two rows per iteration: their direction words leave as one 16-byte store per group
+                    int r = 0;
+                    for (; r + 1 < rend; r += 2, dp += (size_t)NG * g.duos) {
+                        const uint2 t0 = nt0, t1 = nt1;
+                        const uint32_t l0 = nl0, l1 = nl1;
+                        {  // rows r+2, r+3 (the first two rows of the next chunk after rows 14, 15)
+                            const uint8_t *pi = r == 14 ? ip_next : ip;
+                            const uint32_t *pl = r == 14 ? lp_next : lp;
+                            nt0 = s_T2[pi[0]];
+                            nt1 = s_T2[pi[1]];
+                            nl0 = pl[0];
+                            nl1 = pl[128];
+                            ip += 2;
+                            lp += 256;
+                        }
+                        uint2 w0[NG], w1[NG];
+                        do_row(t0, l0, w0);
+                        do_row(t1, l1, w1);
+                        if (ALIGN) {
+#pragma unroll
+                            for (int q = 0; q < NG; ++q) dp[(size_t)q * g.duos] = make_uint4(w0[q].x, w0[q].y, w1[q].x, w1[q].y);
+                        }
+                    }
+                    if (r < rend) {  // odd row count (last chunk only): the last word holds one row
+                        uint2 w0[NG];
+                        do_row(nt0, nl0, w0);
+                        if (ALIGN) {
+#pragma unroll
+                            for (int q = 0; q < NG; ++q) dp[(size_t)q * g.duos] = make_uint4(w0[q].x, w0[q].y, 0u, 0u);
+                        }
+                    }
+                    buf = buf1;
+                }
+                cp_async_wait<0>();
+            };
+            // align without a padded ref never looks at the cells past n: its last strip runs unguarded too
+            if constexpr (ALIGN && !EDGE) {
+                sweep(std::false_type{});
+            } else {
+                if (full) sweep(std::false_type{});
+                else sweep(std::true_type{});
+            }
+            if (ALIGN) {  // the row the end-cell rule scans (DefaultKernel.cpp:352-355,381-387), still shifted
+#pragma unroll
+                for (int k = 0; k < TW; ++k)
+                    if (c0 + k < n) b.hrow[(size_t)(c0 + k) * g.duos + duo] = H[k];
+            } else {  // whole last row (SSEKernel.cpp:1302-1310), un-shifted; column 0 is 0 and `best` starts at 0
+                const int base = fc.gF * m + fc.gR * (c0 + 1);
+#pragma unroll
+                for (int k = 0; k < TW; ++k)
+                    if (c0 + k < n) best = __viaddmax_s16x2(H[k], pk(base + fc.gR * k), best);
+            }
+        }
+        if (!ALIGN) {
+            b.scores[b.pair_of[slot_a]] = (int16_t)(best & 0xFFFF);
+            b.scores[b.pair_of[slot_b]] = (int16_t)(best >> 16);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) cells += __shfl_xor_sync(0xffffffffu, cells, o);
+    if ((threadIdx.x & 31) == 0 && cells) atomicAdd(b.cell_count, cells);
+}
+
+template <bool ALIGN, int TW>
+void launch_one(const ChunkGeom &g, const ChunkBuffers &b, const FastConsts &fc, cudaStream_t stream) {
+    const int threads = 128;
+    const int duos = (g.n + 1) / 2;
+    const int blocks = (duos + threads - 1) / threads;
+    fill_nw_kernel<ALIGN, TW, false><<<blocks, threads, 0, stream>>>(g, b, fc);
+    // align: the padded-ref duos (nothing to do on an unpadded batch)
+    if constexpr (ALIGN) fill_nw_kernel<ALIGN, TW, true><<<blocks, threads, 0, stream>>>(g, b, fc);
+}
+
+}  // namespace
+
+int launch_fill_nw(const ChunkGeom &g, const ChunkBuffers &b, int mode, const FastConsts &fc, cudaStream_t stream) {
+    const bool align = mode == MODE_NW_ALIGN;
+    if (g.fast_tw == 30) {
+        if (align) launch_one<true, 30>(g, b, fc, stream);
+        else launch_one<false, 30>(g, b, fc, stream);
+    } else {
+        if (align) launch_one<true, 32>(g, b, fc, stream);
+        else launch_one<false, 32>(g, b, fc, stream);
+    }
+    return 1;
+}
+
+}  // namespace va

@@ -172,8 +172,16 @@ __global__ void __launch_bounds__(256) encode_kernel(ChunkGeom g, ChunkBuffers b
             b.pair_of[slot] = pair;
         }
         // scratch is [chunk][pair]: for a batch that keeps its order both sides are coalesced
-        if (c < g.read_chunks) b.code_reads[(size_t)c * g.slots + slot] = codes_pair_reads[(size_t)c * g.slots + pair];
-        else b.code_refs[(size_t)(c - g.read_chunks) * g.slots + slot] = codes_pair_refs[(size_t)(c - g.read_chunks) * g.slots + pair];
+        if (c < g.read_chunks) {
+            const uint4 ca = codes_pair_reads[(size_t)c * g.slots + pair];
+            b.code_reads[(size_t)c * g.slots + slot] = ca;
+            if (b.row_idx && (slot & 1) == 0) {
+                // the duo's row index: 6*code_a + code_b per byte (no carries: codes are <= 5)
+                uint4 cb = make_uint4(0x05050505u, 0x05050505u, 0x05050505u, 0x05050505u);
+                if (slot + 1 < g.n) cb = codes_pair_reads[(size_t)c * g.slots + order[slot + 1]];
+                b.row_idx[(size_t)c * g.duos + (slot >> 1)] = make_uint4(ca.x * 6u + cb.x, ca.y * 6u + cb.y, ca.z * 6u + cb.z, ca.w * 6u + cb.w);
+            }
+        } else b.code_refs[(size_t)(c - g.read_chunks) * g.slots + slot] = codes_pair_refs[(size_t)(c - g.read_chunks) * g.slots + pair];
     }
 }
 

@@ -81,12 +81,12 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
     // ---- end cell ----------------------------------------------------------------------
     int i, j;
     if (packed && NW) {
-        // first strictly greater column of matrix row `rows`, starting from column 0 = rows*gap_ref;
-        // hrow holds H + gap_ref
+        // first strictly greater column of matrix row `rows`, starting from column 0 = rows*gap_ref.
+        // hrow holds that row in the fill kernel's shifted form V = H - gap_ref*I - gap_read*J (va_nw.cu)
         int best = rows * gap_ref, idx = 0;
         const uint32_t *hr = b.hrow + duo;
         for (int c = 0; c < cols; ++c) {
-            const int h = (int)(int16_t)(hr[(size_t)c * g.duos] >> lane_shift) - gap_ref;
+            const int h = (int)(int16_t)(hr[(size_t)c * g.duos] >> lane_shift) + rows * gap_ref + (c + 1) * sc.gap_read;
             if (h > best) {
                 best = h;
                 idx = c;
@@ -100,9 +100,9 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
         const int pad_cols = g.ref_length - cols, reach = min(pad_cols, rows);
         int col_max = (reach == rows && rows > 0) ? 0 : INT_MIN;  // matrix row 0
         if (reach > 0) {
-            const uint32_t *bl = b.fboundary + duo;  // last true column, H + gap_read
+            const uint32_t *bl = b.fboundary + duo;  // last true column (matrix column `cols`), shifted
             for (int r = rows - 2; r >= rows - 1 - reach && r >= 0; --r)
-                col_max = max(col_max, (int)(int16_t)(bl[(size_t)r * g.duos] >> lane_shift) - sc.gap_read);
+                col_max = max(col_max, (int)(int16_t)(bl[(size_t)r * g.duos] >> lane_shift) + (r + 1) * gap_ref + cols * sc.gap_read);
         }
         j = (pad_cols > 0 && col_max > best) ? (int)meta.max_ref_pos : min((int)meta.max_ref_pos, idx);
         b.end_cell[2 * pair] = (int16_t)i;
