@@ -214,7 +214,7 @@ struct PinBuf {
 
 // Device workspace of one chunk in flight.
 struct ChunkSlot {
-    DevBuf raw_reads, raw_refs, code_reads, code_refs, row_idx, meta, pair_of, prep_scratch, boundary, dirs, hrow, queue, scores, end_cell, aln_read, aln_ref, start;
+    DevBuf raw_reads, raw_refs, code_reads, code_refs, row_idx, solo_list, meta, pair_of, prep_scratch, boundary, dirs, hrow, queue, scores, end_cell, aln_read, aln_ref, start;
     PinBuf h_reads, h_refs, h_scores, h_end_cell, h_aln_read, h_aln_ref, h_start;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_done = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
@@ -224,7 +224,7 @@ struct ChunkSlot {
     bool busy = false;
 
     void release() {
-        DevBuf *d[] = {&raw_reads, &raw_refs, &code_reads, &code_refs, &row_idx, &meta, &pair_of, &prep_scratch, &boundary, &dirs, &hrow, &queue, &scores, &end_cell, &aln_read, &aln_ref, &start};
+        DevBuf *d[] = {&raw_reads, &raw_refs, &code_reads, &code_refs, &row_idx, &solo_list, &meta, &pair_of, &prep_scratch, &boundary, &dirs, &hrow, &queue, &scores, &end_cell, &aln_read, &aln_ref, &start};
         for (auto *b : d) b->release();
         PinBuf *h[] = {&h_reads, &h_refs, &h_scores, &h_end_cell, &h_aln_read, &h_aln_ref, &h_start};
         for (auto *b : h) b->release();
@@ -359,6 +359,7 @@ int reserve_slot(ChunkSlot &s, const Shape &sh, int cap_pairs, bool pinned) {
     if ((rc = s.code_reads.reserve(slots * sh.read_chunks * 16 + 16))) return rc;
     if ((rc = s.code_refs.reserve(slots * sh.ref_chunks * 16 + 16))) return rc;
     if ((rc = s.row_idx.reserve(slots / 2 * sh.read_chunks * 16 + 16))) return rc;
+    if ((rc = s.solo_list.reserve(slots * 4 + 64))) return rc;  // [0]: count, list from +16
     if ((rc = s.meta.reserve(slots * sizeof(PairMeta)))) return rc;
     if ((rc = s.pair_of.reserve(slots * 4))) return rc;
     if ((rc = s.prep_scratch.reserve(prep_scratch_bytes((int)slots, sh.read_length, sh.ref_length)))) return rc;
@@ -404,6 +405,7 @@ void fill_geom(ChunkGeom &g, const Shape &sh, int n) {
     g.segs = sh.segs;
     g.duos = g.slots / 2;
     g.fast_tw = 0;
+    g.solo = 0;
 }
 
 // Enqueue prep + fill (+ traceback) for n pairs whose raw bytes are at raw_reads/raw_refs on
@@ -424,6 +426,8 @@ int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int
     b.code_reads = (uint4 *)ws.code_reads.p;
     b.code_refs = (uint4 *)ws.code_refs.p;
     b.row_idx = (uint4 *)ws.row_idx.p;
+    b.solo_count = (int32_t *)ws.solo_list.p;
+    b.solo_list = (int32_t *)ws.solo_list.p + 16;
     b.meta = (PairMeta *)ws.meta.p;
     b.pair_of = (int32_t *)ws.pair_of.p;
     b.boundary = (int32_t *)ws.boundary.p;
@@ -451,10 +455,15 @@ int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int
         e.prof_used += 4;
         cudaEventRecord(pe[0], stream);
     }
+    static const bool no_intra = [] { const char *v = getenv("VERSALIGN_CUDA_NO_INTRA"); return v && atoi(v) != 0; }();
+    const bool intra = g.fast_tw && !no_intra && intra_preferred(mode, n, sh.read_length, sh.ref_length, e.sm_count);
+    // the inter-task kernels also take single slots (odd leftovers of the bucketing); the intra-task kernel
+    // leaves those to the general kernel.  Decided before prep: every kernel of the chunk reads it.
+    static const bool no_solo = [] { const char *v = getenv("VERSALIGN_CUDA_NO_SOLO"); return v && atoi(v) != 0; }();
+    g.solo = (g.fast_tw && !intra && !no_solo) ? 1 : 0;
     launches += launch_prep(g, b, mode, policy, sc, ws.prep_scratch.p, ws.prep_scratch.cap, stream);
     if (pe) cudaEventRecord(pe[1], stream);
-    static const bool no_intra = [] { const char *v = getenv("VERSALIGN_CUDA_NO_INTRA"); return v && atoi(v) != 0; }();
-    if (g.fast_tw && !no_intra && intra_preferred(mode, n, sh.read_length, sh.ref_length, e.sm_count))
+    if (intra)
         launches += launch_fill_intra(g, b, mode, make_fast_consts(mode, sc), stream);
     else
         launches += launch_fill_fast(g, b, mode, sc, stream);

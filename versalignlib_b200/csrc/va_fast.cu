@@ -1,23 +1,25 @@
-// va_fast.cu -- the packed inter-task fill kernels: one thread computes TWO pairs at once in the
-// two signed 16-bit lanes of every register, with the Blackwell DPX instructions
-// (VIADDMNMX.S16x2[.RELU], VIMNMX.S16x2 with predicate outputs, VIMNMX3.S16x2).
+// va_fast.cu -- the packed inter-task fill kernels of the Smith-Waterman modes: one thread computes
+// TWO pairs at once in the two signed 16-bit lanes of every register, with the Blackwell DPX
+// instructions (VIADDMNMX.S16x2[.RELU], VIMNMX.S16x2 with predicate outputs, VIMNMX3.S16x2).
+// (The NW modes use a shifted recurrence with fewer instructions per cell: va_nw.cu.)
 //
-// Same recurrences as the reference's kernels (score: DefaultKernel.cpp:83-202,
-// SSEKernel.cpp:1007-1315; NW fill with pointers: DefaultKernel.cpp:282-389), restructured for
-// the GPU instead of translated:
+// Same recurrences as the reference's kernels (score: DefaultKernel.cpp:83-138,
+// SSEKernel.cpp:1007-1150; fill with pointers: DefaultKernel.cpp:204-280), restructured for the GPU
+// instead of translated:
 //   * a strip of TW ref columns lives in registers (previous-row H per column + one PRMT selector
 //     per column); the thread sweeps all read rows of the strip, then moves to the next strip; the
 //     strip's right edge goes through a slot-interleaved boundary array (coalesced 4 B / thread);
 //   * the substitution score of both lanes is ONE prmt: the row supplies two 4-byte tables
 //     (scores of read base A/B against ref A,C,G,T), the column supplies the selector; the
 //     selector's sign-replicate nibbles widen the 8-bit entries to 16-bit lanes;
-//   * per cell: t = max(up+gF, left+gR); H = max(diag+s, t [,0])  -> 3 DPX instructions
-//     (+ 1 prmt, + 1/2 VIMNMX3 for the SW running maximum);
-//   * NW align keeps H+gF per column so that both comparisons the Default/OpenCL pointer rule
+//   * per cell: t = max(up+gF, left+gR); H = max(diag+s, t, 0)  -> 3 DPX instructions
+//     (+ 1 prmt, + 1/2 VIMNMX3 for the running maximum);
+//   * SW align keeps H+gF per column so that both comparisons the Default/OpenCL pointer rule
 //     needs (diag+s >= max(up,left) -> DIAG, else up >= left -> UP, else LEFT) fall out of the
 //     two max instructions as predicates; the predicates are banked into bit planes with
 //     predicated FADDs (2^23-biased floats: exact integers, runs on the FP pipes and leaves the
-//     integer pipe to the recurrence).  2 bits per cell reach HBM, as coalesced 8-byte stores.
+//     integer pipe to the recurrence).  2 bits per cell reach HBM, as coalesced 16-byte stores;
+//   * the per-row inputs are staged 16 rows ahead with cp.async (see `sweep`).
 #include <algorithm>
 #include <cstdlib>
 #include <type_traits>
@@ -32,45 +34,50 @@ constexpr uint32_t NEG2 = 0x80008000u;  // (-32768, -32768): identity of the pac
 
 __device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b) { return __viaddmax_s16x2(a, b, NEG2); }
 
+// Ampere-style asynchronous global -> shared copies (LDGSTS): the data never passes through a register.
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// The Smith-Waterman kernels (the NW modes run on a shifted recurrence, va_nw.cu).
 // SYM: gap_read == gap_ref, so "H + gR" (what the cell to the right needs) and "H + gF" (what the
-// cell below needs) are the same register: one add less per cell in NW align.
-// EDGE (NW align only): the duo's ref is padded (cols < ref_length), so the last true column is kept
-// for the traceback kernel's pad-column rule.  It is a separate instantiation -- launched next to the
-// plain one, each taking only its own kind of duo -- because the plain kernel sits right at its
-// register budget and the extra state costs it spills.
-template <int MODE, int TW, bool SYM, bool EDGE>
+// cell below needs) are the same register: one add less per cell in SW align.
+// SOLO: the instantiation for single slots whose duo is not fast (va_fast.cuh): same sweep, the owner's
+// halves of the shared words stored with 16-bit stores.
+template <int MODE, int TW, bool SYM, bool SOLO>
 __global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuffers b, FastConsts fc) {
     constexpr bool SWA = MODE == MODE_SW_ALIGN;
-    constexpr bool NWA = MODE == MODE_NW_ALIGN || SWA;  // both align modes keep H + gF and emit direction planes
-    constexpr bool SWS = MODE == MODE_SW_SCORE;
-    constexpr bool NWS = MODE == MODE_NW_SCORE;
     constexpr int NG = (TW + 15) / 16;
+    static_assert(MODE == MODE_SW_ALIGN || MODE == MODE_SW_SCORE, "SW modes only");
 
-    __shared__ uint32_t T[8];
-    if (threadIdx.x < 8) T[threadIdx.x] = fc.tab[threadIdx.x];
+    __shared__ uint2 s_T2[256];              // [6*code_a + code_b] -> the two lanes' 4-entry score tables (36 used)
+    __shared__ uint4 s_idx[3][128];           // staged row indices: 16 rows per thread and buffer
+    __shared__ uint32_t s_bnd[3][16][128];    // staged right edge of the previous strip, [row][thread]
+    for (int t = threadIdx.x; t < 256; t += 128) s_T2[t] = t < 36 ? make_uint2(fc.tab[t / 6], fc.tab[t % 6]) : make_uint2(0u, 0u);
     __syncthreads();
 
-    const int duo = blockIdx.x * blockDim.x + threadIdx.x;
-    const int slot_a = 2 * duo, slot_b = slot_a + 1;
     unsigned long long cells = 0;
-    bool mine = false;
-    PairMeta ma, mb;
-    if (slot_b < g.n) {
-        ma = b.meta[slot_a];
-        mb = b.meta[slot_b];
-        mine = duo_is_fast(g, MODE, slot_a, ma, mb);
-        if (MODE == MODE_NW_ALIGN) mine = mine && (EDGE == (g.ref_length > ma.cols));
-    }
-    if (mine) {
-        const int m = max((int)ma.rows, (int)mb.rows), n = ma.cols;
-        cells = ((unsigned long long)ma.rows + (unsigned long long)mb.rows) * (unsigned long long)n;
-        const uint32_t gF2 = fc.gF2, gR2 = fc.gR2, dFR2 = fc.dFR2;
-        const uint8_t *cread = reinterpret_cast<const uint8_t *>(b.code_reads);
+    // one work item: a duo (both lanes) or, in the SOLO instantiation, one slot (one lane)
+    auto run = [&](const FastWork &fw) {
+        const int duo = fw.duo;
+        const int slot_a = 2 * duo, slot_b = slot_a + 1;
+        const int m = fw.rows, n = fw.cols;
+        cells += !SOLO ? ((unsigned long long)fw.ma.rows + (unsigned long long)fw.mb.rows) * (unsigned long long)n
+                      : (unsigned long long)m * (unsigned long long)n;
+        const uint32_t gF2 = fc.gF2, gR2 = fc.gR2, dFR2 = fc.dFR2, k32 = fc.swa_k32;
         const uint8_t *cref = reinterpret_cast<const uint8_t *>(b.code_refs);
         uint32_t *bnd = b.fboundary;
         uint4 *dirs = b.fdirs;
 
-        uint32_t best = 0;  // SW: running max; NW score: max(0, last column, last row)
+        uint32_t best = 0;  // SW score: running max
         // SW align: best cell so far, per lane (first strictly greater in row-major order)
         int gbest_a = 0, gbest_b = 0, gi_a = 0, gi_b = 0, gj_a = 0, gj_b = 0;
         const int nstrips = (n + TW - 1) / TW;
@@ -80,18 +87,21 @@ __global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuf
             uint32_t sel[TW], H[TW];
 #pragma unroll
             for (int k = 0; k < TW; ++k) {
-                const int col = min(c0 + k, n - 1);  // columns past n repeat the last one; their cells are never used
+                // Columns past n (partial last strip) get a selector that yields s <= 0 for both lanes (the sign
+                // byte of a table entry): with both gap scores <= 0 such a cell never exceeds the real cells
+                // above / left of it, so the running maximum and the best-cell search need no per-column guards.
+                const int col = min(c0 + k, n - 1);
                 const size_t off = ((size_t)(col >> 4) * g.slots) * 16 + (col & 15);
                 const uint32_t fa = cref[off + (size_t)slot_a * 16], fb = cref[off + (size_t)slot_b * 16];
                 // nibbles: lane A low byte <- table a[fa], high byte <- its sign; lane B from table b (bytes 4..7)
-                sel[k] = fa | ((fa | 8u) << 4) | ((fb | 4u) << 8) | ((fb | 12u) << 12);
-                // matrix row 0 is 0 (the align modes keep H + gF; SW align adds its bias, see below)
-                H[k] = SWA ? fc.swa_g0 : NWA ? gF2 : 0u;
+                sel[k] = c0 + k < n ? (fa | ((fa | 8u) << 4) | ((fb | 4u) << 8) | ((fb | 12u) << 12)) : 0xCC88u;
+                // matrix row 0 is 0 (SW align keeps H + gF, biased, see below)
+                H[k] = SWA ? fc.swa_g0 : 0u;
             }
             // H[i][c0] feeding the first column's diagonal: 0 for matrix row 0
-            uint32_t diag_next = SWA ? fc.swa_g0 : NWA ? gF2 : 0u;
-            // matrix column 0: 0 in the score modes and SW align, (i+1)*gF in NW align; carried as "left + gR"
-            uint32_t col0 = SWA ? fc.swa_l0 : NWA ? add2(gF2, gR2) : gR2;
+            uint32_t diag_next = SWA ? fc.swa_g0 : 0u;
+            // matrix column 0 is 0; carried as "left + gR"
+            const uint32_t col0 = SWA ? fc.swa_l0 : gR2;
             // SW align runs the whole recurrence with a constant bias B on every stored value, so that
             //  - the zero floor folds into the two adds:  left = max(h+gR, 0+gR)  (one VIADDMNMX each), and
             //  - "left" is never negative, so  key = left*32 + (31-k)  is one IMAD on the FMA pipe and the
@@ -100,42 +110,31 @@ __global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuf
             int sval_a = fc.swa_off, sval_b = fc.swa_off;  // best (biased) value so far in this strip; swa_off = value 0
             uint32_t skey_a = 0, skey_b = 0;     // key that first exceeded it (gives the column)
             int srow_a = -1, srow_b = -1;        // and its row
-            const int kv = min(TW, n - c0);  // valid columns of this strip
-            const bool full = kv == TW;
-
-            const uint8_t *ra = cread + (size_t)slot_a * 16;  // read codes of lane A; lane B is the next uint4
-            const uint32_t chunk_stride = (uint32_t)g.slots * 16u;
-            // One sweep over all read rows of this strip.  PARTIAL (only ever the last strip) guards
-            // the few places that must not see the columns past n; full strips run unguarded.
-            auto sweep = [&](auto partial_tag) {
-                constexpr bool PARTIAL = decltype(partial_tag)::value;
+            // One sweep over all read rows of this strip.
+            //
+            // Per-row inputs (the row's pair of substitution tables, the previous strip's right edge) never
+            // make a row wait on HBM: they are staged 16 rows ahead with cp.async into this thread's own
+            // shared-memory slots -- no registers held across the loop, nothing for the scheduler to sink
+            // next to the consumer -- one commit group per 16-row chunk, three buffers.
+            {
                 uint32_t *bp = bnd + duo;
                 uint4 *dp = dirs + fast_dir_index(g, s, 0, 0, duo);
-                // Software pipeline of the per-row inputs so no row starts by waiting on memory: the
-                // read-code bytes are fetched two rows ahead, the row tables (shared-memory look-up by
-                // that code) and the boundary word one row ahead.
-                auto code_off = [&](int r) { return (uint32_t)(r >> 4) * chunk_stride + (uint32_t)(r & 15); };
-                const int mlast = m - 1;
-                uint32_t o1 = code_off(min(1, mlast));
-                uint32_t ca1 = ra[o1], cb1 = ra[o1 + 16];
-                uint32_t o0 = code_off(0);
-                uint32_t nta = T[ra[o0]], ntb = T[ra[o0 + 16]];
-                uint32_t nleft = first ? 0u : *bp;
-                // one matrix row of this strip; NW align returns the row's two direction planes per group
-                auto do_row = [&](int i, uint2(&w)[NG]) {
-                    const uint32_t ta = nta, tb = ntb;
-                    uint32_t left = first ? col0 : nleft;
-                    {
-                        nta = T[ca1];  // tables of row i+1
-                        ntb = T[cb1];
-                        const uint32_t o2 = code_off(min(i + 2, mlast));
-                        ca1 = ra[o2];  // codes of row i+2
-                        cb1 = ra[o2 + 16];
-                        if (!first) nleft = bp[i < mlast ? g.duos : 0];  // boundary of row i+1
+                const int nchunks = (m + 15) >> 4;
+                auto stage = [&](int c, int buf) {
+                    cp_async16(&s_idx[buf][threadIdx.x], b.row_idx + (size_t)c * g.duos + duo);
+                    if (!first) {
+                        const uint32_t *src = bnd + (size_t)(c * 16) * g.duos + duo;
+#pragma unroll
+                        for (int r = 0; r < 16; ++r)
+                            if (c * 16 + r < m) cp_async4(&s_bnd[buf][r][threadIdx.x], src + (size_t)r * g.duos);
                     }
-                    if (NWA && !SWA && first) col0 = add2(col0, gF2);
+                    cp_async_commit();
+                };
+                // one matrix row of this strip; SW align returns the row's two direction planes per group
+                auto do_row = [&](int i, const uint2 tt, uint32_t left_in, uint2(&w)[NG]) {
+                    const uint32_t ta = tt.x, tb = tt.y;
+                    uint32_t left = first ? col0 : left_in;
                     uint32_t rowkey = 0;
-                    uint32_t edge = 0;
                     uint32_t diag = diag_next;
                     diag_next = add2(left, dFR2);
                     float p1l[NG], p1h[NG], p2l[NG], p2h[NG];
@@ -146,7 +145,7 @@ __global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuf
                     for (int k = 0; k < TW; ++k) {
                         const uint32_t sub = prmt(ta, tb, sel[k]);
                         const uint32_t up = H[k];
-                        if (NWA) {
+                        if (SWA) {
                             bool dl, dh, ul, uh;
                             const uint32_t t = __vibmax_s16x2(up, left, &uh, &ul);  // up+gF >= left+gR : UP before LEFT
                             const uint32_t d = add2(diag, sub);                     // diag + s (table holds s - gF)
@@ -156,47 +155,29 @@ __global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuf
                             if (dh) p1h[k >> 4] += bit;
                             if (ul) p2l[k >> 4] += bit;
                             if (uh) p2h[k >> 4] += bit;
-                            if (SWA) {
-                                // the pointer of a positive cell is the NW rule; a zero cell is START, which the
-                                // traceback recognises by tracking the score (DefaultKernel.cpp:238-248)
-                                left = __viaddmax_s16x2(h, gR2, fc.swa_l0);           // max(h, 0) + gR   (biased)
-                                H[k] = SYM ? left : __viaddmax_s16x2(h, gF2, fc.swa_g0);
-                                const uint32_t key = left * 32u + (uint32_t)(31 - k) * 0x00010001u;
-                                if (PARTIAL) {  // columns past n must not win
-                                    if (k < kv) rowkey = __vmaxs2(rowkey, key);
-                                } else if (k & 1) {
-                                    rowkey = __vimax3_s16x2(rowkey, key, prev_key);
-                                } else if (k == TW - 1) {
-                                    rowkey = __vmaxs2(rowkey, key);
-                                }
-                                prev_key = key;
-                            } else {
-                                left = add2(h, gR2);
-                                H[k] = SYM ? left : add2(h, gF2);
-                                if (EDGE && PARTIAL && k == kv - 1) edge = left;  // last true column of a partial last strip
+                            // the pointer of a positive cell is the NW rule; a zero cell is START, which the
+                            // traceback recognises by tracking the score (DefaultKernel.cpp:238-248)
+                            left = __viaddmax_s16x2(h, gR2, fc.swa_l0);           // max(h, 0) + gR   (biased)
+                            H[k] = SYM ? left : __viaddmax_s16x2(h, gF2, fc.swa_g0);
+                            const uint32_t key = left * k32 + (uint32_t)(31 - k) * 0x00010001u;  // k32 = 32, opaque: stays an IMAD (FMA pipe)
+                            if (k & 1) {
+                                rowkey = __vimax3_s16x2(rowkey, key, prev_key);
+                            } else if (k == TW - 1) {
+                                rowkey = __vmaxs2(rowkey, key);
                             }
+                            prev_key = key;
                         } else {
                             const uint32_t t = __viaddmax_s16x2(up, gF2, left);
-                            const uint32_t h = SWS ? __viaddmax_s16x2_relu(diag, sub, t) : __viaddmax_s16x2(diag, sub, t);
+                            const uint32_t h = __viaddmax_s16x2_relu(diag, sub, t);
                             left = add2(h, gR2);
                             H[k] = h;
-                            if (SWS) {
-                                // running maximum: two cells per VIMNMX3; columns past n (repeats of the
-                                // last ref base) stay out of it
-                                if (PARTIAL) {
-                                    if (k < kv) best = __vmaxs2(best, h);
-                                } else if (k & 1) {
-                                    best = __vimax3_s16x2(best, h, H[k - 1]);
-                                }
-                            }
-                            if (NWS && PARTIAL && k == kv - 1) best = __vmaxs2(best, h);  // last column of this row
+                            // running maximum: two cells per VIMNMX3
+                            if (k & 1) best = __vimax3_s16x2(best, h, H[k - 1]);
                         }
                         diag = up;
                     }
-                    // right edge of the strip for the next strip; NW align also keeps the LAST true column
-                    // (the traceback kernel needs it to decide whether the padded arg-max lands in a pad column)
-                    if (!last) *bp = left;
-                    else if (EDGE) *bp = PARTIAL ? edge : left;
+                    // right edge of the strip for the next strip
+                    if (!last) store_lanes<SOLO>(bp, left, fw);
                     bp += g.duos;
                     if (SWA) {
                         // strictly greater VALUE than anything seen before in this strip (rows above): new best cell
@@ -211,9 +192,6 @@ __global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuf
                             srow_b = i;
                             skey_b = rowkey >> 16;
                         }
-                    }
-                    if (NWS && !PARTIAL && last) best = __vmaxs2(best, H[TW - 1]);  // last column (SSEKernel.cpp:1285-1291)
-                    if (NWA) {
 #pragma unroll
                         for (int q = 0; q < NG; ++q) {
                             w[q].x = __byte_perm(__float_as_uint(p1l[q]), __float_as_uint(p1h[q]), 0x5410);
@@ -221,28 +199,69 @@ __global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuf
                         }
                     }
                 };
-                // two rows per iteration: their direction words leave as one 16-byte store per group
-                int i = 0;
-                for (; i + 1 < m; i += 2, dp += (size_t)NG * g.duos) {
-                    uint2 w0[NG], w1[NG];
-                    do_row(i, w0);
-                    do_row(i + 1, w1);
-                    if (NWA) {
+                // Software pipeline on top of the staging: the tables and the left edge of the two rows of an
+                // iteration are fetched from shared memory during the iteration before, so chunks c and c+1
+                // must both have landed while chunk c is swept (three buffers, chunk c+2 in flight).
+                stage(0, 0);
+                if (nchunks > 1) stage(1, 1);
+                else cp_async_commit();
+                cp_async_wait<1>();  // chunk 0
+                const uint8_t *ib = reinterpret_cast<const uint8_t *>(&s_idx[0][threadIdx.x]);
+                const uint32_t *lb = &s_bnd[0][0][threadIdx.x];
+                uint2 nt0 = s_T2[ib[0]], nt1 = s_T2[ib[1]];
+                uint32_t nl0 = lb[0], nl1 = lb[128];
+                int buf = 0;
+                for (int c = 0; c < nchunks; ++c) {
+                    const int buf1 = buf == 2 ? 0 : buf + 1, buf2 = buf1 == 2 ? 0 : buf1 + 1;
+                    if (c + 2 < nchunks) stage(c + 2, buf2);
+                    else cp_async_commit();
+                    cp_async_wait<1>();  // chunk c+1 has landed; only the chunk just requested may be in flight
+                    const uint8_t *ip = reinterpret_cast<const uint8_t *>(&s_idx[buf][threadIdx.x]) + 2;
+                    const uint32_t *lp = &s_bnd[buf][2][threadIdx.x];
+                    const uint8_t *ip_next = reinterpret_cast<const uint8_t *>(&s_idx[buf1][threadIdx.x]);
+                    const uint32_t *lp_next = &s_bnd[buf1][0][threadIdx.x];
+                    const int r0 = c * 16, rend = min(16, m - r0);
+                    // two rows per iteration: their direction words leave as one 16-byte store per group
+                    int r = 0;
+                    for (; r + 1 < rend; r += 2, dp += (size_t)NG * g.duos) {
+                        const uint2 t0 = nt0, t1 = nt1;
+                        const uint32_t l0 = nl0, l1 = nl1;
+                        {  // rows r+2, r+3 (the first two rows of the next chunk after rows 14, 15)
+                            const uint8_t *pi = r == 14 ? ip_next : ip;
+                            const uint32_t *pl = r == 14 ? lp_next : lp;
+                            nt0 = s_T2[pi[0]];
+                            nt1 = s_T2[pi[1]];
+                            nl0 = pl[0];
+                            nl1 = pl[128];
+                            ip += 2;
+                            lp += 256;
+                        }
+                        // each row's planes leave as soon as the row is done (8-byte halves of the row pair's
+                        // 16-byte word; L2 merges them), so no plane register lives across the other row
+                        uint2 w0[NG];
+                        do_row(r0 + r, t0, l0, w0);
+                        if (SWA) {
 #pragma unroll
-                        for (int q = 0; q < NG; ++q) dp[(size_t)q * g.duos] = make_uint4(w0[q].x, w0[q].y, w1[q].x, w1[q].y);
-                    }
-                }
-                if (i < m) {  // odd row count: the last word holds one row
-                    uint2 w0[NG];
-                    do_row(i, w0);
-                    if (NWA) {
+                            for (int q = 0; q < NG; ++q) store_half<SOLO>(dp + (size_t)q * g.duos, 0, w0[q], fw);
+                        }
+                        do_row(r0 + r + 1, t1, l1, w0);
+                        if (SWA) {
 #pragma unroll
-                        for (int q = 0; q < NG; ++q) dp[(size_t)q * g.duos] = make_uint4(w0[q].x, w0[q].y, 0u, 0u);
+                            for (int q = 0; q < NG; ++q) store_half<SOLO>(dp + (size_t)q * g.duos, 1, w0[q], fw);
+                        }
                     }
+                    if (r < rend) {  // odd row count (last chunk only): the last word holds one row
+                        uint2 w0[NG];
+                        do_row(r0 + r, nt0, nl0, w0);
+                        if (SWA) {
+#pragma unroll
+                            for (int q = 0; q < NG; ++q) store_half<SOLO>(dp + (size_t)q * g.duos, 0, w0[q], fw);
+                        }
+                    }
+                    buf = buf1;
                 }
-            };
-            if (full || (NWA && !SWA && !EDGE)) sweep(std::false_type{});
-            else sweep(std::true_type{});
+                cp_async_wait<0>();
+            }
             if (SWA) {
                 // fold this strip into the pair's best cell: greater wins; equal wins only from an earlier row
                 // (an equal value further right in the same row, or below, comes later in row-major order)
@@ -258,30 +277,33 @@ __global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuf
                     gj_b = c0 + 31 - (int)(skey_b & 31u);
                 }
             }
-            if (NWA && !SWA) {  // the row the end-cell rule scans (DefaultKernel.cpp:352-355,381-387)
-#pragma unroll
-                for (int k = 0; k < TW; ++k)
-                    if (c0 + k < n) b.hrow[(size_t)(c0 + k) * g.duos + duo] = H[k];
+        }
+        const bool out_a = !SOLO || fw.lane == 0, out_b = !SOLO || fw.lane == 1;
+        if (!SWA) {
+            if (out_a) b.scores[b.pair_of[slot_a]] = (int16_t)(best & 0xFFFF);
+            if (out_b) b.scores[b.pair_of[slot_b]] = (int16_t)(best >> 16);
+        } else {
+            if (out_a) {
+                const int pa = b.pair_of[slot_a];
+                b.scores[pa] = (int16_t)gbest_a;
+                b.end_cell[2 * pa] = (int16_t)gi_a;
+                b.end_cell[2 * pa + 1] = (int16_t)gj_a;
             }
-            if (NWS) {  // whole last row (SSEKernel.cpp:1302-1310); column 0 is 0 and `best` starts at 0
-#pragma unroll
-                for (int k = 0; k < TW; ++k)
-                    if (c0 + k < n) best = __vmaxs2(best, H[k]);
+            if (out_b) {
+                const int pb = b.pair_of[slot_b];
+                b.scores[pb] = (int16_t)gbest_b;
+                b.end_cell[2 * pb] = (int16_t)gi_b;
+                b.end_cell[2 * pb + 1] = (int16_t)gj_b;
             }
         }
-        if (!NWA) {
-            b.scores[b.pair_of[slot_a]] = (int16_t)(best & 0xFFFF);
-            b.scores[b.pair_of[slot_b]] = (int16_t)(best >> 16);
-        }
-        if (SWA) {
-            const int pa = b.pair_of[slot_a], pb = b.pair_of[slot_b];
-            b.scores[pa] = (int16_t)gbest_a;
-            b.end_cell[2 * pa] = (int16_t)gi_a;
-            b.end_cell[2 * pa + 1] = (int16_t)gj_a;
-            b.scores[pb] = (int16_t)gbest_b;
-            b.end_cell[2 * pb] = (int16_t)gi_b;
-            b.end_cell[2 * pb + 1] = (int16_t)gj_b;
-        }
+    };
+    const int thread = blockIdx.x * blockDim.x + threadIdx.x;
+    if constexpr (!SOLO) {  // thread t takes duo t
+        const FastWork fw = fast_work_duo(g, b.meta, MODE, thread);
+        if (fw.own == OWN_DUO) run(fw);
+    } else {  // grid-stride loop over the slots the prep kernel listed
+        const int count = *b.solo_count;
+        for (int e = thread; e < count; e += (int)(gridDim.x * blockDim.x)) run(fast_work_solo(b.meta, b.solo_list[e]));
     }
     for (int o = 16; o > 0; o >>= 1) cells += __shfl_xor_sync(0xffffffffu, cells, o);
     if ((threadIdx.x & 31) == 0 && cells) atomicAdd(b.cell_count, cells);
@@ -292,24 +314,15 @@ void launch_one(const ChunkGeom &g, const ChunkBuffers &b, const FastConsts &fc,
     const int threads = 128;
     const int duos = (g.n + 1) / 2;
     const int blocks = (duos + threads - 1) / threads;
-    if constexpr (MODE == MODE_NW_ALIGN) {
-        // plain duos, then (nothing to do on an unpadded batch) the padded-ref duos
-        if (fc.gF == fc.gR) {
-            fill_fast_kernel<MODE, TW, true, false><<<blocks, threads, 0, stream>>>(g, b, fc);
-            fill_fast_kernel<MODE, TW, true, true><<<blocks, threads, 0, stream>>>(g, b, fc);
-        } else {
-            fill_fast_kernel<MODE, TW, false, false><<<blocks, threads, 0, stream>>>(g, b, fc);
-            fill_fast_kernel<MODE, TW, false, true><<<blocks, threads, 0, stream>>>(g, b, fc);
-        }
+    // SW align with equal gap scores keeps one register per column less
+    if (MODE == MODE_SW_ALIGN && fc.gF == fc.gR) {
+        if (g.n >= 2) fill_fast_kernel<MODE, TW, MODE == MODE_SW_ALIGN, false><<<blocks, threads, 0, stream>>>(g, b, fc);
+        if (g.solo) fill_fast_kernel<MODE, TW, MODE == MODE_SW_ALIGN, true><<<std::min(2 * blocks, 148 * 4), threads, 0, stream>>>(g, b, fc);
         return;
     }
-    if constexpr (MODE == MODE_SW_ALIGN) {
-        if (fc.gF == fc.gR) {
-            fill_fast_kernel<MODE, TW, true, false><<<blocks, threads, 0, stream>>>(g, b, fc);
-            return;
-        }
-    }
-    fill_fast_kernel<MODE, TW, false, false><<<blocks, threads, 0, stream>>>(g, b, fc);
+    if (g.n >= 2) fill_fast_kernel<MODE, TW, false, false><<<blocks, threads, 0, stream>>>(g, b, fc);
+    // leftovers of the bucketing: a fixed grid strides over the list the prep kernel compiled (va_fast.cuh)
+    if (g.solo) fill_fast_kernel<MODE, TW, false, true><<<std::min(2 * blocks, 148 * 4), threads, 0, stream>>>(g, b, fc);
 }
 
 template <int MODE>
@@ -357,6 +370,7 @@ bool fast_scoring_ok(int mode, int policy, const Scoring &sc, int read_length, i
                               (long long)sc.gap_ref * (read_length + 2) - (long long)sc.gap_read * (ref_length + 2);
         return top + 256 <= 32000;
     }
+    if (sc.gap_read > 0 || sc.gap_ref > 0) return false;  // the columns past n of a partial strip rely on it
     const int off = align ? sc.gap_ref : 0;
     if (!fits8(sc.match - off) || !fits8(sc.mismatch - off) || !fits8(-off)) return false;
     // every cell is floored at 0: values stay within [-mx, match * min(rows, cols)]
@@ -419,17 +433,18 @@ FastConsts make_fast_consts(int mode, const Scoring &sc) {
         fc.swa_g0 = pk(sc.gap_ref + B);    // matrix row 0 / zero floor, as "H + gF"
         fc.swa_off = sc.gap_read + B;      // key>>5 minus this is the cell value
         fc.swa_key0 = pk(((sc.gap_read + B) << 5) | 31);
+        fc.swa_k32 = 32;
     }
     return fc;
 }
 
 int launch_fill_fast(const ChunkGeom &g, const ChunkBuffers &b, int mode, const Scoring &sc, cudaStream_t stream) {
-    if (g.fast_tw == 0 || g.n < 2) return 0;
+    if (g.fast_tw == 0 || (g.n < 2 && !g.solo)) return 0;
     const FastConsts fc = make_fast_consts(mode, sc);
     switch (mode) {
         case MODE_SW_SCORE: launch_tw<MODE_SW_SCORE>(g, b, fc, stream); break;
         case MODE_NW_SCORE:
-        case MODE_NW_ALIGN: return launch_fill_nw(g, b, mode, fc, stream);
+        case MODE_NW_ALIGN: launch_fill_nw(g, b, mode, fc, stream); break;
         case MODE_SW_ALIGN: launch_tw<MODE_SW_ALIGN>(g, b, fc, stream); break;
         default: return 0;
     }

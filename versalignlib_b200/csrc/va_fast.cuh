@@ -26,6 +26,101 @@ __device__ __forceinline__ bool duo_is_fast(const ChunkGeom &g, int mode, int sl
     return max(a.rows, b.rows) > 0;
 }
 
+// A slot whose duo is NOT fast can still be computed by the packed inter-task kernels on its own
+// ("solo"): a thread sweeps that slot's extents, the other 16-bit lane computes along on whatever its
+// registers hold (lanes never mix), and only the owner's halves of the shared words are stored.  That
+// keeps the leftovers of the length bucketing (a run of equal extents with an odd number of pairs,
+// the last slot of an odd batch, neighbours with different ref lengths) off the 32-bit general kernel.
+__device__ __forceinline__ bool solo_ok(const ChunkGeom &g, int slot, const PairMeta &m) {
+    if (g.fast_tw == 0 || !g.solo || slot >= g.n) return false;
+    if (m.flags & 2) return false;
+    return m.cols > 0 && m.cols == m.true_cols && m.rows > 0;
+}
+
+enum : int { OWN_NONE = 0, OWN_DUO = 1, OWN_SOLO = 2 };
+
+// Which packed path computes `slot`; a = meta[slot & ~1], b = meta[slot | 1].  The fill kernels, the
+// general kernel and the traceback kernel all evaluate this, so no flag is exchanged.
+__device__ __forceinline__ int slot_owner(const ChunkGeom &g, int mode, int slot, const PairMeta &a, const PairMeta &b) {
+    if (duo_is_fast(g, mode, slot & ~1, a, b)) return OWN_DUO;
+    return solo_ok(g, slot, (slot & 1) ? b : a) ? OWN_SOLO : OWN_NONE;
+}
+
+// Work item of a packed inter-task kernel thread: a duo (both lanes) or one solo slot (one lane).
+struct FastWork {
+    int own;   // OWN_*
+    int duo;   // index into the [duo]-strided arrays
+    int lane;  // solo: which 16-bit lane is this thread's (0 = slot 2*duo, 1 = slot 2*duo+1)
+    int rows, cols;
+    PairMeta ma, mb;
+};
+
+// duo kernels: thread t takes duo t
+__device__ __forceinline__ FastWork fast_work_duo(const ChunkGeom &g, const PairMeta *meta, int mode, int duo) {
+    FastWork w;
+    w.own = OWN_NONE;
+    w.lane = 0;
+    w.duo = duo;
+    w.rows = w.cols = 0;
+    const int slot_a = 2 * duo;
+    if (slot_a + 1 >= g.n) return w;
+    w.ma = meta[slot_a];
+    w.mb = meta[slot_a + 1];
+    if (duo_is_fast(g, mode, slot_a, w.ma, w.mb)) {
+        w.own = OWN_DUO;
+        w.rows = max((int)w.ma.rows, (int)w.mb.rows);
+        w.cols = w.ma.cols;
+    }
+    return w;
+}
+
+// solo kernels: a grid-stride loop over the list the prep kernel compiled (ChunkBuffers::solo_list)
+__device__ __forceinline__ FastWork fast_work_solo(const PairMeta *meta, int slot) {
+    FastWork w;
+    w.own = OWN_SOLO;
+    w.lane = slot & 1;
+    w.duo = slot >> 1;
+    w.ma = meta[slot & ~1];
+    w.mb = meta[slot | 1];  // slots are padded to a multiple of 64: always readable
+    const PairMeta &me = w.lane ? w.mb : w.ma;
+    w.rows = me.rows;
+    w.cols = me.cols;
+    return w;
+}
+
+// Stores into words two solo threads may share: a duo thread writes the word, a solo thread its half.
+template <bool SOLO>
+__device__ __forceinline__ void store_lanes(uint32_t *p, uint32_t v, const FastWork &w) {
+    if (!SOLO) *p = v;
+    else reinterpret_cast<uint16_t *>(p)[w.lane] = (uint16_t)(v >> (16 * w.lane));
+}
+template <bool SOLO>
+__device__ __forceinline__ void store_lanes(uint4 *p, uint4 v, const FastWork &w) {
+    if (!SOLO) {
+        *p = v;
+    } else {
+        uint16_t *h = reinterpret_cast<uint16_t *>(p) + w.lane;
+        const int sh = 16 * w.lane;
+        h[0] = (uint16_t)(v.x >> sh);
+        h[2] = (uint16_t)(v.y >> sh);
+        h[4] = (uint16_t)(v.z >> sh);
+        h[6] = (uint16_t)(v.w >> sh);
+    }
+}
+
+// one row's (DIAG plane, UP plane) of a row pair's direction word: half 0 = even row (.x/.y), 1 = odd row (.z/.w)
+template <bool SOLO>
+__device__ __forceinline__ void store_half(uint4 *p, int half, uint2 v, const FastWork &w) {
+    if (!SOLO) {
+        reinterpret_cast<uint2 *>(p)[half] = v;
+    } else {
+        uint16_t *h = reinterpret_cast<uint16_t *>(p) + 4 * half + w.lane;
+        const int sh = 16 * w.lane;
+        h[0] = (uint16_t)(v.x >> sh);
+        h[2] = (uint16_t)(v.y >> sh);
+    }
+}
+
 __device__ __forceinline__ int fast_groups(int tw) { return (tw + 15) >> 4; }
 
 // Direction words of the packed kernel: one uint4 per (strip, ROW PAIR, group of 16 columns, duo)

@@ -48,6 +48,7 @@ struct ChunkGeom {
     int segs;          // ceil(ref_length/8): direction half-words per row
     int fast_tw;       // column-strip width of the packed 16-bit kernels for this call, 0 = not eligible
     int duos;          // slots / 2: stride of the arrays the packed kernels index by pair-of-pairs
+    int solo;          // 1: the packed inter-task kernels also take single slots whose duo is not fast (va_fast.cuh)
 };
 
 // Constants of the packed (two pairs per thread, s16x2) kernels, built on the host per call.
@@ -57,7 +58,7 @@ struct FastConsts {
     uint32_t dFR2;     // NW align: gap_ref - gap_read ; score modes: -gap_read   (boundary -> diagonal conversion)
     int gF, gR;
     // SW align only (see va_fast.cu): biased initial values and key constants
-    uint32_t swa_l0, swa_g0, swa_key0;
+    uint32_t swa_l0, swa_g0, swa_key0, swa_k32;
     int swa_off;
 };
 
@@ -77,6 +78,8 @@ struct ChunkBuffers {
     uint4 *fdirs;              // packed kernel:  [strip][row pair][group][duos], see va_fast.cuh
                                // (separate regions: one chunk can hold pairs of both kinds)
     uint32_t *hrow;            // packed NW align: [ref_length][duos] last valid matrix row (H + gap_ref)
+    int32_t *solo_list;        // [slots] slots the packed kernels take on their own (va_fast.cuh), written by the prep
+    int32_t *solo_count;       // kernel in no particular order; *solo_count entries
     int16_t *scores;           // [n]
     int16_t *end_cell;         // [n][2]
     // traceback outputs

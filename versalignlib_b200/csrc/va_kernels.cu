@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(128) fill_general_kernel(ChunkGeom g, ChunkBuf
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long cells = 0;
     // pairs the packed kernel owns (va_fast.cuh) are skipped here
-    if (slot < g.n && !duo_is_fast(g, MODE, slot & ~1, b.meta[slot & ~1], b.meta[slot | 1])) {
+    if (slot < g.n && slot_owner(g, MODE, slot, b.meta[slot & ~1], b.meta[slot | 1]) == OWN_NONE) {
         const PairMeta meta = b.meta[slot];
         const int m = meta.rows, n = meta.cols;
         const int gF = sc.gap_ref, gR = sc.gap_read;

@@ -17,6 +17,7 @@
 // non-decreasing along rows and columns, which bounds the 16-bit range check.
 // The matrix borders un-shift what they hand out: NW score's last row / last column maxima, the
 // `hrow` row and the last-true-column values the traceback kernel reads (va_traceback.cu).
+#include <algorithm>
 #include <type_traits>
 
 #include "va_fast.cuh"
@@ -25,6 +26,11 @@ namespace va {
 
 namespace {
 
+#ifndef VA_NW_NT
+#define VA_NW_NT 128
+#endif
+constexpr int NT = VA_NW_NT;                    // threads per block
+constexpr int MAXREG = NT == 96 ? 136 : 128;   // 5 x 96 threads per SM leave 136 registers each, 4 x 128 leave 128
 constexpr uint32_t NEG2 = 0x80008000u;  // (-32768, -32768): identity of the packed max
 
 __device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b) { return __viaddmax_s16x2(a, b, NEG2); }
@@ -43,34 +49,28 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// EDGE (align only): the duo's ref is padded (cols < ref_length); the last true column is kept for the
-// traceback kernel's pad-column rule.  Separate instantiation, launched next to the plain one, each
-// taking only its own kind of duo.
-template <bool ALIGN, int TW, bool EDGE>
-__global__ void __launch_bounds__(128, 4) fill_nw_kernel(ChunkGeom g, ChunkBuffers b, FastConsts fc) {
+// SOLO: the instantiation for single slots whose duo is not fast (va_fast.cuh): same sweep, the owner's
+// halves of the shared words stored with 16-bit stores.  Kept apart so the duo kernel's stores stay
+// unconditional (its schedule sits right at the register budget).
+template <bool ALIGN, int TW, bool SOLO>
+__global__ void __maxnreg__(MAXREG) fill_nw_kernel(ChunkGeom g, ChunkBuffers b, FastConsts fc) {
     constexpr int NG = (TW + 15) / 16;
     constexpr int MODE = ALIGN ? MODE_NW_ALIGN : MODE_NW_SCORE;
 
     __shared__ uint2 s_T2[256];              // [6*code_a + code_b] -> the two lanes' 4-entry score tables (36 used)
-    __shared__ uint4 s_idx[3][128];           // staged row indices: 16 rows per thread and buffer
-    __shared__ uint32_t s_bnd[3][16][128];    // staged right edge of the previous strip, [row][thread]
-    for (int t = threadIdx.x; t < 256; t += 128) s_T2[t] = t < 36 ? make_uint2(fc.tab[t / 6], fc.tab[t % 6]) : make_uint2(0u, 0u);
+    __shared__ uint4 s_idx[3][NT];           // staged row indices: 16 rows per thread and buffer
+    __shared__ uint32_t s_bnd[3][16][NT];    // staged right edge of the previous strip, [row][thread]
+    for (int t = threadIdx.x; t < 256; t += NT) s_T2[t] = t < 36 ? make_uint2(fc.tab[t / 6], fc.tab[t % 6]) : make_uint2(0u, 0u);
     __syncthreads();
 
-    const int duo = blockIdx.x * blockDim.x + threadIdx.x;
-    const int slot_a = 2 * duo, slot_b = slot_a + 1;
     unsigned long long cells = 0;
-    bool mine = false;
-    PairMeta ma, mb;
-    if (slot_b < g.n) {
-        ma = b.meta[slot_a];
-        mb = b.meta[slot_b];
-        mine = duo_is_fast(g, MODE, slot_a, ma, mb);
-        if (ALIGN) mine = mine && (EDGE == (g.ref_length > ma.cols));
-    }
-    if (mine) {
-        const int m = max((int)ma.rows, (int)mb.rows), n = ma.cols;
-        cells = ((unsigned long long)ma.rows + (unsigned long long)mb.rows) * (unsigned long long)n;
+    // one work item: a duo (both lanes) or, in the SOLO instantiation, one slot (one lane)
+    auto run = [&](const FastWork &fw) {
+        const int duo = fw.duo;
+        const int slot_a = 2 * duo, slot_b = slot_a + 1;
+        const int m = fw.rows, n = fw.cols;
+        cells += !SOLO ? ((unsigned long long)fw.ma.rows + (unsigned long long)fw.mb.rows) * (unsigned long long)n
+                      : (unsigned long long)m * (unsigned long long)n;
         const int ngF = -fc.gF, ngR = -fc.gR;  // both >= 0
         const uint32_t gF2 = fc.gF2, ngF2 = pk(ngF);
         const uint8_t *cref = reinterpret_cast<const uint8_t *>(b.code_refs);
@@ -82,33 +82,36 @@ __global__ void __launch_bounds__(128, 4) fill_nw_kernel(ChunkGeom g, ChunkBuffe
         for (int s = 0; s < nstrips; ++s) {
             const int c0 = s * TW;
             const bool first = s == 0, last = s == nstrips - 1;
+            // A partial last strip keeps its kv true columns in the LAST kv registers; the `pad` registers in
+            // front of them are pass-through columns: their selector yields s' <= 0 (the sign byte of a table
+            // entry) and they start from V(0,c0), so with V non-decreasing down the boundary column each of
+            // them reproduces its left neighbour, and the first true column sees exactly the boundary column
+            // to its left and above-left.  The last true column is therefore always register TW-1, and the
+            // sweep needs no per-column guards.  Their direction bits are never read (va_traceback.cu).
+            const int kv = min(TW, n - c0);  // valid columns of this strip
+            const int pad = TW - kv;
             uint32_t sel[TW], H[TW];
 #pragma unroll
             for (int k = 0; k < TW; ++k) {
-                const int col = min(c0 + k, n - 1);  // columns past n repeat the last one; their cells are never used
+                const int col = max(c0 + k - pad, c0);
                 const size_t off = ((size_t)(col >> 4) * g.slots) * 16 + (col & 15);
                 const uint32_t fa = cref[off + (size_t)slot_a * 16], fb = cref[off + (size_t)slot_b * 16];
                 // nibbles: lane A low byte <- table a[fa], high byte <- its sign; lane B from table b (bytes 4..7)
-                sel[k] = fa | ((fa | 8u) << 4) | ((fb | 4u) << 8) | ((fb | 12u) << 12);
-                H[k] = pk(ngR * (c0 + k + 1));  // V(0,J) = -gap_read*J: matrix row 0 is 0
+                sel[k] = k >= pad ? (fa | ((fa | 8u) << 4) | ((fb | 4u) << 8) | ((fb | 12u) << 12)) : 0xCC88u;
+                H[k] = pk(ngR * (max(c0 + k - pad, c0 - 1) + 1));  // V(0,J) = -gap_read*J: matrix row 0 is 0
             }
             uint32_t diag_next = pk(ngR * c0);  // V(0, c0)
             // matrix column 0 in shifted form: H(I,0) = I*gap_ref -> 0 (align); H(I,0) = 0 -> -gap_ref*I (score)
             uint32_t col0 = ALIGN ? 0u : ngF2;
             // score mode, last strip: un-shift of the last column, gap_ref*I + gap_read*n
             uint32_t corr = pk(fc.gR * n + fc.gF);
-            const int kv = min(TW, n - c0);  // valid columns of this strip
-            const bool full = kv == TW;
-
-            // One sweep over all read rows of this strip.  PARTIAL (only ever the last strip) guards the
-            // few places that must tell the columns past n apart; full strips run unguarded.
+            // One sweep over all read rows of this strip.
             //
             // Per-row inputs (the row's pair of substitution tables, the previous strip's right edge) never
             // make a row wait on HBM: they are staged 16 rows ahead with cp.async into this thread's own
             // shared-memory slots -- no registers held across the loop, nothing for the scheduler to sink
             // next to the consumer -- one commit group per 16-row chunk, double buffered.
-            auto sweep = [&](auto partial_tag) {
-                constexpr bool PARTIAL = decltype(partial_tag)::value;
+            {
                 uint32_t *bp = bnd + duo;
                 uint4 *dp = dirs + fast_dir_index(g, s, 0, 0, duo);
                 const int nchunks = (m + 15) >> 4;
@@ -127,7 +130,6 @@ __global__ void __launch_bounds__(128, 4) fill_nw_kernel(ChunkGeom g, ChunkBuffe
                     const uint32_t ta = tt.x, tb = tt.y;
                     uint32_t left = first ? col0 : left_in;
                     if (!ALIGN && first) col0 = add2(col0, ngF2);
-                    uint32_t edge = 0;
                     uint32_t diag = diag_next;
                     diag_next = left;  // V(I, c0) is the next row's diagonal
                     float p1l[NG], p1h[NG], p2l[NG], p2h[NG];
@@ -151,18 +153,17 @@ __global__ void __launch_bounds__(128, 4) fill_nw_kernel(ChunkGeom g, ChunkBuffe
                         } else {
                             h = __viaddmax_s16x2(diag, sub, __vmaxs2(up, left));
                         }
-                        if (PARTIAL && k == kv - 1) edge = h;  // last true column of a partial last strip
                         left = h;
                         H[k] = h;
                         diag = up;
                     }
                     // right edge of the strip for the next strip; align also keeps the LAST true column (the
                     // traceback kernel needs it to decide whether the padded arg-max lands in a pad column)
-                    if (!last) *bp = left;
-                    else if (ALIGN && EDGE) *bp = PARTIAL ? edge : left;
+                    // (align: also of the last strip -- on a padded ref the traceback's pad-column rule needs the last true column)
+                    if (ALIGN || !last) store_lanes<SOLO>(bp, left, fw);
                     bp += g.duos;
                     if (!ALIGN && last) {  // last column of this row, un-shifted (SSEKernel.cpp:1285-1291)
-                        best = __viaddmax_s16x2(PARTIAL ? edge : left, corr, best);
+                        best = __viaddmax_s16x2(left, corr, best);
                         corr = add2(corr, gF2);
                     }
                     if (ALIGN) {
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(128, 4) fill_nw_kernel(ChunkGeom g, ChunkBuffe
                 const uint8_t *ib = reinterpret_cast<const uint8_t *>(&s_idx[0][threadIdx.x]);
                 const uint32_t *lb = &s_bnd[0][0][threadIdx.x];
                 uint2 nt0 = s_T2[ib[0]], nt1 = s_T2[ib[1]];
-                uint32_t nl0 = lb[0], nl1 = lb[128];
+                uint32_t nl0 = lb[0], nl1 = lb[NT];
                 int buf = 0;
                 for (int c = 0; c < nchunks; ++c) {
                     const int buf1 = buf == 2 ? 0 : buf + 1, buf2 = buf1 == 2 ? 0 : buf1 + 1;
@@ -206,16 +207,22 @@ __global__ void __launch_bounds__(128, 4) fill_nw_kernel(ChunkGeom g, ChunkBuffe
                             nt0 = s_T2[pi[0]];
                             nt1 = s_T2[pi[1]];
                             nl0 = pl[0];
-                            nl1 = pl[128];
+                            nl1 = pl[NT];
                             ip += 2;
-                            lp += 256;
+                            lp += 2 * NT;
                         }
-                        uint2 w0[NG], w1[NG];
+                        // each row's planes leave as soon as the row is done (8-byte halves of the row pair's
+                        // 16-byte word; L2 merges them), so no plane register lives across the other row
+                        uint2 w0[NG];
                         do_row(t0, l0, w0);
-                        do_row(t1, l1, w1);
                         if (ALIGN) {
 #pragma unroll
-                            for (int q = 0; q < NG; ++q) dp[(size_t)q * g.duos] = make_uint4(w0[q].x, w0[q].y, w1[q].x, w1[q].y);
+                            for (int q = 0; q < NG; ++q) store_half<SOLO>(dp + (size_t)q * g.duos, 0, w0[q], fw);
+                        }
+                        do_row(t1, l1, w0);
+                        if (ALIGN) {
+#pragma unroll
+                            for (int q = 0; q < NG; ++q) store_half<SOLO>(dp + (size_t)q * g.duos, 1, w0[q], fw);
                         }
                     }
                     if (r < rend) {  // odd row count (last chunk only): the last word holds one row
@@ -223,35 +230,37 @@ __global__ void __launch_bounds__(128, 4) fill_nw_kernel(ChunkGeom g, ChunkBuffe
                         do_row(nt0, nl0, w0);
                         if (ALIGN) {
 #pragma unroll
-                            for (int q = 0; q < NG; ++q) dp[(size_t)q * g.duos] = make_uint4(w0[q].x, w0[q].y, 0u, 0u);
+                            for (int q = 0; q < NG; ++q) store_half<SOLO>(dp + (size_t)q * g.duos, 0, w0[q], fw);
                         }
                     }
                     buf = buf1;
                 }
                 cp_async_wait<0>();
-            };
-            // align without a padded ref never looks at the cells past n: its last strip runs unguarded too
-            if constexpr (ALIGN && !EDGE) {
-                sweep(std::false_type{});
-            } else {
-                if (full) sweep(std::false_type{});
-                else sweep(std::true_type{});
             }
+            // Pass-through columns hold the value of the column left of the strip, so they are handed out
+            // like that column (no per-column guards: an idempotent store / a harmless repeat in the maximum).
             if (ALIGN) {  // the row the end-cell rule scans (DefaultKernel.cpp:352-355,381-387), still shifted
 #pragma unroll
                 for (int k = 0; k < TW; ++k)
-                    if (c0 + k < n) b.hrow[(size_t)(c0 + k) * g.duos + duo] = H[k];
+                    store_lanes<SOLO>(b.hrow + (size_t)max(c0 + k - pad, max(c0 - 1, 0)) * g.duos + duo, H[k], fw);
             } else {  // whole last row (SSEKernel.cpp:1302-1310), un-shifted; column 0 is 0 and `best` starts at 0
-                const int base = fc.gF * m + fc.gR * (c0 + 1);
 #pragma unroll
                 for (int k = 0; k < TW; ++k)
-                    if (c0 + k < n) best = __viaddmax_s16x2(H[k], pk(base + fc.gR * k), best);
+                    best = __viaddmax_s16x2(H[k], pk(fc.gF * m + fc.gR * (max(c0 + k - pad, c0 - 1) + 1)), best);
             }
         }
         if (!ALIGN) {
-            b.scores[b.pair_of[slot_a]] = (int16_t)(best & 0xFFFF);
-            b.scores[b.pair_of[slot_b]] = (int16_t)(best >> 16);
+            if (!SOLO || fw.lane == 0) b.scores[b.pair_of[slot_a]] = (int16_t)(best & 0xFFFF);
+            if (!SOLO || fw.lane == 1) b.scores[b.pair_of[slot_b]] = (int16_t)(best >> 16);
         }
+    };
+    const int thread = blockIdx.x * blockDim.x + threadIdx.x;
+    if constexpr (!SOLO) {  // thread t takes duo t
+        const FastWork fw = fast_work_duo(g, b.meta, MODE, thread);
+        if (fw.own == OWN_DUO) run(fw);
+    } else {  // grid-stride loop over the slots the prep kernel listed
+        const int count = *b.solo_count;
+        for (int e = thread; e < count; e += (int)(gridDim.x * blockDim.x)) run(fast_work_solo(b.meta, b.solo_list[e]));
     }
     for (int o = 16; o > 0; o >>= 1) cells += __shfl_xor_sync(0xffffffffu, cells, o);
     if ((threadIdx.x & 31) == 0 && cells) atomicAdd(b.cell_count, cells);
@@ -259,12 +268,13 @@ __global__ void __launch_bounds__(128, 4) fill_nw_kernel(ChunkGeom g, ChunkBuffe
 
 template <bool ALIGN, int TW>
 void launch_one(const ChunkGeom &g, const ChunkBuffers &b, const FastConsts &fc, cudaStream_t stream) {
-    const int threads = 128;
+    const int threads = NT;
     const int duos = (g.n + 1) / 2;
     const int blocks = (duos + threads - 1) / threads;
-    fill_nw_kernel<ALIGN, TW, false><<<blocks, threads, 0, stream>>>(g, b, fc);
-    // align: the padded-ref duos (nothing to do on an unpadded batch)
-    if constexpr (ALIGN) fill_nw_kernel<ALIGN, TW, true><<<blocks, threads, 0, stream>>>(g, b, fc);
+    if (g.n >= 2) fill_nw_kernel<ALIGN, TW, false><<<blocks, threads, 0, stream>>>(g, b, fc);
+    // leftovers of the bucketing: a fixed grid strides over the list the prep kernel compiled (empty on a
+    // uniform batch: the blocks read the count and leave)
+    if (g.solo) fill_nw_kernel<ALIGN, TW, true><<<std::min(2 * blocks, 148 * 4), threads, 0, stream>>>(g, b, fc);
 }
 
 }  // namespace

@@ -18,7 +18,7 @@
 
 #include <cub/device/device_radix_sort.cuh>
 
-#include "va_internal.h"
+#include "va_fast.cuh"
 
 namespace va {
 
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(128) meta_kernel(ChunkGeom g, const uint8_t *_
 __global__ void __launch_bounds__(256) encode_kernel(ChunkGeom g, ChunkBuffers b, const PairMeta *__restrict__ meta_pair,
                                                      const uint4 *__restrict__ codes_pair_reads,
                                                      const uint4 *__restrict__ codes_pair_refs,
-                                                     const uint32_t *__restrict__ order) {
+                                                     const uint32_t *__restrict__ order, int mode) {
     const int per_slot = g.read_chunks + g.ref_chunks;
     const size_t total = (size_t)g.slots * per_slot;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
@@ -168,8 +168,15 @@ __global__ void __launch_bounds__(256) encode_kernel(ChunkGeom g, ChunkBuffers b
         }
         const int pair = (int)order[slot];
         if (c == 0) {
-            b.meta[slot] = meta_pair[pair];
+            const PairMeta me = meta_pair[pair];
+            b.meta[slot] = me;
             b.pair_of[slot] = pair;
+            if (g.solo) {  // slots the packed kernels compute on their own (va_fast.cuh): compiled into a list
+                PairMeta other{};
+                if ((slot ^ 1) < g.n) other = meta_pair[order[slot ^ 1]];
+                if (slot_owner(g, mode, slot, (slot & 1) ? other : me, (slot & 1) ? me : other) == OWN_SOLO)
+                    b.solo_list[atomicAdd(b.solo_count, 1)] = slot;
+            }
         }
         // scratch is [chunk][pair]: for a batch that keeps its order both sides are coalesced
         if (c < g.read_chunks) {
@@ -239,8 +246,9 @@ int launch_prep(const ChunkGeom &g, const ChunkBuffers &b, int mode, int policy,
                                                      vals_in, mode, policy, trim, row_bits);
     // only the bits that can differ are sorted: rows, cols and the "dirty" flag above them
     cub::DeviceRadixSort::SortPairs(p, temp_bytes, keys_in, keys_out, vals_in, vals_out, g.n, 0, row_bits + 16, stream);
+    if (g.solo) cudaMemsetAsync(b.solo_count, 0, sizeof(int32_t), stream);
     encode_kernel<<<enc_blocks, threads, 0, stream>>>(g, b, meta_pair, codes_reads, codes_refs,
-                                                      vals_out);
+                                                      vals_out, mode);
     return 2;  // our kernels; the sort is the library's
 }
 

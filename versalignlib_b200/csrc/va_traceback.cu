@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
     const PairMeta meta = b.meta[slot];
     const int rows = meta.rows, cols = meta.cols;
     const int mode = NW ? MODE_NW_ALIGN : MODE_SW_ALIGN;
-    const bool packed = duo_is_fast(g, mode, slot & ~1, b.meta[slot & ~1], b.meta[slot | 1]);
+    const bool packed = slot_owner(g, mode, slot, b.meta[slot & ~1], b.meta[slot | 1]) != OWN_NONE;
     const int duo = slot >> 1, lane_shift = (slot & 1) * 16;
     const int pair = b.pair_of[slot];  // raw bytes and results are indexed in the caller's pair order
 
@@ -120,6 +120,12 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
     if (packed) {
         const int tw = g.fast_tw, ng = fast_groups(tw);
         int strip = j >= 0 ? j / tw : 0, k = j >= 0 ? j - strip * tw : 0;
+        // NW: a partial last strip keeps its true columns in the LAST registers of the strip (va_nw.cu)
+        int kmin = 0;
+        if (NW && cols > 0 && strip == (cols - 1) / tw) {
+            kmin = tw - (cols - strip * tw);
+            k += kmin;
+        }
         const size_t pair_step = (size_t)ng * g.duos, strip_step = (size_t)fast_row_pairs(g) * pair_step;
         const uint4 *p = b.fdirs + (size_t)strip * strip_step + (size_t)(max(i, 0) >> 1) * pair_step + duo;
         int have_pair = -1, have_strip = -1, have_grp = -1;
@@ -168,8 +174,9 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
             }
             if (code != DIR_UP) {
                 --j;
-                if (--k < 0) {
-                    k += tw;
+                if (--k < kmin) {
+                    k = tw - 1;
+                    kmin = 0;
                     --strip;
                     p -= strip_step;
                 }
