@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define VA_CUDA_ABI_VERSION 1
+#define VA_CUDA_ABI_VERSION 2
 
 /* status codes */
 #define VA_OK 0
@@ -135,6 +135,24 @@ int va_cuda_align_alloc(va_cuda_ctx *ctx, int opt, int policy, const va_cuda_sco
                         const char *const *refs, int ref_length,
                         va_cuda_alloc_fn alloc, void *user,
                         char **out_read, char **out_ref, int16_t *start, int16_t *end_cell);
+
+/* Same again, but the results are written straight into the caller's array of result records
+ * laid out like the reference's struct Alignment (include/AlignmentKernel.h:12-24): two block
+ * pointers followed by four shorts.  records points at record 0, record_stride is sizeof the
+ * caller's struct (>= sizeof(va_cuda_alignment_record)).  Per pair: read / ref = alloc(L, user),
+ * read_start = ref_start = first used index, read_end = ref_end = L-1 (DefaultKernel.cpp:441-453).
+ * The plug-in class calls this with its Alignment[n] array, so no per-pair pass is left on the
+ * calling thread after the pipeline has drained. */
+typedef struct va_cuda_alignment_record {
+    char *read;
+    char *ref;
+    int16_t read_start, read_end, ref_start, ref_end;
+} va_cuda_alignment_record;
+int va_cuda_align_records(va_cuda_ctx *ctx, int opt, int policy, const va_cuda_scoring *sc, int n,
+                          const char *const *reads, int read_length,
+                          const char *const *refs, int ref_length,
+                          va_cuda_alloc_fn alloc, void *user,
+                          void *records, size_t record_stride, int16_t *end_cell);
 
 /* ---- host buffers, contiguous (fixed stride) ----------------------------------------- */
 

@@ -41,7 +41,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_library_loads_and_reports_version():
     L = capi.lib()
-    assert L.va_cuda_abi_version() == 1
+    assert L.va_cuda_abi_version() == 2
     for sym in capi.C_ABI_SYMBOLS + capi.PLUGIN_SYMBOLS:
         assert getattr(L, sym) is not None
 

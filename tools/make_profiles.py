@@ -36,6 +36,7 @@ def main():
              "Command: `python bench.py --steps 2 --warmup 1 --no-cpu` under "
              "`ncu --set full --clock-control none --import-source on`; per-launch times are cold-cache and serialised.", ""]
     traffic = {}
+    done = set()
     for row in rr[2:]:
         name = row[kk]
         lines.append(f"## {name[:110]}")
@@ -49,7 +50,8 @@ def main():
                 lines.append(f"| {m} | {row[i]} | {units[i]} |")
                 vals[m] = (row[i], units[i])
         lines.append("")
-        if "fill_fast" in name and "dram__bytes_read.sum" in vals:
+        if ("fill_nw_kernel" in name or "fill_fast" in name) and "traffic" not in done and "dram__bytes_read.sum" in vals:
+            done.add("traffic")
             def to_bytes(v, u):
                 x = float(v.replace(",", ""))
                 return x * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)

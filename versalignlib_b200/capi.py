@@ -18,7 +18,7 @@ POLICY_DEFAULT_OCL, POLICY_SIMD = 0, 1
 # every symbol include/versalign_cuda.h declares (tests check the .so exports all of them)
 C_ABI_SYMBOLS = [
     "va_cuda_abi_version", "va_cuda_last_error", "va_cuda_device_count", "va_cuda_create", "va_cuda_destroy",
-    "va_cuda_set_host_threads", "va_cuda_get_timings", "va_cuda_score_ptrs", "va_cuda_align_ptrs", "va_cuda_align_alloc",
+    "va_cuda_set_host_threads", "va_cuda_get_timings", "va_cuda_score_ptrs", "va_cuda_align_ptrs", "va_cuda_align_alloc", "va_cuda_align_records",
     "va_cuda_score_flat", "va_cuda_align_flat", "va_cuda_score_device", "va_cuda_align_device",
     "va_cuda_max_resident_pairs", "va_cuda_int_peak", "va_cuda_set_profiling", "va_cuda_get_kernel_ms",
     "va_cuda_plugin_timings",
@@ -57,6 +57,7 @@ def lib():
     global _lib
     if _lib is None:
         path = _build.build_cuda() if os.path.exists(os.path.join(_build.CSRC, "va_kernels.cu")) else _build.CUDA_PLUGIN
+        path = os.environ.get("VERSALIGN_CUDA_LIB", path)  # development aid: an alternative build of the same ABI
         if not os.path.exists(path):
             raise CudaError(f"{path} is missing: run `python -m versalignlib_b200.build`")
         L = ctypes.CDLL(path)

@@ -10,6 +10,7 @@
 //   DefaultKernel_dllexport.cpp:18-42  the four extern "C" symbols + _parameters/_logger     bottom of this file
 //
 // All device work goes through the flat C ABI (versalign_cuda.h); there is no CPU path.
+#include <cstddef>
 #include <stdlib.h>
 #include <string.h>
 
@@ -135,31 +136,20 @@ public:
         if (n <= 0) return;
         // Result blocks must be individually delete[]-able (Alignment::~Alignment), so each is a
         // plain array-new block; the C ABI calls this allocator from its staging threads while
-        // results stream back from the device.
-        std::vector<char *> out_read(n), out_ref(n);
-        std::vector<short> start(n);
-        int rc = va_cuda_align_alloc(ctx_, opt, policy_, &scoring_, n, reads, read_length_, refs, ref_length_,
-                                     [](size_t bytes, void *) -> char * { return new (std::nothrow) char[bytes]; }, nullptr,
-                                     out_read.data(), out_ref.data(), start.data(), nullptr);
-        if (rc != VA_OK) {
-            for (int i = 0; i < n; ++i) {
-                delete[] out_read[i];
-                delete[] out_ref[i];
-            }
-            fatal(std::string("compute_alignments failed: ") + va_cuda_last_error());
-        }
-        const short end = (short)(aln_length_ - 1);
-        parallel_blocks(n, threads, [&](int b, int e) {
-            for (int i = b; i < e; ++i) {
-                Alignment &a = alignments[i];
-                a.read = out_read[i];  // previous contents are neither freed nor reused (reference semantics)
-                a.ref = out_ref[i];
-                a.readStart = start[i];
-                a.refStart = start[i];
-                a.readEnd = end;
-                a.refEnd = end;
-            }
-        });
+        // results stream back from the device, and fills the Alignment records there too (previous
+        // contents are neither freed nor reused: reference semantics).
+        static_assert(sizeof(Alignment) >= sizeof(va_cuda_alignment_record), "Alignment layout");
+        static_assert(offsetof(Alignment, read) == offsetof(va_cuda_alignment_record, read) &&
+                          offsetof(Alignment, ref) == offsetof(va_cuda_alignment_record, ref) &&
+                          offsetof(Alignment, readStart) == offsetof(va_cuda_alignment_record, read_start) &&
+                          offsetof(Alignment, readEnd) == offsetof(va_cuda_alignment_record, read_end) &&
+                          offsetof(Alignment, refStart) == offsetof(va_cuda_alignment_record, ref_start) &&
+                          offsetof(Alignment, refEnd) == offsetof(va_cuda_alignment_record, ref_end),
+                      "va_cuda_alignment_record restates struct Alignment (AlignmentKernel.h:12-24)");
+        int rc = va_cuda_align_records(ctx_, opt, policy_, &scoring_, n, reads, read_length_, refs, ref_length_,
+                                       [](size_t bytes, void *) -> char * { return new (std::nothrow) char[bytes]; }, nullptr,
+                                       alignments, sizeof(Alignment), nullptr);
+        if (rc != VA_OK) fatal(std::string("compute_alignments failed: ") + va_cuda_last_error());
     }
 
 private:

@@ -502,6 +502,8 @@ struct HostCall {
     char **out_read_w = nullptr;
     char **out_ref_w = nullptr;
     std::atomic<int> *alloc_failed = nullptr;
+    char *records = nullptr;  // when set (with alloc): va_cuda_alignment_record at records + i * record_stride
+    size_t record_stride = 0;
     char *out_read_f = nullptr;
     char *out_ref_f = nullptr;
     int16_t *start = nullptr;
@@ -527,7 +529,14 @@ void gather_chunk(va_cuda_ctx *ctx, const HostCall &c, ChunkSlot &s, int64_t fir
         });
     } else {
         ctx->pool->parallel_for(count, 2048, [&](int64_t b, int64_t e) {
+            // the blocks are scattered over the caller's heap: ask for the ones a few pairs ahead now
+            constexpr int AHEAD = 8;
             for (int64_t i = b; i < e; ++i) {
+                if (i + AHEAD < e) {
+                    const char *pr = c.reads_p[first + i + AHEAD], *pf = c.refs_p[first + i + AHEAD];
+                    for (int o = 0; o < RL; o += 64) __builtin_prefetch(pr + o, 0, 0);
+                    for (int o = 0; o < FL; o += 64) __builtin_prefetch(pf + o, 0, 0);
+                }
                 memcpy(hr + i * RL, c.reads_p[first + i], RL);
                 memcpy(hf + i * FL, c.refs_p[first + i], FL);
             }
@@ -544,7 +553,7 @@ void scatter_chunk(va_cuda_ctx *ctx, const HostCall &c, ChunkSlot &s, int64_t fi
     const int16_t *st = (const int16_t *)s.h_start.p;
     const int16_t *ec = (const int16_t *)s.h_end_cell.p;
     const char *ha = (const char *)s.h_aln_read.p, *hb = (const char *)s.h_aln_ref.p;
-    memcpy(c.start + first, st, (size_t)count * sizeof(int16_t));
+    if (c.start) memcpy(c.start + first, st, (size_t)count * sizeof(int16_t));
     if (c.end_cell) memcpy(c.end_cell + 2 * first, ec, (size_t)count * 2 * sizeof(int16_t));
     if (c.out_read_f) {
         ctx->pool->parallel_for(count, 2048, [&](int64_t b, int64_t e) {
@@ -555,6 +564,27 @@ void scatter_chunk(va_cuda_ctx *ctx, const HostCall &c, ChunkSlot &s, int64_t fi
                 char *da = c.out_read_f + (first + i) * L, *db = c.out_ref_f + (first + i) * L;
                 memset(da, 0, (size_t)s0);
                 memset(db, 0, (size_t)s0);
+                memcpy(da + s0, ha + i * L + s0, (size_t)(L - s0));
+                memcpy(db + s0, hb + i * L + s0, (size_t)(L - s0));
+            }
+        });
+    } else if (c.alloc && c.records) {
+        ctx->pool->parallel_for(count, 1024, [&](int64_t b, int64_t e) {
+            for (int64_t i = b; i < e; ++i) {
+                int s0 = st[i];
+                if (s0 < 0) s0 = 0;
+                if (s0 > L) s0 = L;
+                char *da = c.alloc((size_t)(L > 0 ? L : 1), c.alloc_user);
+                char *db = c.alloc((size_t)(L > 0 ? L : 1), c.alloc_user);
+                va_cuda_alignment_record *rec = reinterpret_cast<va_cuda_alignment_record *>(c.records + (size_t)(first + i) * c.record_stride);
+                rec->read = da;
+                rec->ref = db;
+                rec->read_start = rec->ref_start = st[i];
+                rec->read_end = rec->ref_end = (int16_t)(L - 1);
+                if (!da || !db) {
+                    c.alloc_failed->store(1);
+                    continue;
+                }
                 memcpy(da + s0, ha + i * L + s0, (size_t)(L - s0));
                 memcpy(db + s0, hb + i * L + s0, (size_t)(L - s0));
             }
@@ -889,6 +919,30 @@ int va_cuda_align_alloc(va_cuda_ctx *ctx, int opt, int policy, const va_cuda_sco
     c.out_ref_w = out_ref;
     c.alloc_failed = &failed;
     c.start = start;
+    c.end_cell = end_cell;
+    rc = run_host_call(ctx, c);
+    if (rc == VA_OK && failed.load()) return set_error(VA_ERR_MEMORY, "the caller's allocator returned NULL");
+    return rc;
+}
+
+int va_cuda_align_records(va_cuda_ctx *ctx, int opt, int policy, const va_cuda_scoring *sc, int n, const char *const *reads,
+                          int read_length, const char *const *refs, int ref_length, va_cuda_alloc_fn alloc, void *user,
+                          void *records, size_t record_stride, int16_t *end_cell) {
+    HostCall c;
+    bool noop;
+    int rc = prepare_call(ctx, c, opt, true, policy, sc, n, read_length, ref_length, &noop);
+    if (rc || noop) return rc;
+    if (!alloc) return set_error(VA_ERR_ARG, "alloc is null");
+    if (n > 0 && (!reads || !refs || !records)) return set_error(VA_ERR_ARG, "null buffer");
+    if (record_stride < sizeof(va_cuda_alignment_record)) return set_error(VA_ERR_ARG, "record_stride is smaller than the record");
+    std::atomic<int> failed{0};
+    c.reads_p = reads;
+    c.refs_p = refs;
+    c.alloc = alloc;
+    c.alloc_user = user;
+    c.records = (char *)records;
+    c.record_stride = record_stride;
+    c.alloc_failed = &failed;
     c.end_cell = end_cell;
     rc = run_host_call(ctx, c);
     if (rc == VA_OK && failed.load()) return set_error(VA_ERR_MEMORY, "the caller's allocator returned NULL");

@@ -26,11 +26,13 @@ namespace va {
 
 namespace {
 
-#ifndef VA_NW_NT
-#define VA_NW_NT 128
-#endif
-constexpr int NT = VA_NW_NT;                    // threads per block
-constexpr int MAXREG = NT == 96 ? 136 : 128;   // 5 x 96 threads per SM leave 136 registers each, 4 x 128 leave 128
+// Threads per block: 4 x 128 threads per SM leave 128 registers each (align: the planes need the warps),
+// 5 x 96 leave 136 (score: measured faster).
+template <bool ALIGN>
+struct Block {
+    static constexpr int NT = ALIGN ? 128 : 96;
+    static constexpr int MAXREG = ALIGN ? 128 : 136;
+};
 constexpr uint32_t NEG2 = 0x80008000u;  // (-32768, -32768): identity of the packed max
 
 __device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b) { return __viaddmax_s16x2(a, b, NEG2); }
@@ -53,8 +55,9 @@ __device__ __forceinline__ void cp_async_wait() {
 // halves of the shared words stored with 16-bit stores.  Kept apart so the duo kernel's stores stay
 // unconditional (its schedule sits right at the register budget).
 template <bool ALIGN, int TW, bool SOLO>
-__global__ void __maxnreg__(MAXREG) fill_nw_kernel(ChunkGeom g, ChunkBuffers b, FastConsts fc) {
+__global__ void __maxnreg__(Block<ALIGN>::MAXREG) fill_nw_kernel(ChunkGeom g, ChunkBuffers b, FastConsts fc) {
     constexpr int NG = (TW + 15) / 16;
+    constexpr int NT = Block<ALIGN>::NT;
     constexpr int MODE = ALIGN ? MODE_NW_ALIGN : MODE_NW_SCORE;
 
     __shared__ uint2 s_T2[256];              // [6*code_a + code_b] -> the two lanes' 4-entry score tables (36 used)
@@ -256,7 +259,9 @@ __global__ void __maxnreg__(MAXREG) fill_nw_kernel(ChunkGeom g, ChunkBuffers b, 
     };
     const int thread = blockIdx.x * blockDim.x + threadIdx.x;
     if constexpr (!SOLO) {  // thread t takes duo t
-        const FastWork fw = fast_work_duo(g, b.meta, MODE, thread);
+        // slots are sorted by ascending extents: blocks are taken from the far end so the longest pairs start
+        // first and the last wave is made of the short ones
+        const FastWork fw = fast_work_duo(g, b.meta, MODE, (int)(gridDim.x - 1 - blockIdx.x) * (int)blockDim.x + (int)threadIdx.x);
         if (fw.own == OWN_DUO) run(fw);
     } else {  // grid-stride loop over the slots the prep kernel listed
         const int count = *b.solo_count;
@@ -268,7 +273,7 @@ __global__ void __maxnreg__(MAXREG) fill_nw_kernel(ChunkGeom g, ChunkBuffers b, 
 
 template <bool ALIGN, int TW>
 void launch_one(const ChunkGeom &g, const ChunkBuffers &b, const FastConsts &fc, cudaStream_t stream) {
-    const int threads = NT;
+    const int threads = Block<ALIGN>::NT;
     const int duos = (g.n + 1) / 2;
     const int blocks = (duos + threads - 1) / threads;
     if (g.n >= 2) fill_nw_kernel<ALIGN, TW, false><<<blocks, threads, 0, stream>>>(g, b, fc);
