@@ -169,6 +169,33 @@ int va_cuda_align_flat(va_cuda_ctx *ctx, int opt, int policy, const va_cuda_scor
                        const char *reads, int read_length, const char *refs, int ref_length,
                        char *aln_read, char *aln_ref, int16_t *start, int16_t *end_cell);
 
+/* ---- batch-friendly entry points (beside the reference's convention) ------------------ */
+
+/* The reference's interface forces three host-side costs on a large batch: every sequence is a
+ * separate heap block padded to the batch maximum (versalignUtil.cpp:17-33 pad()), every result
+ * is two more heap blocks of read_length+ref_length bytes (DefaultKernel.cpp:441-442), and the
+ * gapped strings are ~4x the information of the alignment itself.  These two entry points keep
+ * the kernels and their semantics (same scores, same end cells, same paths) and change only the
+ * containers:
+ *   in   read i = reads[read_off[i] .. read_off[i+1]), ref i likewise: contiguous ASCII bases,
+ *        per-pair lengths (<= 32000 each, read+ref <= 32767), no padding, no terminator;
+ *        n+1 offsets per side
+ *   out  scores[n];  coords[n][4] = read_begin, read_end, ref_begin, ref_end of the aligned
+ *        region in SEQUENCE coordinates (0-based, half open);  a CIGAR per pair in BAM encoding
+ *        (length << 4 | op, op 0 = M read and ref base, 1 = I read base against a gap, 2 = D ref
+ *        base against a gap), pair i's runs at (*cigar)[cigar_off[i] .. cigar_off[i+1]).
+ * Results leave the device as 2-bit moves (~(read+ref)/4 bytes per pair instead of 2*(read+ref)).
+ * *cigar is ONE block obtained from alloc(bytes, user) after the batch is done (the caller frees
+ * it); pass cigar = NULL to skip CIGARs, coords / scores = NULL to skip those. */
+int va_cuda_score_packed(va_cuda_ctx *ctx, int opt, const va_cuda_scoring *sc, int n,
+                         const char *reads, const int64_t *read_off,
+                         const char *refs, const int64_t *ref_off, int16_t *scores);
+int va_cuda_align_packed(va_cuda_ctx *ctx, int opt, int policy, const va_cuda_scoring *sc, int n,
+                         const char *reads, const int64_t *read_off,
+                         const char *refs, const int64_t *ref_off,
+                         int16_t *scores, int32_t *coords, int64_t *cigar_off,
+                         va_cuda_alloc_fn alloc, void *user, uint32_t **cigar);
+
 /* ---- device-resident buffers (device 0 of the context) ------------------------------- */
 
 /* Inputs and outputs already in HBM, same flat layouts as above; work is enqueued on

@@ -228,3 +228,62 @@ def test_long_pairs_intra_task_kernel(ctx):
     # mixed lengths + an odd pair count: partial last pass, general-kernel tail
     reads, refs, _, _ = synth.mixed_batch(33, 900, 1500, p_sub=0.1, q_indel=0.02, seed=34)
     assert np.array_equal(ctx.score_flat(ora.SW, reads, refs), ora.score(ora.SW, reads, refs))
+
+
+@pytest.mark.parametrize("opt", [ora.SW, ora.NW])
+def test_packed_entry_points(ctx, opt):
+    """Batch-friendly containers, same kernels: offset-addressed sequences in; scores, sequence coordinates
+    and CIGARs out must be exactly what the reference-style outputs (oracle) say."""
+    for name, reads, refs in [BATCHES[3], BATCHES[1], BATCHES[6]]:  # mixed lengths, uniform with indels, tiny
+        pr, ro = synth.pack_batch(reads)
+        pf, fo = synth.pack_batch(refs)
+        # the semantics are the reference's on the batch padded to ITS maximum lengths
+        reads = np.ascontiguousarray(reads[:, :max(int(np.diff(ro).max()), 1)])
+        refs = np.ascontiguousarray(refs[:, :max(int(np.diff(fo).max()), 1)])
+        assert np.array_equal(ctx.score_packed(opt, pr, ro, pf, fo), ora.score(opt, reads, refs)), name
+        for policy in (0, 1):
+            scores, coords, coff, cigar = ctx.align_packed(opt, policy, pr, ro, pf, fo)
+            oa, ob, ostart, oend = ora.align(opt, policy, reads, refs)
+            want_coords, want_off, want_cigar = synth.cigar_from_strings(oa, ob, ostart, oend)
+            assert np.array_equal(coff, want_off), (name, policy)
+            assert np.array_equal(cigar, want_cigar), (name, policy)
+            assert np.array_equal(coords, want_coords), (name, policy)
+            if opt == ora.SW:
+                assert np.array_equal(scores, ora.score(opt, reads, refs)), (name, policy)
+
+
+def test_positive_gap_scores_stay_exact(ctx):
+    """Gap scores > 0 are outside the packed kernels' domain (their padding arguments need gaps <= 0):
+    the general kernel must take over, results unchanged."""
+    _, reads, refs = BATCHES[3]
+    for sc in [(2, -1, 1, -3), (2, -1, -2, 1)]:
+        for opt in (ora.SW, ora.NW):
+            assert np.array_equal(ctx.score_flat(opt, reads, refs, sc), ora.score(opt, reads, refs, sc)), (sc, opt)
+
+
+def test_mixed_lengths_at_scale(ctx):
+    """Length-bucketed mixed batch big enough that every strip width, padded last strips, and the
+    solo path (odd leftovers of the bucketing) all occur many times: all four functions against the oracle."""
+    reads, refs, _, _ = synth.mixed_batch(12_000, 60, 250, p_sub=0.1, q_indel=0.02, seed=synth.BASE_SEED + 33)
+    for opt in (ora.SW, ora.NW):
+        assert np.array_equal(ctx.score_flat(opt, reads, refs), ora.score(opt, reads, refs)), opt
+        a, b, start, end = ctx.align_flat(opt, 0, reads, refs)
+        oa, ob, ostart, oend = ora.align(opt, 0, reads, refs)
+        assert np.array_equal(start, ostart) and np.array_equal(end, oend), opt
+        assert used_region_equal(a, b, start, oa, ob, ostart).size == 0, opt
+
+
+def test_workspace_reuse_across_scorings(ctx):
+    """The device workspace is reused between calls.  A call whose values are large (NW with big scores)
+    must not leak into a later SW-align call through the halves of the words that solo threads share
+    (regression: SW align's packed key crosses lanes)."""
+    r0, f0 = synth.uniform_batch(1000, 100, 150, p_sub=0.10, seed=synth.BASE_SEED + 1)
+    big = (20, -30, -50, -40)
+    assert np.array_equal(ctx.score_flat(ora.NW, r0, f0, big), ora.score(ora.NW, r0, f0, big))
+    ctx.align_flat(ora.NW, 0, r0, f0, big)
+    _, reads, refs = BATCHES[3]
+    for opt in (ora.SW, ora.NW):
+        a, b, start, end = ctx.align_flat(opt, 0, reads, refs)
+        oa, ob, ostart, oend = ora.align(opt, 0, reads, refs)
+        assert np.array_equal(start, ostart) and np.array_equal(end, oend), opt
+        assert used_region_equal(a, b, start, oa, ob, ostart).size == 0, opt

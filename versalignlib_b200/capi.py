@@ -18,7 +18,7 @@ POLICY_DEFAULT_OCL, POLICY_SIMD = 0, 1
 # every symbol include/versalign_cuda.h declares (tests check the .so exports all of them)
 C_ABI_SYMBOLS = [
     "va_cuda_abi_version", "va_cuda_last_error", "va_cuda_device_count", "va_cuda_create", "va_cuda_destroy",
-    "va_cuda_set_host_threads", "va_cuda_get_timings", "va_cuda_score_ptrs", "va_cuda_align_ptrs", "va_cuda_align_alloc", "va_cuda_align_records",
+    "va_cuda_set_host_threads", "va_cuda_get_timings", "va_cuda_score_ptrs", "va_cuda_align_ptrs", "va_cuda_align_alloc", "va_cuda_align_records", "va_cuda_score_packed", "va_cuda_align_packed",
     "va_cuda_score_flat", "va_cuda_align_flat", "va_cuda_score_device", "va_cuda_align_device",
     "va_cuda_max_resident_pairs", "va_cuda_int_peak", "va_cuda_set_profiling", "va_cuda_get_kernel_ms",
     "va_cuda_plugin_timings",
@@ -46,6 +46,9 @@ class CudaError(RuntimeError):
 
 
 _lib = None
+
+# va_cuda_alloc_fn: char* (*)(size_t bytes, void* user)
+_ALLOC_FN = ctypes.CFUNCTYPE(ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p)
 
 
 def library_path() -> str:
@@ -75,6 +78,8 @@ def lib():
         L.va_cuda_align_ptrs.argtypes = [vp, ci, ci, sp, ci, vp, ci, vp, ci, vp, vp, vp, vp]
         L.va_cuda_score_flat.argtypes = [vp, ci, sp, ci, vp, ci, vp, ci, vp]
         L.va_cuda_align_flat.argtypes = [vp, ci, ci, sp, ci, vp, ci, vp, ci, vp, vp, vp, vp]
+        L.va_cuda_score_packed.argtypes = [vp, ci, sp, ci, vp, vp, vp, vp, vp]
+        L.va_cuda_align_packed.argtypes = [vp, ci, ci, sp, ci, vp, vp, vp, vp, vp, vp, vp, _ALLOC_FN, vp, vp]
         L.va_cuda_score_device.argtypes = [vp, ci, sp, ci, vp, ci, vp, ci, vp, vp]
         L.va_cuda_align_device.argtypes = [vp, ci, ci, sp, ci, vp, ci, vp, ci, vp, vp, vp, vp, vp]
         L.va_cuda_max_resident_pairs.argtypes = [vp, ci, ci, ci, ctypes.POINTER(ctypes.c_int64)]
@@ -204,6 +209,45 @@ class CudaContext:
                                                fp.ctypes.data, refs.shape[1], ap.ctypes.data, bp.ctypes.data,
                                                start.ctypes.data, end.ctypes.data), "va_cuda_align_ptrs")
         return a, b, start, end
+
+    # ---- batch-friendly: offset-addressed sequences, CIGAR out -------------------------
+    def score_packed(self, opt: int, reads: np.ndarray, read_off: np.ndarray, refs: np.ndarray, ref_off: np.ndarray,
+                     scoring=(2, -1, -3, -3)) -> np.ndarray:
+        """reads / refs: 1-D uint8 (all sequences back to back); *_off: int64[n+1]."""
+        reads, refs = np.ascontiguousarray(reads, np.uint8), np.ascontiguousarray(refs, np.uint8)
+        read_off, ref_off = np.ascontiguousarray(read_off, np.int64), np.ascontiguousarray(ref_off, np.int64)
+        n = read_off.shape[0] - 1
+        out = np.zeros(n, dtype=np.int16)
+        sc = Scoring(*scoring)
+        self._check(self._L.va_cuda_score_packed(self._h, opt, ctypes.byref(sc), n, reads.ctypes.data, read_off.ctypes.data,
+                                                 refs.ctypes.data, ref_off.ctypes.data, out.ctypes.data), "va_cuda_score_packed")
+        return out
+
+    def align_packed(self, opt: int, policy: int, reads: np.ndarray, read_off: np.ndarray, refs: np.ndarray,
+                     ref_off: np.ndarray, scoring=(2, -1, -3, -3)):
+        """Returns (scores[n], coords[n,4] = read_begin, read_end, ref_begin, ref_end, cigar_off[n+1], cigar uint32[])."""
+        reads, refs = np.ascontiguousarray(reads, np.uint8), np.ascontiguousarray(refs, np.uint8)
+        read_off, ref_off = np.ascontiguousarray(read_off, np.int64), np.ascontiguousarray(ref_off, np.int64)
+        n = read_off.shape[0] - 1
+        scores = np.zeros(n, dtype=np.int16)
+        coords = np.zeros((n, 4), dtype=np.int32)
+        cigar_off = np.zeros(n + 1, dtype=np.int64)
+        blocks = []
+
+        def _alloc(nbytes, _user):
+            buf = np.empty(max(int(nbytes) // 4, 1), dtype=np.uint32)
+            blocks.append(buf)
+            return buf.ctypes.data
+
+        cb = _ALLOC_FN(_alloc)
+        out_ptr = ctypes.c_void_p()
+        sc = Scoring(*scoring)
+        self._check(self._L.va_cuda_align_packed(self._h, opt, policy, ctypes.byref(sc), n, reads.ctypes.data,
+                                                 read_off.ctypes.data, refs.ctypes.data, ref_off.ctypes.data,
+                                                 scores.ctypes.data, coords.ctypes.data, cigar_off.ctypes.data, cb, None,
+                                                 ctypes.byref(out_ptr)), "va_cuda_align_packed")
+        cigar = blocks[0][: int(cigar_off[n])] if blocks else np.zeros(0, np.uint32)
+        return scores, coords, cigar_off, cigar
 
     # ---- device-resident (torch tensors supply the memory and the stream) --------------
     def score_device(self, opt: int, d_reads, d_refs, d_scores, scoring=(2, -1, -3, -3), stream: int = 0) -> None:

@@ -214,8 +214,8 @@ struct PinBuf {
 
 // Device workspace of one chunk in flight.
 struct ChunkSlot {
-    DevBuf raw_reads, raw_refs, code_reads, code_refs, row_idx, solo_list, meta, pair_of, prep_scratch, boundary, dirs, hrow, queue, scores, end_cell, aln_read, aln_ref, start;
-    PinBuf h_reads, h_refs, h_scores, h_end_cell, h_aln_read, h_aln_ref, h_start;
+    DevBuf raw_reads, raw_refs, code_reads, code_refs, row_idx, solo_list, meta, pair_of, prep_scratch, boundary, dirs, hrow, queue, scores, end_cell, aln_read, aln_ref, start, moves;
+    PinBuf h_reads, h_refs, h_scores, h_end_cell, h_aln_read, h_aln_ref, h_start, h_moves;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_done = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
     // what is currently in flight in this slot
@@ -224,9 +224,9 @@ struct ChunkSlot {
     bool busy = false;
 
     void release() {
-        DevBuf *d[] = {&raw_reads, &raw_refs, &code_reads, &code_refs, &row_idx, &solo_list, &meta, &pair_of, &prep_scratch, &boundary, &dirs, &hrow, &queue, &scores, &end_cell, &aln_read, &aln_ref, &start};
+        DevBuf *d[] = {&raw_reads, &raw_refs, &code_reads, &code_refs, &row_idx, &solo_list, &meta, &pair_of, &prep_scratch, &boundary, &dirs, &hrow, &queue, &scores, &end_cell, &aln_read, &aln_ref, &start, &moves};
         for (auto *b : d) b->release();
-        PinBuf *h[] = {&h_reads, &h_refs, &h_scores, &h_end_cell, &h_aln_read, &h_aln_ref, &h_start};
+        PinBuf *h[] = {&h_reads, &h_refs, &h_scores, &h_end_cell, &h_aln_read, &h_aln_ref, &h_start, &h_moves};
         for (auto *b : h) b->release();
         if (ev_done) cudaEventDestroy(ev_done);
         if (ev_k0) cudaEventDestroy(ev_k0);
@@ -288,6 +288,8 @@ struct Shape {
     int read_length, ref_length, L;
     int read_chunks, ref_chunks, segs, rows_alloc;
     bool align;
+    bool moves = false;  // align results leave the device as 2-bit move queues (packed entry points), not as strings
+    size_t queue_words() const { return traceback_queue_words(read_length, ref_length); }
     // direction bytes per matrix row and pair: the general and the packed kernel keep separate
     // regions because one chunk can hold pairs of both kinds
     size_t gen_dir_row_bytes() const { return (size_t)segs * 2; }
@@ -303,7 +305,7 @@ struct Shape {
     }
     size_t per_pair_io() const {
         size_t b = (size_t)read_length + ref_length + 2 + 4;
-        if (align) b += 2 * (size_t)L + 2;
+        if (align) b += (moves ? queue_words() * 4 : 2 * (size_t)L) + 2;
         return b;
     }
 };
@@ -374,8 +376,12 @@ int reserve_slot(ChunkSlot &s, const Shape &sh, int cap_pairs, bool pinned) {
         const size_t qw = traceback_queue_words(sh.read_length, sh.ref_length);
         if (qw * 128 * 4 > 48 * 1024 && (rc = s.queue.reserve(slots * qw * 4 + 64))) return rc;
         if (pinned) {
-            if ((rc = s.aln_read.reserve((size_t)cap_pairs * sh.L + 16))) return rc;
-            if ((rc = s.aln_ref.reserve((size_t)cap_pairs * sh.L + 16))) return rc;
+            if (sh.moves) {
+                if ((rc = s.moves.reserve((size_t)cap_pairs * sh.queue_words() * 4 + 16))) return rc;
+            } else {
+                if ((rc = s.aln_read.reserve((size_t)cap_pairs * sh.L + 16))) return rc;
+                if ((rc = s.aln_ref.reserve((size_t)cap_pairs * sh.L + 16))) return rc;
+            }
             if ((rc = s.start.reserve(slots * 2))) return rc;
         }
     }
@@ -386,8 +392,12 @@ int reserve_slot(ChunkSlot &s, const Shape &sh, int cap_pairs, bool pinned) {
         if ((rc = s.h_scores.reserve(slots * 2))) return rc;
         if ((rc = s.h_end_cell.reserve(slots * 4))) return rc;
         if (sh.align) {
-            if ((rc = s.h_aln_read.reserve((size_t)cap_pairs * sh.L + 16))) return rc;
-            if ((rc = s.h_aln_ref.reserve((size_t)cap_pairs * sh.L + 16))) return rc;
+            if (sh.moves) {
+                if ((rc = s.h_moves.reserve((size_t)cap_pairs * sh.queue_words() * 4 + 16))) return rc;
+            } else {
+                if ((rc = s.h_aln_read.reserve((size_t)cap_pairs * sh.L + 16))) return rc;
+                if ((rc = s.h_aln_ref.reserve((size_t)cap_pairs * sh.L + 16))) return rc;
+            }
             if ((rc = s.h_start.reserve(slots * 2))) return rc;
         }
     }
@@ -413,7 +423,7 @@ void fill_geom(ChunkGeom &g, const Shape &sh, int n) {
 int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int policy, const Scoring &sc, int n,
                         const uint8_t *raw_reads, const uint8_t *raw_refs, int16_t *scores, int16_t *end_cell,
                         uint8_t *aln_read, uint8_t *aln_ref, int16_t *start, bool zero_prefix, cudaStream_t stream,
-                        bool profile = false) {
+                        bool profile = false, uint32_t *moves_out = nullptr) {
     ChunkGeom g;
     fill_geom(g, sh, n);
     // VERSALIGN_CUDA_GENERAL_ONLY=1 keeps every pair on the 32-bit kernel (parity tests use it to
@@ -440,6 +450,7 @@ int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int
     b.aln_read = aln_read;
     b.aln_ref = aln_ref;
     b.start = start;
+    b.moves_out = moves_out;
     b.cell_count = e.d_cells;
     int launches = 0;
     cudaEvent_t *pe = nullptr;
@@ -470,7 +481,7 @@ int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int
     launches += launch_fill_general(g, b, mode, policy, sc, stream);
     if (pe) cudaEventRecord(pe[2], stream);
     if (sh.align) {
-        if (zero_prefix) {  // bytes before start[i] are promised to be zero on this path
+        if (zero_prefix && !moves_out) {  // bytes before start[i] are promised to be zero on this path
             cudaMemsetAsync(aln_read, 0, (size_t)n * sh.L, stream);
             cudaMemsetAsync(aln_ref, 0, (size_t)n * sh.L, stream);
         }
@@ -508,6 +519,14 @@ struct HostCall {
     char *out_ref_f = nullptr;
     int16_t *start = nullptr;
     int16_t *end_cell = nullptr;
+    // packed (offset-addressed) inputs and CIGAR outputs of the batch-friendly entry points
+    const int64_t *read_off = nullptr;
+    const int64_t *ref_off = nullptr;
+    int32_t *coords = nullptr;                        // [n][4]: read_begin, read_end, ref_begin, ref_end (0-based, half open)
+    int64_t *cigar_off = nullptr;                     // [n+1]; filled with per-pair op counts first, prefix-summed at the end
+    std::vector<std::vector<uint32_t>> *cigar_parts = nullptr;  // one vector per chunk, indexed by global chunk number
+    std::vector<int64_t> *cigar_part_first = nullptr;           // first pair of each part
+    std::mutex *cigar_mu = nullptr;
 };
 
 struct ShardStats {
@@ -522,7 +541,19 @@ struct ShardStats {
 void gather_chunk(va_cuda_ctx *ctx, const HostCall &c, ChunkSlot &s, int64_t first, int count) {
     char *hr = (char *)s.h_reads.p, *hf = (char *)s.h_refs.p;
     const int RL = c.sh.read_length, FL = c.sh.ref_length;
-    if (c.reads_f) {
+    if (c.read_off) {
+        // offset-addressed sequences -> the kernels' fixed-stride, '\0'-padded staging layout
+        ctx->pool->parallel_for(count, 2048, [&](int64_t b, int64_t e) {
+            for (int64_t i = b; i < e; ++i) {
+                const int64_t r0 = c.read_off[first + i], r1 = c.read_off[first + i + 1];
+                const int64_t f0 = c.ref_off[first + i], f1 = c.ref_off[first + i + 1];
+                memcpy(hr + i * RL, c.reads_f + r0, (size_t)(r1 - r0));
+                memset(hr + i * RL + (r1 - r0), 0, (size_t)(RL - (r1 - r0)));
+                memcpy(hf + i * FL, c.refs_f + f0, (size_t)(f1 - f0));
+                memset(hf + i * FL + (f1 - f0), 0, (size_t)(FL - (f1 - f0)));
+            }
+        });
+    } else if (c.reads_f) {
         ctx->pool->parallel_for(count, 4096, [&](int64_t b, int64_t e) {
             memcpy(hr + b * RL, c.reads_f + (first + b) * RL, (size_t)(e - b) * RL);
             memcpy(hf + b * FL, c.refs_f + (first + b) * FL, (size_t)(e - b) * FL);
@@ -544,6 +575,70 @@ void gather_chunk(va_cuda_ctx *ctx, const HostCall &c, ChunkSlot &s, int64_t fir
     }
 }
 
+// Packed entry points: a pair's result arrives as its 2-bit move queue (last alignment column first).
+// Replayed backwards it becomes a CIGAR (BAM encoding: length << 4 | op; M = 0 read and ref base,
+// I = 1 read base against a gap, D = 2 ref base against a gap) and the aligned coordinate ranges.
+void scatter_moves(va_cuda_ctx *ctx, const HostCall &c, ChunkSlot &s, int64_t first, int count) {
+    const int L = c.sh.L;
+    const size_t qw = c.sh.queue_words();
+    const int16_t *st = (const int16_t *)s.h_start.p;
+    const int16_t *ec = (const int16_t *)s.h_end_cell.p;
+    const int16_t *sc = (const int16_t *)s.h_scores.p;
+    const uint32_t *mv = (const uint32_t *)s.h_moves.p;
+    if (c.scores) memcpy(c.scores + first, sc, (size_t)count * sizeof(int16_t));
+    if (c.end_cell) memcpy(c.end_cell + 2 * first, ec, (size_t)count * 2 * sizeof(int16_t));
+    // forward replay of pair i: fn(op, run length) per CIGAR run; returns the number of runs
+    auto replay = [&](int64_t i, auto &&fn) -> int {
+        const int n_moves = std::max(0, L - 1 - (int)st[i]);
+        const uint32_t *q = mv + (size_t)i * qw;
+        int runs = 0, cur = -1, len = 0;
+        for (int t = n_moves - 1; t >= 0; --t) {
+            const int code = (q[t >> 4] >> (2 * (t & 15))) & 3;
+            const int op = code == DIR_DIAG ? 0 : code == DIR_UP ? 1 : 2;
+            if (op == cur) {
+                ++len;
+            } else {
+                if (len) { fn(cur, len); ++runs; }
+                cur = op;
+                len = 1;
+            }
+        }
+        if (len) { fn(cur, len); ++runs; }
+        return runs;
+    };
+    std::vector<int64_t> offs((size_t)count + 1, 0);
+    ctx->pool->parallel_for(count, 2048, [&](int64_t b, int64_t e) {
+        for (int64_t i = b; i < e; ++i) {
+            int used_read = 0, used_ref = 0;
+            const int runs = replay(i, [&](int op, int len) {
+                if (op != 2) used_read += len;
+                if (op != 1) used_ref += len;
+            });
+            offs[(size_t)i + 1] = runs;
+            if (c.coords) {
+                int32_t *co = c.coords + 4 * (first + i);
+                co[1] = (int32_t)ec[2 * i] + 1;
+                co[0] = co[1] - used_read;
+                co[3] = (int32_t)ec[2 * i + 1] + 1;
+                co[2] = co[3] - used_ref;
+            }
+            if (c.cigar_off) c.cigar_off[first + i + 1] = runs;
+        }
+    });
+    if (!c.cigar_parts) return;
+    for (int64_t i = 0; i < count; ++i) offs[(size_t)i + 1] += offs[(size_t)i];
+    std::vector<uint32_t> part((size_t)offs[(size_t)count]);
+    ctx->pool->parallel_for(count, 2048, [&](int64_t b, int64_t e) {
+        for (int64_t i = b; i < e; ++i) {
+            uint32_t *out = part.data() + offs[(size_t)i];
+            replay(i, [&](int op, int len) { *out++ = ((uint32_t)len << 4) | (uint32_t)op; });
+        }
+    });
+    std::lock_guard<std::mutex> lk(*c.cigar_mu);
+    c.cigar_parts->push_back(std::move(part));
+    c.cigar_part_first->push_back(first);
+}
+
 void scatter_chunk(va_cuda_ctx *ctx, const HostCall &c, ChunkSlot &s, int64_t first, int count) {
     const int L = c.sh.L;
     if (!c.sh.align) {
@@ -552,6 +647,10 @@ void scatter_chunk(va_cuda_ctx *ctx, const HostCall &c, ChunkSlot &s, int64_t fi
     }
     const int16_t *st = (const int16_t *)s.h_start.p;
     const int16_t *ec = (const int16_t *)s.h_end_cell.p;
+    if (c.sh.moves) {
+        scatter_moves(ctx, c, s, first, count);
+        return;
+    }
     const char *ha = (const char *)s.h_aln_read.p, *hb = (const char *)s.h_aln_ref.p;
     if (c.start) memcpy(c.start + first, st, (size_t)count * sizeof(int16_t));
     if (c.end_cell) memcpy(c.end_cell + 2 * first, ec, (size_t)count * 2 * sizeof(int16_t));
@@ -667,13 +766,20 @@ void run_shard(va_cuda_ctx *ctx, Engine &e, const HostCall &c, int64_t lo, int64
         int launches = enqueue_device_work(e, s, c.sh, c.mode, c.policy, c.sc, count, (const uint8_t *)s.raw_reads.p,
                                            (const uint8_t *)s.raw_refs.p, (int16_t *)s.scores.p, (int16_t *)s.end_cell.p,
                                            (uint8_t *)s.aln_read.p, (uint8_t *)s.aln_ref.p, (int16_t *)s.start.p,
-                                           zero_prefix, s.stream);
+                                           zero_prefix, s.stream, false, c.sh.moves ? (uint32_t *)s.moves.p : nullptr);
         if (launches < 0) return fail(launches);
         st.launches += launches;
         cudaEventRecord(s.ev_k1, s.stream);
         if (!c.sh.align) {
             cudaMemcpyAsync(s.h_scores.p, s.scores.p, (size_t)count * 2, cudaMemcpyDeviceToHost, s.stream);
             st.d2h += (int64_t)count * 2;
+        } else if (c.sh.moves) {
+            const size_t qb = c.sh.queue_words() * 4;
+            cudaMemcpyAsync(s.h_moves.p, s.moves.p, (size_t)count * qb, cudaMemcpyDeviceToHost, s.stream);
+            cudaMemcpyAsync(s.h_start.p, s.start.p, (size_t)count * 2, cudaMemcpyDeviceToHost, s.stream);
+            cudaMemcpyAsync(s.h_end_cell.p, s.end_cell.p, (size_t)count * 4, cudaMemcpyDeviceToHost, s.stream);
+            cudaMemcpyAsync(s.h_scores.p, s.scores.p, (size_t)count * 2, cudaMemcpyDeviceToHost, s.stream);
+            st.d2h += (int64_t)count * (int64_t)(qb + 8);
         } else {
             cudaMemcpyAsync(s.h_aln_read.p, s.aln_read.p, (size_t)count * L, cudaMemcpyDeviceToHost, s.stream);
             cudaMemcpyAsync(s.h_aln_ref.p, s.aln_ref.p, (size_t)count * L, cudaMemcpyDeviceToHost, s.stream);
@@ -964,6 +1070,87 @@ int va_cuda_align_flat(va_cuda_ctx *ctx, int opt, int policy, const va_cuda_scor
     c.start = start;
     c.end_cell = end_cell;
     return run_host_call(ctx, c);
+}
+
+// ---- batch-friendly entry points: offset-addressed sequences in, scores / coordinates / CIGARs out ----
+static int packed_lengths(int n, const int64_t *read_off, const int64_t *ref_off, int *read_length, int *ref_length) {
+    int64_t rl = 0, fl = 0;
+    for (int i = 0; i < n; ++i) {
+        const int64_t a = read_off[i + 1] - read_off[i], b = ref_off[i + 1] - ref_off[i];
+        if (a < 0 || b < 0) return set_error(VA_ERR_ARG, "offsets of pair %d decrease", i);
+        rl = std::max(rl, a);
+        fl = std::max(fl, b);
+    }
+    if (rl > 32000 || fl > 32000) return set_error(VA_ERR_RANGE, "a sequence is longer than 32000 bases");
+    *read_length = (int)rl;
+    *ref_length = (int)fl;
+    return VA_OK;
+}
+
+int va_cuda_score_packed(va_cuda_ctx *ctx, int opt, const va_cuda_scoring *sc, int n, const char *reads,
+                         const int64_t *read_off, const char *refs, const int64_t *ref_off, int16_t *scores) {
+    if (n < 0) return set_error(VA_ERR_ARG, "n < 0");
+    if (n > 0 && (!reads || !refs || !read_off || !ref_off || !scores)) return set_error(VA_ERR_ARG, "null buffer");
+    int rl = 0, fl = 0;
+    int rc = packed_lengths(n, read_off, ref_off, &rl, &fl);
+    if (rc) return rc;
+    HostCall c;
+    bool noop;
+    rc = prepare_call(ctx, c, opt, false, 0, sc, n, rl, fl, &noop);
+    if (rc || noop) return rc;
+    c.reads_f = reads;
+    c.refs_f = refs;
+    c.read_off = read_off;
+    c.ref_off = ref_off;
+    c.scores = scores;
+    return run_host_call(ctx, c);
+}
+
+int va_cuda_align_packed(va_cuda_ctx *ctx, int opt, int policy, const va_cuda_scoring *sc, int n, const char *reads,
+                         const int64_t *read_off, const char *refs, const int64_t *ref_off, int16_t *scores,
+                         int32_t *coords, int64_t *cigar_off, va_cuda_alloc_fn alloc, void *user, uint32_t **cigar) {
+    if (n < 0) return set_error(VA_ERR_ARG, "n < 0");
+    if (n > 0 && (!reads || !refs || !read_off || !ref_off)) return set_error(VA_ERR_ARG, "null buffer");
+    if (cigar && (!alloc || !cigar_off)) return set_error(VA_ERR_ARG, "cigar output needs alloc and cigar_off");
+    if (cigar) *cigar = nullptr;
+    int rl = 0, fl = 0;
+    int rc = packed_lengths(n, read_off, ref_off, &rl, &fl);
+    if (rc) return rc;
+    HostCall c;
+    bool noop;
+    rc = prepare_call(ctx, c, opt, true, policy, sc, n, rl, fl, &noop);
+    if (rc || noop) return rc;
+    c.sh.moves = true;
+    c.reads_f = reads;
+    c.refs_f = refs;
+    c.read_off = read_off;
+    c.ref_off = ref_off;
+    c.scores = scores;
+    c.coords = coords;
+    c.cigar_off = cigar_off;
+    std::vector<std::vector<uint32_t>> parts;
+    std::vector<int64_t> part_first;
+    std::mutex mu;
+    if (cigar) {
+        c.cigar_parts = &parts;
+        c.cigar_part_first = &part_first;
+        c.cigar_mu = &mu;
+    }
+    if (cigar_off) cigar_off[0] = 0;
+    rc = run_host_call(ctx, c);
+    if (rc) return rc;
+    if (cigar_off) {
+        for (int i = 0; i < n; ++i) cigar_off[i + 1] += cigar_off[i];  // per-pair counts -> offsets
+    }
+    if (cigar) {
+        const int64_t total = cigar_off[n];
+        uint32_t *out = (uint32_t *)alloc((size_t)std::max<int64_t>(total, 1) * sizeof(uint32_t), user);
+        if (!out) return set_error(VA_ERR_MEMORY, "the caller's allocator returned NULL");
+        for (size_t k = 0; k < parts.size(); ++k)
+            if (!parts[k].empty()) memcpy(out + cigar_off[part_first[k]], parts[k].data(), parts[k].size() * sizeof(uint32_t));
+        *cigar = out;
+    }
+    return VA_OK;
 }
 
 int va_cuda_max_resident_pairs(va_cuda_ctx *ctx, int align, int read_length, int ref_length, int64_t *max_n) {

@@ -133,6 +133,10 @@ __global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuf
                 // one matrix row of this strip; SW align returns the row's two direction planes per group
                 auto do_row = [&](int i, const uint2 tt, uint32_t left_in, uint2(&w)[NG]) {
                     const uint32_t ta = tt.x, tb = tt.y;
+                    // A solo thread shares its boundary words with another thread: the half that is not its own
+                    // holds whatever was there.  SW align's key (left * 32) is the one operation that crosses
+                    // lanes, so that half is replaced by a sane value before it enters the recurrence.
+                    if (SOLO && SWA) left_in = fw.lane ? ((left_in & 0xFFFF0000u) | (col0 & 0x0000FFFFu)) : ((left_in & 0x0000FFFFu) | (col0 & 0xFFFF0000u));
                     uint32_t left = first ? col0 : left_in;
                     uint32_t rowkey = 0;
                     uint32_t diag = diag_next;

@@ -48,6 +48,63 @@ struct ByteWindow {
     }
 };
 
+// Backwards byte STREAM over one raw sequence for the emit phase, which consumes each sequence strictly
+// from its end cell down to index 0: aligned 16-byte window loads, the window's words shifted down as
+// they are used up, one shift per byte -- no address arithmetic and no selects per byte.  Windows are
+// loaded lazily (only when a byte of them is needed), so nothing below the buffer is touched; the first
+// window is assembled byte-wise when it would reach past `limit` (end of the whole raw buffer).
+struct BackStream {
+    const uint4 *p;  // next (lower) window
+    uint4 w;
+    uint32_t cur;
+    int nbytes, nwords;
+    __device__ __forceinline__ void pop_word() {
+        cur = w.w;
+        w.w = w.z;
+        w.z = w.y;
+        w.y = w.x;
+        --nwords;
+    }
+    // the first byte returned is base[idx]; idx < 0 makes an empty stream (never read)
+    __device__ __forceinline__ void init(const uint8_t *base, int idx, const uint8_t *limit) {
+        nbytes = nwords = 0;
+        cur = 0;
+        w = make_uint4(0, 0, 0, 0);
+        p = nullptr;
+        if (idx < 0) return;
+        const uintptr_t a = reinterpret_cast<uintptr_t>(base + idx), a16 = a & ~(uintptr_t)15;
+        if (a16 + 16 <= reinterpret_cast<uintptr_t>(limit)) {
+            w = *reinterpret_cast<const uint4 *>(a16);
+        } else {  // last window of the buffer: only the bytes that exist
+            uint32_t t[4] = {0, 0, 0, 0};
+            for (uintptr_t q = a16; q <= a; ++q) t[(q - a16) >> 2] |= (uint32_t)*reinterpret_cast<const uint8_t *>(q) << (8 * ((q - a16) & 3));
+            w = make_uint4(t[0], t[1], t[2], t[3]);
+        }
+        p = reinterpret_cast<const uint4 *>(a16) - 1;
+        nwords = 4;
+        const int o = (int)(a & 15);
+        for (int d = 3; d > (o >> 2); --d) pop_word();  // words above the start are not part of the stream
+        pop_word();
+        cur <<= 8 * (3 - (o & 3));
+        nbytes = (o & 3) + 1;
+    }
+    __device__ __forceinline__ uint32_t next() {
+        if (nbytes == 0) {
+            if (nwords == 0) {
+                w = *p;
+                --p;
+                nwords = 4;
+            }
+            pop_word();
+            nbytes = 4;
+        }
+        const uint32_t b = cur >> 24;
+        cur <<= 8;
+        --nbytes;
+        return b;
+    }
+};
+
 // 2-bit move queue of one thread: word w lives at q[w * stride]
 struct MoveQueue {
     uint32_t *q;
@@ -61,15 +118,18 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
     extern __shared__ uint32_t sq[];
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= g.n) return;
+    const bool moves_only = b.moves_out != nullptr;
     MoveQueue mq;
-    if (gq) {
+    if (moves_only) {  // the queue itself is the result: pair-major, contiguous per pair
+        mq.q = b.moves_out + (size_t)b.pair_of[slot] * queue_words;
+        mq.stride = 1;
+    } else if (gq) {
         mq.q = gq + slot;
         mq.stride = (size_t)g.slots;
     } else {
         mq.q = sq + threadIdx.x;
         mq.stride = TB_THREADS;
     }
-    (void)queue_words;
     const int L = g.read_length + g.ref_length;
     const PairMeta meta = b.meta[slot];
     const int rows = meta.rows, cols = meta.cols;
@@ -200,9 +260,14 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
     }
     if (n_moves & 15) mq.q[(size_t)(n_moves >> 4) * mq.stride] = acc;
 
+    if (moves_only) {
+        b.start[pair] = (int16_t)(g.read_length + g.ref_length - 1 - n_moves);
+        return;
+    }
     // ---- emit ----------------------------------------------------------------------------
-    ByteWindow read(b.raw_reads + (size_t)pair * g.read_length, b.raw_reads + (size_t)g.n * g.read_length);
-    ByteWindow ref(b.raw_refs + (size_t)pair * g.ref_length, b.raw_refs + (size_t)g.n * g.ref_length);
+    BackStream read, ref;
+    read.init(b.raw_reads + (size_t)pair * g.read_length, end_i, b.raw_reads + (size_t)g.n * g.read_length);
+    ref.init(b.raw_refs + (size_t)pair * g.ref_length, end_j, b.raw_refs + (size_t)g.n * g.ref_length);
     uint8_t *oa = b.aln_read + (size_t)pair * L;
     uint8_t *ob = b.aln_ref + (size_t)pair * L;
     const int start = L - 1 - n_moves;  // may be negative only when every move was a gap (never with gap scores < 0)
@@ -211,21 +276,28 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
         oa[L - 1] = 0;
         ob[L - 1] = 0;
     }
-    i = end_i;
-    j = end_j;
     int pos = L - 2;
-    int t = 0;
-    uint32_t word = n_moves ? mq.q[0] : 0;
+    int t = 0;  // moves replayed so far
+    uint32_t mw = n_moves ? mq.q[0] : 0;
+    int mleft = 16;  // moves left in mw
+    size_t mnext = mq.stride;
     auto next_move = [&]() -> int {
-        const int code = (word >> (2 * (t & 15))) & 3;
-        if ((++t & 15) == 0 && t < n_moves) word = mq.q[(size_t)(t >> 4) * mq.stride];
+        if (mleft == 0) {
+            mw = mq.q[mnext];
+            mnext += mq.stride;
+            mleft = 16;
+        }
+        const int code = mw & 3;
+        mw >>= 2;
+        --mleft;
+        ++t;
         return code;
     };
     auto one_byte = [&]() {
         const int code = next_move();
         uint8_t a = '-', c = '-';
-        if (code != DIR_LEFT) a = (uint8_t)read.get(i--);
-        if (code != DIR_UP) c = (uint8_t)ref.get(j--);
+        if (code != DIR_LEFT) a = (uint8_t)read.next();
+        if (code != DIR_UP) c = (uint8_t)ref.next();
         if (pos >= 0) {
             oa[pos] = a;
             ob[pos] = c;
@@ -243,8 +315,8 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
         for (int r = 0; r < 4; ++r) {
             const int code = next_move();
             uint32_t a = '-', c = '-';
-            if (code != DIR_LEFT) a = read.get(i--);
-            if (code != DIR_UP) c = ref.get(j--);
+            if (code != DIR_LEFT) a = read.next();
+            if (code != DIR_UP) c = ref.next();
             wa |= a << (8 * (3 - r));
             wb |= c << (8 * (3 - r));
         }
@@ -284,7 +356,7 @@ int launch_traceback(const ChunkGeom &g, const ChunkBuffers &b, int mode, const 
     const int blocks = (g.n + TB_THREADS - 1) / TB_THREADS;
     const int qw = (int)traceback_queue_words(g.read_length, g.ref_length);
     const size_t smem = (size_t)qw * TB_THREADS * sizeof(uint32_t);
-    const bool use_shared = smem <= 48 * 1024;
+    const bool use_shared = smem <= 48 * 1024 && !b.moves_out;
     uint32_t *gq = use_shared ? nullptr : global_queue;
     if (mode == MODE_NW_ALIGN) traceback_kernel<true><<<blocks, TB_THREADS, use_shared ? smem : 0, stream>>>(g, b, sc, gq, qw);
     else traceback_kernel<false><<<blocks, TB_THREADS, use_shared ? smem : 0, stream>>>(g, b, sc, gq, qw);

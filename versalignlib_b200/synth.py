@@ -119,3 +119,42 @@ def edge_deck(read_len: int, ref_len: int):
     reads = np.stack([row(a, read_len) for a, _ in cases])
     refs = np.stack([row(b, ref_len) for _, b in cases])
     return np.ascontiguousarray(reads), np.ascontiguousarray(refs)
+
+
+def pack_batch(seqs: np.ndarray, lens: np.ndarray | None = None):
+    """(n, L) padded rows -> (flat uint8, int64 offsets[n+1]); lens defaults to the '\\0'-trimmed lengths."""
+    n, L = seqs.shape
+    if lens is None:
+        nz = seqs != 0
+        lens = np.where(nz.any(axis=1), L - np.argmax(nz[:, ::-1], axis=1), 0)
+    lens = np.asarray(lens, dtype=np.int64)
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    mask = np.arange(L)[None, :] < lens[:, None]
+    return np.ascontiguousarray(seqs[mask]), off
+
+
+def cigar_from_strings(aln_read: np.ndarray, aln_ref: np.ndarray, start: np.ndarray, end_cell: np.ndarray):
+    """What the packed entry points return, derived from the reference-style outputs (gapped strings,
+    right-aligned, used region [start, L-1)): coords[n,4], cigar_off[n+1], cigar (BAM encoding)."""
+    n, L = aln_read.shape
+    coords = np.zeros((n, 4), dtype=np.int32)
+    off = np.zeros(n + 1, dtype=np.int64)
+    runs = []
+    dash = ord("-")
+    for i in range(n):
+        s0 = max(int(start[i]), 0)
+        a, b = aln_read[i, s0:L - 1], aln_ref[i, s0:L - 1]
+        op = np.where(b == dash, 1, np.where(a == dash, 2, 0)).astype(np.int64)
+        used_read, used_ref = int((op != 2).sum()), int((op != 1).sum())
+        coords[i] = (end_cell[i, 0] + 1 - used_read, end_cell[i, 0] + 1, end_cell[i, 1] + 1 - used_ref, end_cell[i, 1] + 1)
+        if op.size:
+            cut = np.flatnonzero(np.diff(op)) + 1
+            starts = np.concatenate(([0], cut))
+            lens = np.diff(np.concatenate((starts, [op.size])))
+            runs.append(((lens << 4) | op[starts]).astype(np.uint32))
+            off[i + 1] = off[i] + starts.size
+        else:
+            off[i + 1] = off[i]
+    cigar = np.concatenate(runs) if runs else np.zeros(0, np.uint32)
+    return coords, off, cigar
