@@ -234,7 +234,7 @@ def test_long_pairs_intra_task_kernel(ctx):
 def test_packed_entry_points(ctx, opt):
     """Batch-friendly containers, same kernels: offset-addressed sequences in; scores, sequence coordinates
     and CIGARs out must be exactly what the reference-style outputs (oracle) say."""
-    for name, reads, refs in [BATCHES[3], BATCHES[1], BATCHES[6]]:  # mixed lengths, uniform with indels, tiny
+    for name, reads, refs in [BATCHES[3], BATCHES[1], BATCHES[6], BATCHES[2]]:  # mixed lengths, uniform with indels, tiny, random (raw-move fallback)
         pr, ro = synth.pack_batch(reads)
         pf, fo = synth.pack_batch(refs)
         # the semantics are the reference's on the batch padded to ITS maximum lengths

@@ -224,19 +224,28 @@ class CudaContext:
         return out
 
     def align_packed(self, opt: int, policy: int, reads: np.ndarray, read_off: np.ndarray, refs: np.ndarray,
-                     ref_off: np.ndarray, scoring=(2, -1, -3, -3)):
-        """Returns (scores[n], coords[n,4] = read_begin, read_end, ref_begin, ref_end, cigar_off[n+1], cigar uint32[])."""
+                     ref_off: np.ndarray, scoring=(2, -1, -3, -3), out: dict | None = None):
+        """Returns (scores[n], coords[n,4] = read_begin, read_end, ref_begin, ref_end, cigar_off[n+1], cigar uint32[]).
+        `out`: a dict the call keeps its output arrays in, so a caller that repeats calls of the same size
+        reuses them (keys scores, coords, cigar_off, cigar)."""
         reads, refs = np.ascontiguousarray(reads, np.uint8), np.ascontiguousarray(refs, np.uint8)
         read_off, ref_off = np.ascontiguousarray(read_off, np.int64), np.ascontiguousarray(ref_off, np.int64)
         n = read_off.shape[0] - 1
-        scores = np.zeros(n, dtype=np.int16)
-        coords = np.zeros((n, 4), dtype=np.int32)
-        cigar_off = np.zeros(n + 1, dtype=np.int64)
-        blocks = []
+        out = {} if out is None else out
+
+        def _arr(key, shape, dtype):
+            a = out.get(key)
+            if a is None or a.shape != shape:
+                a = out[key] = np.zeros(shape, dtype=dtype)
+            return a
+
+        scores, coords, cigar_off = _arr("scores", (n,), np.int16), _arr("coords", (n, 4), np.int32), _arr("cigar_off", (n + 1,), np.int64)
 
         def _alloc(nbytes, _user):
-            buf = np.empty(max(int(nbytes) // 4, 1), dtype=np.uint32)
-            blocks.append(buf)
+            words = max(int(nbytes) // 4, 1)
+            buf = out.get("cigar")
+            if buf is None or buf.shape[0] < words:
+                buf = out["cigar"] = np.empty(words + words // 8, dtype=np.uint32)
             return buf.ctypes.data
 
         cb = _ALLOC_FN(_alloc)
@@ -246,7 +255,7 @@ class CudaContext:
                                                  read_off.ctypes.data, refs.ctypes.data, ref_off.ctypes.data,
                                                  scores.ctypes.data, coords.ctypes.data, cigar_off.ctypes.data, cb, None,
                                                  ctypes.byref(out_ptr)), "va_cuda_align_packed")
-        cigar = blocks[0][: int(cigar_off[n])] if blocks else np.zeros(0, np.uint32)
+        cigar = out["cigar"][: int(cigar_off[n])] if "cigar" in out else np.zeros(0, np.uint32)
         return scores, coords, cigar_off, cigar
 
     # ---- device-resident (torch tensors supply the memory and the stream) --------------

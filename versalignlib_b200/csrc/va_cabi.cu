@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -305,7 +306,7 @@ struct Shape {
     }
     size_t per_pair_io() const {
         size_t b = (size_t)read_length + ref_length + 2 + 4;
-        if (align) b += (moves ? queue_words() * 4 : 2 * (size_t)L) + 2;
+        if (align) b += (moves ? (queue_words() + 1) * 4 : 2 * (size_t)L) + 2;
         return b;
     }
 };
@@ -377,7 +378,7 @@ int reserve_slot(ChunkSlot &s, const Shape &sh, int cap_pairs, bool pinned) {
         if (qw * 128 * 4 > 48 * 1024 && (rc = s.queue.reserve(slots * qw * 4 + 64))) return rc;
         if (pinned) {
             if (sh.moves) {
-                if ((rc = s.moves.reserve((size_t)cap_pairs * sh.queue_words() * 4 + 16))) return rc;
+                if ((rc = s.moves.reserve((size_t)cap_pairs * (sh.queue_words() + 1) * 4 + 16))) return rc;
             } else {
                 if ((rc = s.aln_read.reserve((size_t)cap_pairs * sh.L + 16))) return rc;
                 if ((rc = s.aln_ref.reserve((size_t)cap_pairs * sh.L + 16))) return rc;
@@ -393,7 +394,7 @@ int reserve_slot(ChunkSlot &s, const Shape &sh, int cap_pairs, bool pinned) {
         if ((rc = s.h_end_cell.reserve(slots * 4))) return rc;
         if (sh.align) {
             if (sh.moves) {
-                if ((rc = s.h_moves.reserve((size_t)cap_pairs * sh.queue_words() * 4 + 16))) return rc;
+                if ((rc = s.h_moves.reserve((size_t)cap_pairs * (sh.queue_words() + 1) * 4 + 16))) return rc;
             } else {
                 if ((rc = s.h_aln_read.reserve((size_t)cap_pairs * sh.L + 16))) return rc;
                 if ((rc = s.h_aln_ref.reserve((size_t)cap_pairs * sh.L + 16))) return rc;
@@ -493,6 +494,13 @@ int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int
     return launches;
 }
 
+// CIGAR runs of one chunk of a packed align call
+struct CigarPart {
+    int64_t first = 0;
+    size_t words = 0;
+    std::unique_ptr<uint32_t[]> data;
+};
+
 // What the host-buffer entry points have in common.
 struct HostCall {
     int mode = 0, policy = 0;
@@ -524,8 +532,7 @@ struct HostCall {
     const int64_t *ref_off = nullptr;
     int32_t *coords = nullptr;                        // [n][4]: read_begin, read_end, ref_begin, ref_end (0-based, half open)
     int64_t *cigar_off = nullptr;                     // [n+1]; filled with per-pair op counts first, prefix-summed at the end
-    std::vector<std::vector<uint32_t>> *cigar_parts = nullptr;  // one vector per chunk, indexed by global chunk number
-    std::vector<int64_t> *cigar_part_first = nullptr;           // first pair of each part
+    std::vector<CigarPart> *cigar_parts = nullptr;  // one per chunk, any order
     std::mutex *cigar_mu = nullptr;
 };
 
@@ -544,6 +551,13 @@ void gather_chunk(va_cuda_ctx *ctx, const HostCall &c, ChunkSlot &s, int64_t fir
     if (c.read_off) {
         // offset-addressed sequences -> the kernels' fixed-stride, '\0'-padded staging layout
         ctx->pool->parallel_for(count, 2048, [&](int64_t b, int64_t e) {
+            // no sequence is longer than RL / FL, so a block whose bytes add up to (e-b)*RL holds full-length
+            // sequences only and already IS the staging layout
+            const bool full_r = c.read_off[first + e] - c.read_off[first + b] == (e - b) * (int64_t)RL;
+            const bool full_f = c.ref_off[first + e] - c.ref_off[first + b] == (e - b) * (int64_t)FL;
+            if (full_r) memcpy(hr + b * RL, c.reads_f + c.read_off[first + b], (size_t)(e - b) * RL);
+            if (full_f) memcpy(hf + b * FL, c.refs_f + c.ref_off[first + b], (size_t)(e - b) * FL);
+            if (full_r && full_f) return;
             for (int64_t i = b; i < e; ++i) {
                 const int64_t r0 = c.read_off[first + i], r1 = c.read_off[first + i + 1];
                 const int64_t f0 = c.ref_off[first + i], f1 = c.ref_off[first + i + 1];
@@ -575,13 +589,12 @@ void gather_chunk(va_cuda_ctx *ctx, const HostCall &c, ChunkSlot &s, int64_t fir
     }
 }
 
-// Packed entry points: a pair's result arrives as its 2-bit move queue (last alignment column first).
-// Replayed backwards it becomes a CIGAR (BAM encoding: length << 4 | op; M = 0 read and ref base,
+// Packed entry points: a pair's result arrives as its moves in walk order (last alignment column first),
+// normally already run-length encoded by the traceback kernel, else as the raw 2-bit queue
+// (va_traceback.cu).  Reversed it is the CIGAR (BAM encoding: length << 4 | op; M = 0 read and ref base,
 // I = 1 read base against a gap, D = 2 ref base against a gap) and the aligned coordinate ranges.
 void scatter_moves(va_cuda_ctx *ctx, const HostCall &c, ChunkSlot &s, int64_t first, int count) {
-    const int L = c.sh.L;
-    const size_t qw = c.sh.queue_words();
-    const int16_t *st = (const int16_t *)s.h_start.p;
+    const size_t qw = c.sh.queue_words() + 1;
     const int16_t *ec = (const int16_t *)s.h_end_cell.p;
     const int16_t *sc = (const int16_t *)s.h_scores.p;
     const uint32_t *mv = (const uint32_t *)s.h_moves.p;
@@ -589,8 +602,14 @@ void scatter_moves(va_cuda_ctx *ctx, const HostCall &c, ChunkSlot &s, int64_t fi
     if (c.end_cell) memcpy(c.end_cell + 2 * first, ec, (size_t)count * 2 * sizeof(int16_t));
     // forward replay of pair i: fn(op, run length) per CIGAR run; returns the number of runs
     auto replay = [&](int64_t i, auto &&fn) -> int {
-        const int n_moves = std::max(0, L - 1 - (int)st[i]);
         const uint32_t *q = mv + (size_t)i * qw;
+        const uint32_t head = q[0];
+        ++q;
+        if (!(head & 0x80000000u)) {  // runs, last first
+            for (int r = (int)head - 1; r >= 0; --r) fn((int)(q[r] & 15u), (int)(q[r] >> 4));
+            return (int)head;
+        }
+        const int n_moves = (int)(head & 0x7FFFFFFFu);
         int runs = 0, cur = -1, len = 0;
         for (int t = n_moves - 1; t >= 0; --t) {
             const int code = (q[t >> 4] >> (2 * (t & 15))) & 3;
@@ -606,15 +625,34 @@ void scatter_moves(va_cuda_ctx *ctx, const HostCall &c, ChunkSlot &s, int64_t fi
         if (len) { fn(cur, len); ++runs; }
         return runs;
     };
-    std::vector<int64_t> offs((size_t)count + 1, 0);
-    ctx->pool->parallel_for(count, 2048, [&](int64_t b, int64_t e) {
+    // pass 1: runs per pair (the header says it unless the pair came back as raw moves)
+    std::unique_ptr<int64_t[]> offs(new int64_t[(size_t)count + 1]);
+    offs[0] = 0;
+    ctx->pool->parallel_for(count, 8192, [&](int64_t b, int64_t e) {
+        for (int64_t i = b; i < e; ++i) {
+            const uint32_t head = mv[(size_t)i * qw];
+            const int runs = (head & 0x80000000u) ? replay(i, [](int, int) {}) : (int)head;
+            offs[(size_t)i + 1] = runs;
+            if (c.cigar_off) c.cigar_off[first + i + 1] = runs;
+        }
+    });
+    for (int64_t i = 0; i < count; ++i) offs[(size_t)i + 1] += offs[(size_t)i];
+    // pass 2: coordinates and the runs themselves
+    std::unique_ptr<uint32_t[]> part;
+    uint32_t *pout = nullptr;
+    if (c.cigar_parts) {
+        part.reset(new uint32_t[(size_t)offs[(size_t)count] + 1]);  // not zero filled: every word is written below
+        pout = part.get();
+    }
+    ctx->pool->parallel_for(count, 4096, [&](int64_t b, int64_t e) {
         for (int64_t i = b; i < e; ++i) {
             int used_read = 0, used_ref = 0;
-            const int runs = replay(i, [&](int op, int len) {
+            uint32_t *out = pout ? pout + offs[(size_t)i] : nullptr;
+            replay(i, [&](int op, int len) {
                 if (op != 2) used_read += len;
                 if (op != 1) used_ref += len;
+                if (out) *out++ = ((uint32_t)len << 4) | (uint32_t)op;
             });
-            offs[(size_t)i + 1] = runs;
             if (c.coords) {
                 int32_t *co = c.coords + 4 * (first + i);
                 co[1] = (int32_t)ec[2 * i] + 1;
@@ -622,21 +660,15 @@ void scatter_moves(va_cuda_ctx *ctx, const HostCall &c, ChunkSlot &s, int64_t fi
                 co[3] = (int32_t)ec[2 * i + 1] + 1;
                 co[2] = co[3] - used_ref;
             }
-            if (c.cigar_off) c.cigar_off[first + i + 1] = runs;
         }
     });
     if (!c.cigar_parts) return;
-    for (int64_t i = 0; i < count; ++i) offs[(size_t)i + 1] += offs[(size_t)i];
-    std::vector<uint32_t> part((size_t)offs[(size_t)count]);
-    ctx->pool->parallel_for(count, 2048, [&](int64_t b, int64_t e) {
-        for (int64_t i = b; i < e; ++i) {
-            uint32_t *out = part.data() + offs[(size_t)i];
-            replay(i, [&](int op, int len) { *out++ = ((uint32_t)len << 4) | (uint32_t)op; });
-        }
-    });
     std::lock_guard<std::mutex> lk(*c.cigar_mu);
-    c.cigar_parts->push_back(std::move(part));
-    c.cigar_part_first->push_back(first);
+    c.cigar_parts->emplace_back();
+    CigarPart &cp = c.cigar_parts->back();
+    cp.first = first;
+    cp.words = (size_t)offs[(size_t)count];
+    cp.data = std::move(part);
 }
 
 void scatter_chunk(va_cuda_ctx *ctx, const HostCall &c, ChunkSlot &s, int64_t first, int count) {
@@ -774,7 +806,7 @@ void run_shard(va_cuda_ctx *ctx, Engine &e, const HostCall &c, int64_t lo, int64
             cudaMemcpyAsync(s.h_scores.p, s.scores.p, (size_t)count * 2, cudaMemcpyDeviceToHost, s.stream);
             st.d2h += (int64_t)count * 2;
         } else if (c.sh.moves) {
-            const size_t qb = c.sh.queue_words() * 4;
+            const size_t qb = (c.sh.queue_words() + 1) * 4;
             cudaMemcpyAsync(s.h_moves.p, s.moves.p, (size_t)count * qb, cudaMemcpyDeviceToHost, s.stream);
             cudaMemcpyAsync(s.h_start.p, s.start.p, (size_t)count * 2, cudaMemcpyDeviceToHost, s.stream);
             cudaMemcpyAsync(s.h_end_cell.p, s.end_cell.p, (size_t)count * 4, cudaMemcpyDeviceToHost, s.stream);
@@ -1128,12 +1160,10 @@ int va_cuda_align_packed(va_cuda_ctx *ctx, int opt, int policy, const va_cuda_sc
     c.scores = scores;
     c.coords = coords;
     c.cigar_off = cigar_off;
-    std::vector<std::vector<uint32_t>> parts;
-    std::vector<int64_t> part_first;
+    std::vector<CigarPart> parts;
     std::mutex mu;
     if (cigar) {
         c.cigar_parts = &parts;
-        c.cigar_part_first = &part_first;
         c.cigar_mu = &mu;
     }
     if (cigar_off) cigar_off[0] = 0;
@@ -1146,8 +1176,10 @@ int va_cuda_align_packed(va_cuda_ctx *ctx, int opt, int policy, const va_cuda_sc
         const int64_t total = cigar_off[n];
         uint32_t *out = (uint32_t *)alloc((size_t)std::max<int64_t>(total, 1) * sizeof(uint32_t), user);
         if (!out) return set_error(VA_ERR_MEMORY, "the caller's allocator returned NULL");
-        for (size_t k = 0; k < parts.size(); ++k)
-            if (!parts[k].empty()) memcpy(out + cigar_off[part_first[k]], parts[k].data(), parts[k].size() * sizeof(uint32_t));
+        ctx->pool->parallel_for((int64_t)parts.size(), 1, [&](int64_t b, int64_t e) {
+            for (int64_t k = b; k < e; ++k)
+                if (parts[k].words) memcpy(out + cigar_off[parts[k].first], parts[k].data.get(), parts[k].words * sizeof(uint32_t));
+        });
         *cigar = out;
     }
     return VA_OK;

@@ -86,9 +86,9 @@ struct ChunkBuffers {
     uint8_t *aln_read;         // [n][read_length+ref_length]
     uint8_t *aln_ref;
     int16_t *start;            // [n]
-    uint32_t *moves_out;       // when set: the traceback stops after the walk and leaves pair i's 2-bit move queue
-                               // (last alignment column first, 16 moves per word) at moves_out[i * queue_words ..);
-                               // start[i] = L - 1 - moves as usual, aln_read / aln_ref are not written
+    uint32_t *moves_out;       // when set: the traceback stops after the walk and leaves pair i's moves at
+                               // moves_out[i * (queue_words + 1) ..): CIGAR runs in walk order or the raw 2-bit queue
+                               // (va_traceback.cu); start[i] = L - 1 - moves as usual, aln_read / aln_ref are not written
     unsigned long long *cell_count;  // device counter: DP cells computed
 };
 

@@ -120,8 +120,8 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
     if (slot >= g.n) return;
     const bool moves_only = b.moves_out != nullptr;
     MoveQueue mq;
-    if (moves_only) {  // the queue itself is the result: pair-major, contiguous per pair
-        mq.q = b.moves_out + (size_t)b.pair_of[slot] * queue_words;
+    if (moves_only) {  // set below: the result region of the pair
+        mq.q = nullptr;
         mq.stride = 1;
     } else if (gq) {
         mq.q = gq + slot;
@@ -175,90 +175,134 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
     const int end_i = i, end_j = j;
 
     // ---- walk ----------------------------------------------------------------------------
-    int n_moves = 0;
-    uint32_t acc = 0;
-    if (packed) {
-        const int tw = g.fast_tw, ng = fast_groups(tw);
-        int strip = j >= 0 ? j / tw : 0, k = j >= 0 ? j - strip * tw : 0;
-        // NW: a partial last strip keeps its true columns in the LAST registers of the strip (va_nw.cu)
-        int kmin = 0;
-        if (NW && cols > 0 && strip == (cols - 1) / tw) {
-            kmin = tw - (cols - strip * tw);
-            k += kmin;
-        }
-        const size_t pair_step = (size_t)ng * g.duos, strip_step = (size_t)fast_row_pairs(g) * pair_step;
-        const uint4 *p = b.fdirs + (size_t)strip * strip_step + (size_t)(max(i, 0) >> 1) * pair_step + duo;
-        int have_pair = -1, have_strip = -1, have_grp = -1;
-        uint4 w = make_uint4(0, 0, 0, 0);
-        // SW: the packed fill stores the pointer a cell would have in NW; a cell whose value is 0 is
-        // START (DefaultKernel.cpp:240-241).  The value is known along the path: it starts at the best
-        // score and every move gives back what it added.
-        int hval = NW ? 1 : (int)b.scores[pair];
-        ByteWindow wread(b.raw_reads + (size_t)pair * g.read_length, b.raw_reads + (size_t)g.n * g.read_length);
-        ByteWindow wref(b.raw_refs + (size_t)pair * g.ref_length, b.raw_refs + (size_t)g.n * g.ref_length);
-        while (true) {
-            int code;
-            if (i < 0 || i >= rows || j >= cols) code = DIR_START;
-            else if (j < 0) code = NW ? DIR_UP : DIR_START;  // matrix column 0 (DefaultKernel.cpp:304)
-            else if (!NW && hval <= 0) code = DIR_START;
-            else {
-                const int grp = k >> 4;
-                if ((i >> 1) != have_pair || strip != have_strip || grp != have_grp) {
-                    w = p[(size_t)grp * g.duos];  // two rows x 16 columns x both lanes
-                    have_pair = i >> 1;
-                    have_strip = strip;
-                    have_grp = grp;
-                }
-                const int bit = lane_shift + (k & 15);
-                const uint32_t diag_plane = (i & 1) ? w.z : w.x, up_plane = (i & 1) ? w.w : w.y;
-                code = ((diag_plane >> bit) & 1) ? DIR_DIAG : (((up_plane >> bit) & 1) ? DIR_UP : DIR_LEFT);
+    // One walk from the end cell to START; every move goes to `sink(code, t)` (t = moves so far).
+    auto walk = [&](auto &&sink) -> int {
+        int i = end_i, j = end_j;
+        int n_moves = 0;
+        if (packed) {
+            const int tw = g.fast_tw, ng = fast_groups(tw);
+            int strip = j >= 0 ? j / tw : 0, k = j >= 0 ? j - strip * tw : 0;
+            // NW: a partial last strip keeps its true columns in the LAST registers of the strip (va_nw.cu)
+            int kmin = 0;
+            if (NW && cols > 0 && strip == (cols - 1) / tw) {
+                kmin = tw - (cols - strip * tw);
+                k += kmin;
             }
-            if (code == DIR_START) break;
-            acc |= (uint32_t)code << (2 * (n_moves & 15));
-            if ((++n_moves & 15) == 0) {
-                mq.q[(size_t)((n_moves >> 4) - 1) * mq.stride] = acc;
-                acc = 0;
-            }
-            if (!NW) {
-                if (code == DIR_UP) hval -= sc.gap_ref;
-                else if (code == DIR_LEFT) hval -= sc.gap_read;
+            const size_t pair_step = (size_t)ng * g.duos, strip_step = (size_t)fast_row_pairs(g) * pair_step;
+            const uint4 *p = b.fdirs + (size_t)strip * strip_step + (size_t)(max(i, 0) >> 1) * pair_step + duo;
+            int have_pair = -1, have_strip = -1, have_grp = -1;
+            uint4 w = make_uint4(0, 0, 0, 0);
+            // SW: the packed fill stores the pointer a cell would have in NW; a cell whose value is 0 is
+            // START (DefaultKernel.cpp:240-241).  The value is known along the path: it starts at the best
+            // score and every move gives back what it added.
+            int hval = NW ? 1 : (int)b.scores[pair];
+            ByteWindow wread(b.raw_reads + (size_t)pair * g.read_length, b.raw_reads + (size_t)g.n * g.read_length);
+            ByteWindow wref(b.raw_refs + (size_t)pair * g.ref_length, b.raw_refs + (size_t)g.n * g.ref_length);
+            while (true) {
+                int code;
+                if (i < 0 || i >= rows || j >= cols) code = DIR_START;
+                else if (j < 0) code = NW ? DIR_UP : DIR_START;  // matrix column 0 (DefaultKernel.cpp:304)
+                else if (!NW && hval <= 0) code = DIR_START;
                 else {
-                    const unsigned ca = wread.get(i) & 0xDFu, cb = wref.get(j) & 0xDFu;
-                    const bool va = ca == 'A' || ca == 'C' || ca == 'G' || ca == 'T', vb = cb == 'A' || cb == 'C' || cb == 'G' || cb == 'T';
-                    hval -= (va && vb) ? (ca == cb ? sc.match : sc.mismatch) : 0;
+                    const int grp = k >> 4;
+                    if ((i >> 1) != have_pair || strip != have_strip || grp != have_grp) {
+                        w = p[(size_t)grp * g.duos];  // two rows x 16 columns x both lanes
+                        have_pair = i >> 1;
+                        have_strip = strip;
+                        have_grp = grp;
+                    }
+                    const int bit = lane_shift + (k & 15);
+                    const uint32_t diag_plane = (i & 1) ? w.z : w.x, up_plane = (i & 1) ? w.w : w.y;
+                    code = ((diag_plane >> bit) & 1) ? DIR_DIAG : (((up_plane >> bit) & 1) ? DIR_UP : DIR_LEFT);
+                }
+                if (code == DIR_START) break;
+                sink(code, n_moves);
+                ++n_moves;
+                if (!NW) {
+                    if (code == DIR_UP) hval -= sc.gap_ref;
+                    else if (code == DIR_LEFT) hval -= sc.gap_read;
+                    else {
+                        const unsigned ca = wread.get(i) & 0xDFu, cb = wref.get(j) & 0xDFu;
+                        const bool va = ca == 'A' || ca == 'C' || ca == 'G' || ca == 'T', vb = cb == 'A' || cb == 'C' || cb == 'G' || cb == 'T';
+                        hval -= (va && vb) ? (ca == cb ? sc.match : sc.mismatch) : 0;
+                    }
+                }
+                if (code != DIR_LEFT) {
+                    if ((i & 1) == 0) p -= pair_step;  // leaving an even row: the row above is in the previous word
+                    --i;
+                }
+                if (code != DIR_UP) {
+                    --j;
+                    if (--k < kmin) {
+                        k = tw - 1;
+                        kmin = 0;
+                        --strip;
+                        p -= strip_step;
+                    }
                 }
             }
-            if (code != DIR_LEFT) {
-                if ((i & 1) == 0) p -= pair_step;  // leaving an even row: the row above is in the previous word
-                --i;
+        } else {
+            while (true) {
+                int code;
+                if (i < 0 || i >= rows || j >= cols) code = DIR_START;
+                else if (j < 0) code = NW ? DIR_UP : DIR_START;
+                else code = (b.dirs[((size_t)(j >> 3) * g.rows_alloc + i) * g.slots + slot] >> (2 * (j & 7))) & 3;
+                if (code == DIR_START) break;
+                sink(code, n_moves);
+                ++n_moves;
+                if (code != DIR_LEFT) --i;
+                if (code != DIR_UP) --j;
             }
-            if (code != DIR_UP) {
-                --j;
-                if (--k < kmin) {
-                    k = tw - 1;
-                    kmin = 0;
-                    --strip;
-                    p -= strip_step;
+        }
+        return n_moves;
+    };
+    // 2-bit queue sink: 16 moves per word
+    uint32_t acc = 0;
+    auto queue_sink = [&](int code, int t) {
+        acc |= (uint32_t)code << (2 * (t & 15));
+        if ((t & 15) == 15) {
+            mq.q[(size_t)(t >> 4) * mq.stride] = acc;
+            acc = 0;
+        }
+    };
+    int n_moves;
+    if (moves_only) {
+        // The moves ARE the result (packed entry points).  They leave as CIGAR runs in walk order (length << 4 |
+        // op, last run of the alignment first) when a pair has at most queue_words of them -- word 0 = run count
+        // -- else as the raw 2-bit queue from a second walk, word 0 = 0x80000000 | moves.
+        uint32_t *out = b.moves_out + (size_t)pair * (queue_words + 1);
+        int cur = -1, len = 0, nruns = 0;
+        auto rle_sink = [&](int code, int) {
+            const int op = code == DIR_DIAG ? 0 : code == DIR_UP ? 1 : 2;
+            if (op == cur) {
+                ++len;
+            } else {
+                if (len) {
+                    if (nruns < queue_words) out[1 + nruns] = ((uint32_t)len << 4) | (uint32_t)cur;
+                    ++nruns;
                 }
+                cur = op;
+                len = 1;
             }
+        };
+        n_moves = walk(rle_sink);
+        if (len) {
+            if (nruns < queue_words) out[1 + nruns] = ((uint32_t)len << 4) | (uint32_t)cur;
+            ++nruns;
+        }
+        if (nruns <= queue_words) {
+            out[0] = (uint32_t)nruns;
+        } else {
+            mq.q = out + 1;
+            mq.stride = 1;
+            n_moves = walk(queue_sink);
+            if (n_moves & 15) mq.q[(size_t)(n_moves >> 4)] = acc;
+            out[0] = 0x80000000u | (uint32_t)n_moves;
         }
     } else {
-        while (true) {
-            int code;
-            if (i < 0 || i >= rows || j >= cols) code = DIR_START;
-            else if (j < 0) code = NW ? DIR_UP : DIR_START;
-            else code = (b.dirs[((size_t)(j >> 3) * g.rows_alloc + i) * g.slots + slot] >> (2 * (j & 7))) & 3;
-            if (code == DIR_START) break;
-            acc |= (uint32_t)code << (2 * (n_moves & 15));
-            if ((++n_moves & 15) == 0) {
-                mq.q[(size_t)((n_moves >> 4) - 1) * mq.stride] = acc;
-                acc = 0;
-            }
-            if (code != DIR_LEFT) --i;
-            if (code != DIR_UP) --j;
-        }
+        n_moves = walk(queue_sink);
+        if (n_moves & 15) mq.q[(size_t)(n_moves >> 4) * mq.stride] = acc;
     }
-    if (n_moves & 15) mq.q[(size_t)(n_moves >> 4) * mq.stride] = acc;
 
     if (moves_only) {
         b.start[pair] = (int16_t)(g.read_length + g.ref_length - 1 - n_moves);
