@@ -47,21 +47,40 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// Threads per block and register cap per instantiation (4 x 128 threads per SM leave 128 registers each,
+// 5 x 96 leave 136): see va_nw.cu -- the pairs whose row loops ptxas compiles without parking predicates
+// (tools/check_sass.py).
+#ifndef VA_FAST_FORCE_NT
+template <int MODE, int TW, bool SYM, bool SOLO>
+struct FastBlock {  // 4 x 128 threads, 128 registers -- except SW align's solo instantiation and asymmetric gaps
+    static constexpr bool WIDE = MODE == MODE_SW_ALIGN && (SOLO || !SYM);
+    static constexpr int NT = WIDE ? 96 : 128;
+    static constexpr int MAXREG = WIDE ? 136 : 128;
+};
+#else
+template <int MODE, int TW, bool SYM, bool SOLO>
+struct FastBlock {
+    static constexpr int NT = VA_FAST_FORCE_NT;
+    static constexpr int MAXREG = VA_FAST_FORCE_NT == 96 ? 136 : 128;
+};
+#endif
+
 // The Smith-Waterman kernels (the NW modes run on a shifted recurrence, va_nw.cu).
 // SYM: gap_read == gap_ref, so "H + gR" (what the cell to the right needs) and "H + gF" (what the
 // cell below needs) are the same register: one add less per cell in SW align.
 // SOLO: the instantiation for single slots whose duo is not fast (va_fast.cuh): same sweep, the owner's
 // halves of the shared words stored with 16-bit stores.
 template <int MODE, int TW, bool SYM, bool SOLO>
-__global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuffers b, FastConsts fc) {
+__global__ void __maxnreg__((FastBlock<MODE, TW, SYM, SOLO>::MAXREG)) fill_fast_kernel(ChunkGeom g, ChunkBuffers b, FastConsts fc) {
     constexpr bool SWA = MODE == MODE_SW_ALIGN;
     constexpr int NG = (TW + 15) / 16;
     static_assert(MODE == MODE_SW_ALIGN || MODE == MODE_SW_SCORE, "SW modes only");
 
     __shared__ uint2 s_T2[256];              // [6*code_a + code_b] -> the two lanes' 4-entry score tables (36 used)
-    __shared__ uint4 s_idx[3][128];           // staged row indices: 16 rows per thread and buffer
-    __shared__ uint32_t s_bnd[3][16][128];    // staged right edge of the previous strip, [row][thread]
-    for (int t = threadIdx.x; t < 256; t += 128) s_T2[t] = t < 36 ? make_uint2(fc.tab[t / 6], fc.tab[t % 6]) : make_uint2(0u, 0u);
+    constexpr int NT = FastBlock<MODE, TW, SYM, SOLO>::NT;
+    __shared__ uint4 s_idx[3][NT];           // staged row indices: 16 rows per thread and buffer
+    __shared__ uint32_t s_bnd[3][16][NT];    // staged right edge of the previous strip, [row][thread]
+    for (int t = threadIdx.x; t < 256; t += NT) s_T2[t] = t < 36 ? make_uint2(fc.tab[t / 6], fc.tab[t % 6]) : make_uint2(0u, 0u);
     __syncthreads();
 
     unsigned long long cells = 0;
@@ -213,7 +232,7 @@ __global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuf
                 const uint8_t *ib = reinterpret_cast<const uint8_t *>(&s_idx[0][threadIdx.x]);
                 const uint32_t *lb = &s_bnd[0][0][threadIdx.x];
                 uint2 nt0 = s_T2[ib[0]], nt1 = s_T2[ib[1]];
-                uint32_t nl0 = lb[0], nl1 = lb[128];
+                uint32_t nl0 = lb[0], nl1 = lb[NT];
                 int buf = 0;
                 for (int c = 0; c < nchunks; ++c) {
                     const int buf1 = buf == 2 ? 0 : buf + 1, buf2 = buf1 == 2 ? 0 : buf1 + 1;
@@ -236,9 +255,9 @@ __global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuf
                             nt0 = s_T2[pi[0]];
                             nt1 = s_T2[pi[1]];
                             nl0 = pl[0];
-                            nl1 = pl[128];
+                            nl1 = pl[NT];
                             ip += 2;
-                            lp += 256;
+                            lp += 2 * NT;
                         }
                         // each row's planes leave as soon as the row is done (8-byte halves of the row pair's
                         // 16-byte word; L2 merges them), so no plane register lives across the other row
@@ -313,20 +332,26 @@ __global__ void __launch_bounds__(128, 4) fill_fast_kernel(ChunkGeom g, ChunkBuf
     if ((threadIdx.x & 31) == 0 && cells) atomicAdd(b.cell_count, cells);
 }
 
-template <int MODE, int TW>
-void launch_one(const ChunkGeom &g, const ChunkBuffers &b, const FastConsts &fc, cudaStream_t stream) {
-    const int threads = 128;
+template <int MODE, int TW, bool SYM, bool SOLO>
+void launch_inst(const ChunkGeom &g, const ChunkBuffers &b, const FastConsts &fc, cudaStream_t stream) {
+    const int threads = FastBlock<MODE, TW, SYM, SOLO>::NT;
     const int duos = (g.n + 1) / 2;
     const int blocks = (duos + threads - 1) / threads;
+    // duo grid: one thread per duo.  solo grid: a fixed grid strides over the list the prep kernel compiled
+    // (va_fast.cuh); empty on a uniform batch, where the blocks read the count and leave.
+    fill_fast_kernel<MODE, TW, SYM, SOLO><<<SOLO ? std::min(2 * blocks, 148 * 4) : blocks, threads, 0, stream>>>(g, b, fc);
+}
+
+template <int MODE, int TW>
+void launch_one(const ChunkGeom &g, const ChunkBuffers &b, const FastConsts &fc, cudaStream_t stream) {
     // SW align with equal gap scores keeps one register per column less
     if (MODE == MODE_SW_ALIGN && fc.gF == fc.gR) {
-        if (g.n >= 2) fill_fast_kernel<MODE, TW, MODE == MODE_SW_ALIGN, false><<<blocks, threads, 0, stream>>>(g, b, fc);
-        if (g.solo) fill_fast_kernel<MODE, TW, MODE == MODE_SW_ALIGN, true><<<std::min(2 * blocks, 148 * 4), threads, 0, stream>>>(g, b, fc);
+        if (g.n >= 2) launch_inst<MODE, TW, MODE == MODE_SW_ALIGN, false>(g, b, fc, stream);
+        if (g.solo) launch_inst<MODE, TW, MODE == MODE_SW_ALIGN, true>(g, b, fc, stream);
         return;
     }
-    if (g.n >= 2) fill_fast_kernel<MODE, TW, false, false><<<blocks, threads, 0, stream>>>(g, b, fc);
-    // leftovers of the bucketing: a fixed grid strides over the list the prep kernel compiled (va_fast.cuh)
-    if (g.solo) fill_fast_kernel<MODE, TW, false, true><<<std::min(2 * blocks, 148 * 4), threads, 0, stream>>>(g, b, fc);
+    if (g.n >= 2) launch_inst<MODE, TW, false, false>(g, b, fc, stream);
+    if (g.solo) launch_inst<MODE, TW, false, true>(g, b, fc, stream);
 }
 
 template <int MODE>

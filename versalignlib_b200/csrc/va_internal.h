@@ -77,7 +77,6 @@ struct ChunkBuffers {
     uint16_t *dirs;            // general kernel: [segs][rows_alloc][slots] half-words, 2 bits per cell, 8 cells each
     uint4 *fdirs;              // packed kernel:  [strip][row pair][group][duos], see va_fast.cuh
                                // (separate regions: one chunk can hold pairs of both kinds)
-    uint32_t *hrow;            // packed NW align: [ref_length][duos] last valid matrix row (H + gap_ref)
     int32_t *solo_list;        // [slots] slots the packed kernels take on their own (va_fast.cuh), written by the prep
     int32_t *solo_count;       // kernel in no particular order; *solo_count entries
     int16_t *scores;           // [n]

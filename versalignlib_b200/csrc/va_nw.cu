@@ -16,7 +16,7 @@
 // With both gap scores <= 0 (required here; otherwise the general kernel runs) V is non-negative and
 // non-decreasing along rows and columns, which bounds the 16-bit range check.
 // The matrix borders un-shift what they hand out: NW score's last row / last column maxima, the
-// `hrow` row and the last-true-column values the traceback kernel reads (va_traceback.cu).
+// arg-max of the last valid row and the last-true-column values the traceback kernel reads (va_traceback.cu).
 #include <algorithm>
 #include <type_traits>
 
@@ -26,12 +26,16 @@ namespace va {
 
 namespace {
 
-// Threads per block: 4 x 128 threads per SM leave 128 registers each (align: the planes need the warps),
-// 5 x 96 leave 136 (score: measured faster).
-template <bool ALIGN>
+// Threads per block and register cap: 4 x 128 threads per SM leave 128 registers each, 5 x 96 leave 136.
+// The row loop of the align kernels sits right at the limit, and ptxas' allocation there is not monotonic:
+// under the wrong cap it parks the direction predicates in a register and re-materialises them with two
+// LOP3 per cell (~540 -> ~900 instructions per row pair).  The pairs below are the ones whose loops come
+// out clean (tools/check_sass.py asserts it at build time); score kernels are clean under both, 96 x 5
+// measured faster.
+template <bool ALIGN, int TW>
 struct Block {
-    static constexpr int NT = ALIGN ? 128 : 96;
-    static constexpr int MAXREG = ALIGN ? 128 : 136;
+    static constexpr int NT = (ALIGN && TW == 32) ? 128 : 96;
+    static constexpr int MAXREG = (ALIGN && TW == 32) ? 128 : 136;
 };
 constexpr uint32_t NEG2 = 0x80008000u;  // (-32768, -32768): identity of the packed max
 
@@ -55,14 +59,15 @@ __device__ __forceinline__ void cp_async_wait() {
 // halves of the shared words stored with 16-bit stores.  Kept apart so the duo kernel's stores stay
 // unconditional (its schedule sits right at the register budget).
 template <bool ALIGN, int TW, bool SOLO>
-__global__ void __maxnreg__(Block<ALIGN>::MAXREG) fill_nw_kernel(ChunkGeom g, ChunkBuffers b, FastConsts fc) {
+__global__ void __maxnreg__((Block<ALIGN, TW>::MAXREG)) fill_nw_kernel(ChunkGeom g, ChunkBuffers b, FastConsts fc) {
     constexpr int NG = (TW + 15) / 16;
-    constexpr int NT = Block<ALIGN>::NT;
+    constexpr int NT = Block<ALIGN, TW>::NT;
     constexpr int MODE = ALIGN ? MODE_NW_ALIGN : MODE_NW_SCORE;
 
     __shared__ uint2 s_T2[256];              // [6*code_a + code_b] -> the two lanes' 4-entry score tables (36 used)
     __shared__ uint4 s_idx[3][NT];           // staged row indices: 16 rows per thread and buffer
     __shared__ uint32_t s_bnd[3][16][NT];    // staged right edge of the previous strip, [row][thread]
+    __shared__ uint32_t s_park[2][NT];        // per-thread values that only live between the strips
     for (int t = threadIdx.x; t < 256; t += NT) s_T2[t] = t < 36 ? make_uint2(fc.tab[t / 6], fc.tab[t % 6]) : make_uint2(0u, 0u);
     __syncthreads();
 
@@ -81,6 +86,11 @@ __global__ void __maxnreg__(Block<ALIGN>::MAXREG) fill_nw_kernel(ChunkGeom g, Ch
         uint4 *dirs = b.fdirs;
 
         uint32_t best = 0;  // score mode: max(0, last column, last row) of H
+        // align: best of the last valid row so far (shifted by gap_ref*rows, per lane) and its column per lane.
+        // Parked in shared memory during the sweeps: the row loop runs at the register limit, and anything
+        // that merely lives across it costs the schedule dearly.
+        volatile uint32_t *park = &s_park[0][threadIdx.x];
+        if (ALIGN) park[0] = park[NT] = 0x0000FFFFu;  // matrix column 0: value 0 (= rows*gap_ref), reported as column 0
         const int nstrips = (n + TW - 1) / TW;
         for (int s = 0; s < nstrips; ++s) {
             const int c0 = s * TW;
@@ -241,11 +251,23 @@ __global__ void __maxnreg__(Block<ALIGN>::MAXREG) fill_nw_kernel(ChunkGeom g, Ch
                 cp_async_wait<0>();
             }
             // Pass-through columns hold the value of the column left of the strip, so they are handed out
-            // like that column (no per-column guards: an idempotent store / a harmless repeat in the maximum).
-            if (ALIGN) {  // the row the end-cell rule scans (DefaultKernel.cpp:352-355,381-387), still shifted
+            // like that column (no per-column guards: a harmless repeat in the maximum).
+            if (ALIGN) {
+                // end-cell rule (DefaultKernel.cpp:352-355,381-387): first strictly greater column of the last
+                // valid row, column 0 (= rows*gap_ref) first.  Compared as V + gap_read*J, i.e. H - gap_ref*rows.
+                // Kept as one 32-bit key per lane, (value << 16) | (0xFFFF - column): the signed maximum is the
+                // larger value and, among equals, the smaller column -- no predicates.
+                int key_a = (int)park[0], key_b = (int)park[NT];
 #pragma unroll
-                for (int k = 0; k < TW; ++k)
-                    store_lanes<SOLO>(b.hrow + (size_t)max(c0 + k - pad, max(c0 - 1, 0)) * g.duos + duo, H[k], fw);
+                for (int k = 0; k < TW; ++k) {
+                    const int col = max(c0 + k - pad, c0 - 1);  // 0-based ref column of register k
+                    const uint32_t cand = add2(H[k], pk(fc.gR * (col + 1)));
+                    const uint32_t low = 0xFFFFu - (uint32_t)max(col, 0);
+                    key_a = max(key_a, (int)((cand << 16) | low));
+                    key_b = max(key_b, (int)((cand & 0xFFFF0000u) | low));
+                }
+                park[0] = (uint32_t)key_a;
+                park[NT] = (uint32_t)key_b;
             } else {  // whole last row (SSEKernel.cpp:1302-1310), un-shifted; column 0 is 0 and `best` starts at 0
 #pragma unroll
                 for (int k = 0; k < TW; ++k)
@@ -255,6 +277,21 @@ __global__ void __maxnreg__(Block<ALIGN>::MAXREG) fill_nw_kernel(ChunkGeom g, Ch
         if (!ALIGN) {
             if (!SOLO || fw.lane == 0) b.scores[b.pair_of[slot_a]] = (int16_t)(best & 0xFFFF);
             if (!SOLO || fw.lane == 1) b.scores[b.pair_of[slot_b]] = (int16_t)(best >> 16);
+        } else {
+            // the traceback kernel applies the pad-column / max_ref_pos clip to the column (va_traceback.cu)
+            const int key_a = (int)park[0], key_b = (int)park[NT];
+            if (!SOLO || fw.lane == 0) {
+                const int pa = b.pair_of[slot_a];
+                b.scores[pa] = (int16_t)((key_a >> 16) + fc.gF * m);
+                b.end_cell[2 * pa] = (int16_t)(m - 1);
+                b.end_cell[2 * pa + 1] = (int16_t)(0xFFFF - (key_a & 0xFFFF));
+            }
+            if (!SOLO || fw.lane == 1) {
+                const int pb = b.pair_of[slot_b];
+                b.scores[pb] = (int16_t)((key_b >> 16) + fc.gF * m);
+                b.end_cell[2 * pb] = (int16_t)(m - 1);
+                b.end_cell[2 * pb + 1] = (int16_t)(0xFFFF - (key_b & 0xFFFF));
+            }
         }
     };
     const int thread = blockIdx.x * blockDim.x + threadIdx.x;
@@ -273,7 +310,7 @@ __global__ void __maxnreg__(Block<ALIGN>::MAXREG) fill_nw_kernel(ChunkGeom g, Ch
 
 template <bool ALIGN, int TW>
 void launch_one(const ChunkGeom &g, const ChunkBuffers &b, const FastConsts &fc, cudaStream_t stream) {
-    const int threads = Block<ALIGN>::NT;
+    const int threads = Block<ALIGN, TW>::NT;
     const int duos = (g.n + 1) / 2;
     const int blocks = (duos + threads - 1) / threads;
     if (g.n >= 2) fill_nw_kernel<ALIGN, TW, false><<<blocks, threads, 0, stream>>>(g, b, fc);

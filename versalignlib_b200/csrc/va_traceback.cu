@@ -3,14 +3,14 @@
 // calc_alignment_* (DefaultKernel.cpp:391-525; SSEKernel.cpp:729-1005;
 // alignment_kernels.cl:146-192,370-414).
 //
-// One thread per pair, two phases, so that the only dependent chain through HBM is the walk:
-//   walk  follow the pointers from the end cell to START, one direction word per step (L2/HBM
-//         latency bound, hidden by occupancy); the moves go into a per-thread 2-bit queue in
-//         shared memory (global memory when the sequences are too long for that);
-//   emit  replay the queue: fetch the read/ref bytes it names and write both strings backwards,
-//         four characters per 32-bit store, so every output sector is written whole.
-// The packed fill kernel leaves NW's end-cell decision (arg-max of the last valid row,
-// DefaultKernel.cpp:352-355,381-387) to this kernel: `hrow` holds that row.
+// Two phases, so that the only dependent chain through HBM is the walk:
+//   walk  one thread per pair: follow the pointers from the end cell to START, one direction word per
+//         step (L2/HBM latency bound, hidden by occupancy); the moves go into a per-thread 2-bit queue
+//         in shared memory (global memory when the sequences are too long for that);
+//   emit  one warp per pair, 32 moves per step: replay the queue, fetch the read/ref bytes it names
+//         and write both strings backwards -- consecutive lanes, consecutive bytes.
+// The packed NW fill kernel finds the arg-max of the last valid row (DefaultKernel.cpp:352-355,381-387);
+// the clip to max_ref_pos and the pad-column rule of a trimmed ref are applied here.
 #include <climits>
 
 #include "va_fast.cuh"
@@ -48,63 +48,6 @@ struct ByteWindow {
     }
 };
 
-// Backwards byte STREAM over one raw sequence for the emit phase, which consumes each sequence strictly
-// from its end cell down to index 0: aligned 16-byte window loads, the window's words shifted down as
-// they are used up, one shift per byte -- no address arithmetic and no selects per byte.  Windows are
-// loaded lazily (only when a byte of them is needed), so nothing below the buffer is touched; the first
-// window is assembled byte-wise when it would reach past `limit` (end of the whole raw buffer).
-struct BackStream {
-    const uint4 *p;  // next (lower) window
-    uint4 w;
-    uint32_t cur;
-    int nbytes, nwords;
-    __device__ __forceinline__ void pop_word() {
-        cur = w.w;
-        w.w = w.z;
-        w.z = w.y;
-        w.y = w.x;
-        --nwords;
-    }
-    // the first byte returned is base[idx]; idx < 0 makes an empty stream (never read)
-    __device__ __forceinline__ void init(const uint8_t *base, int idx, const uint8_t *limit) {
-        nbytes = nwords = 0;
-        cur = 0;
-        w = make_uint4(0, 0, 0, 0);
-        p = nullptr;
-        if (idx < 0) return;
-        const uintptr_t a = reinterpret_cast<uintptr_t>(base + idx), a16 = a & ~(uintptr_t)15;
-        if (a16 + 16 <= reinterpret_cast<uintptr_t>(limit)) {
-            w = *reinterpret_cast<const uint4 *>(a16);
-        } else {  // last window of the buffer: only the bytes that exist
-            uint32_t t[4] = {0, 0, 0, 0};
-            for (uintptr_t q = a16; q <= a; ++q) t[(q - a16) >> 2] |= (uint32_t)*reinterpret_cast<const uint8_t *>(q) << (8 * ((q - a16) & 3));
-            w = make_uint4(t[0], t[1], t[2], t[3]);
-        }
-        p = reinterpret_cast<const uint4 *>(a16) - 1;
-        nwords = 4;
-        const int o = (int)(a & 15);
-        for (int d = 3; d > (o >> 2); --d) pop_word();  // words above the start are not part of the stream
-        pop_word();
-        cur <<= 8 * (3 - (o & 3));
-        nbytes = (o & 3) + 1;
-    }
-    __device__ __forceinline__ uint32_t next() {
-        if (nbytes == 0) {
-            if (nwords == 0) {
-                w = *p;
-                --p;
-                nwords = 4;
-            }
-            pop_word();
-            nbytes = 4;
-        }
-        const uint32_t b = cur >> 24;
-        cur <<= 8;
-        --nbytes;
-        return b;
-    }
-};
-
 // 2-bit move queue of one thread: word w lives at q[w * stride]
 struct MoveQueue {
     uint32_t *q;
@@ -116,9 +59,12 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
                                                                int queue_words) {
     const int gap_ref = sc.gap_ref;
     extern __shared__ uint32_t sq[];
+    __shared__ int s_moves[TB_THREADS], s_end_i[TB_THREADS], s_end_j[TB_THREADS], s_pair[TB_THREADS];
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= g.n) return;
     const bool moves_only = b.moves_out != nullptr;
+    const int L = g.read_length + g.ref_length;
+    s_moves[threadIdx.x] = -1;
+    if (slot < g.n) {
     MoveQueue mq;
     if (moves_only) {  // set below: the result region of the pair
         mq.q = nullptr;
@@ -130,7 +76,6 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
         mq.q = sq + threadIdx.x;
         mq.stride = TB_THREADS;
     }
-    const int L = g.read_length + g.ref_length;
     const PairMeta meta = b.meta[slot];
     const int rows = meta.rows, cols = meta.cols;
     const int mode = NW ? MODE_NW_ALIGN : MODE_SW_ALIGN;
@@ -141,17 +86,9 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
     // ---- end cell ----------------------------------------------------------------------
     int i, j;
     if (packed && NW) {
-        // first strictly greater column of matrix row `rows`, starting from column 0 = rows*gap_ref.
-        // hrow holds that row in the fill kernel's shifted form V = H - gap_ref*I - gap_read*J (va_nw.cu)
-        int best = rows * gap_ref, idx = 0;
-        const uint32_t *hr = b.hrow + duo;
-        for (int c = 0; c < cols; ++c) {
-            const int h = (int)(int16_t)(hr[(size_t)c * g.duos] >> lane_shift) + rows * gap_ref + (c + 1) * sc.gap_read;
-            if (h > best) {
-                best = h;
-                idx = c;
-            }
-        }
+        // the fill kernel left the arg-max of the last valid row (first strictly greater column, column 0 =
+        // rows*gap_ref first) in scores / end_cell; the clip is applied here
+        const int best = b.scores[pair], idx = b.end_cell[2 * pair + 1];
         i = rows - 1;
         // Pad columns (past `cols`, never filled) take part in the arg-max of the reference.  With both
         // gaps <= 0 one of them beats the best true cell exactly when a value of the last true column in
@@ -167,7 +104,6 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
         j = (pad_cols > 0 && col_max > best) ? (int)meta.max_ref_pos : min((int)meta.max_ref_pos, idx);
         b.end_cell[2 * pair] = (int16_t)i;
         b.end_cell[2 * pair + 1] = (int16_t)j;
-        b.scores[pair] = (int16_t)best;
     } else {
         i = b.end_cell[2 * pair];
         j = b.end_cell[2 * pair + 1];
@@ -305,87 +241,65 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
     }
 
     if (moves_only) {
-        b.start[pair] = (int16_t)(g.read_length + g.ref_length - 1 - n_moves);
-        return;
+        b.start[pair] = (int16_t)(L - 1 - n_moves);
+    } else {
+        s_moves[threadIdx.x] = n_moves;
+        s_end_i[threadIdx.x] = end_i;
+        s_end_j[threadIdx.x] = end_j;
+        s_pair[threadIdx.x] = pair;
     }
+    }  // slot < g.n
+    if (moves_only) return;
+    __syncthreads();
+
     // ---- emit ----------------------------------------------------------------------------
-    BackStream read, ref;
-    read.init(b.raw_reads + (size_t)pair * g.read_length, end_i, b.raw_reads + (size_t)g.n * g.read_length);
-    ref.init(b.raw_refs + (size_t)pair * g.ref_length, end_j, b.raw_refs + (size_t)g.n * g.ref_length);
-    uint8_t *oa = b.aln_read + (size_t)pair * L;
-    uint8_t *ob = b.aln_ref + (size_t)pair * L;
-    const int start = L - 1 - n_moves;  // may be negative only when every move was a gap (never with gap scores < 0)
-    b.start[pair] = (int16_t)start;
-    if (L >= 1) {
-        oa[L - 1] = 0;
-        ob[L - 1] = 0;
+    // Warp-cooperative: the walks of the block are done, their move queues sit in shared (or global)
+    // memory.  Each warp replays the queues of its 32 threads one pair at a time, 32 moves per step: lane l
+    // takes move t0+l, two ballots give every lane how many read / ref bases the moves before it consumed,
+    // so consecutive lanes fetch consecutive bases and write consecutive bytes of both gapped strings --
+    // every load and store of the step is one or two sectors.  (One thread per pair wrote its two strings
+    // with scattered 16-byte stores and spent most of the kernel doing so.)
+    const int lane = threadIdx.x & 31, warp_first = threadIdx.x & ~31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (int q = warp_first; q < warp_first + 32; ++q) {
+        const int n_moves = s_moves[q];
+        if (n_moves < 0) continue;  // past the end of the chunk
+        const int pair = s_pair[q];
+        const int end_i = s_end_i[q], end_j = s_end_j[q];
+        const uint32_t *qq = gq ? gq + (blockIdx.x * blockDim.x + q) : sq + q;
+        const size_t qstride = gq ? (size_t)g.slots : (size_t)TB_THREADS;
+        const uint8_t *rd = b.raw_reads + (size_t)pair * g.read_length;
+        const uint8_t *rf = b.raw_refs + (size_t)pair * g.ref_length;
+        uint8_t *oa = b.aln_read + (size_t)pair * L;
+        uint8_t *ob = b.aln_ref + (size_t)pair * L;
+        int used_r = 0, used_f = 0;  // bases consumed by the moves before this step
+        for (int t0 = 0; t0 < n_moves; t0 += 32) {
+            const int t = t0 + lane;
+            const bool valid = t < n_moves;
+            const uint32_t word = valid ? qq[(size_t)(t >> 4) * qstride] : 0u;
+            const int code = (word >> (2 * (t & 15))) & 3;
+            const bool takes_r = valid && code != DIR_LEFT, takes_f = valid && code != DIR_UP;
+            const unsigned mr = __ballot_sync(0xffffffffu, takes_r), mf = __ballot_sync(0xffffffffu, takes_f);
+            uint8_t a = '-', c = '-';
+            if (takes_r) a = rd[end_i - used_r - __popc(mr & lt_mask)];
+            if (takes_f) c = rf[end_j - used_f - __popc(mf & lt_mask)];
+            const int pos = L - 2 - t;
+            if (valid && pos >= 0) {
+                oa[pos] = a;
+                ob[pos] = c;
+            }
+            used_r += __popc(mr);
+            used_f += __popc(mf);
+        }
+        if (lane == 0) {
+            // start may be negative only when every move was a gap (never with gap scores < 0)
+            b.start[pair] = (int16_t)(L - 1 - n_moves);
+            if (L >= 1) {
+                oa[L - 1] = 0;
+                ob[L - 1] = 0;
+            }
+        }
     }
-    int pos = L - 2;
-    int t = 0;  // moves replayed so far
-    uint32_t mw = n_moves ? mq.q[0] : 0;
-    int mleft = 16;  // moves left in mw
-    size_t mnext = mq.stride;
-    auto next_move = [&]() -> int {
-        if (mleft == 0) {
-            mw = mq.q[mnext];
-            mnext += mq.stride;
-            mleft = 16;
-        }
-        const int code = mw & 3;
-        mw >>= 2;
-        --mleft;
-        ++t;
-        return code;
-    };
-    auto one_byte = [&]() {
-        const int code = next_move();
-        uint8_t a = '-', c = '-';
-        if (code != DIR_LEFT) a = (uint8_t)read.next();
-        if (code != DIR_UP) c = (uint8_t)ref.next();
-        if (pos >= 0) {
-            oa[pos] = a;
-            ob[pos] = c;
-        }
-        --pos;
-    };
-    // Both output rows start at pair*L from (at least 256-byte aligned) buffers, so they share their
-    // alignment: bytes down to a 4-byte boundary, words down to a 16-byte boundary, then 16 moves
-    // per pair of 16-byte stores, then the remainder the same way back down.
-    const uintptr_t base_a = reinterpret_cast<uintptr_t>(oa), base_b = reinterpret_cast<uintptr_t>(ob);
-    auto four_moves = [&](uint32_t &wa, uint32_t &wb) {
-        wa = 0;
-        wb = 0;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int code = next_move();
-            uint32_t a = '-', c = '-';
-            if (code != DIR_LEFT) a = read.next();
-            if (code != DIR_UP) c = ref.next();
-            wa |= a << (8 * (3 - r));
-            wb |= c << (8 * (3 - r));
-        }
-    };
-    auto one_word = [&]() {
-        uint32_t wa, wb;
-        four_moves(wa, wb);
-        *reinterpret_cast<uint32_t *>(oa + pos - 3) = wa;
-        *reinterpret_cast<uint32_t *>(ob + pos - 3) = wb;
-        pos -= 4;
-    };
-    if ((base_a & 15) == (base_b & 15)) {
-        while (t < n_moves && pos >= 0 && ((base_a + pos) & 3) != 3) one_byte();
-        while (n_moves - t >= 4 && pos >= 3 && ((base_a + pos) & 15) != 15) one_word();
-        while (n_moves - t >= 16 && pos >= 15) {
-            uint32_t wa[4], wb[4];
-#pragma unroll
-            for (int q = 3; q >= 0; --q) four_moves(wa[q], wb[q]);  // highest addresses first
-            *reinterpret_cast<uint4 *>(oa + pos - 15) = make_uint4(wa[0], wa[1], wa[2], wa[3]);
-            *reinterpret_cast<uint4 *>(ob + pos - 15) = make_uint4(wb[0], wb[1], wb[2], wb[3]);
-            pos -= 16;
-        }
-        while (n_moves - t >= 4 && pos >= 3) one_word();
-    }
-    while (t < n_moves) one_byte();
 }
 
 }  // namespace
