@@ -90,3 +90,20 @@ def ref_lib(name: str) -> str | None:
     """Path of a reference kernel built from /root/reference (Default, SSE, AVX) or None."""
     p = os.path.join(REF_DIR, f"lib{name}Kernel.so")
     return p if os.path.exists(p) else None
+
+
+def ref_parse_fasta(path: str) -> list[bytes] | None:
+    """The reference's own FastaProvider::parse_fasta (oracle/_ref/libref_util.so, built from
+    /root/reference by oracle/Makefile) -- None when that library is not there."""
+    p = os.path.join(REF_DIR, "libref_util.so")
+    if not os.path.exists(p):
+        return None
+    L = ctypes.CDLL(p)
+    L.ref_parse_fasta.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.POINTER(ctypes.c_char_p))]
+    L.ref_parse_fasta.restype = ctypes.c_int
+    L.ref_free_strings.argtypes = [ctypes.POINTER(ctypes.c_char_p), ctypes.c_int]
+    seqs = ctypes.POINTER(ctypes.c_char_p)()
+    n = L.ref_parse_fasta(path.encode(), ctypes.byref(seqs))
+    out = [seqs[i] for i in range(n)]  # c_char_p -> bytes (copied)
+    L.ref_free_strings(seqs, n)
+    return out

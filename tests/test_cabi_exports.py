@@ -24,8 +24,8 @@ def _no_gpu():
 
 
 def test_header_and_binding_agree():
-    text = open(os.path.join(ROOT, "include", "versalign_cuda.h")).read()
-    declared = sorted(set(re.findall(r"\b(va_cuda_[a-z_0-9]+)\s*\(", text)))
+    text = open(os.path.join(ROOT, "include", "versalign_cuda.h")).read() + open(os.path.join(ROOT, "include", "versalign_fasta.h")).read()
+    declared = sorted(set(re.findall(r"\b(va_(?:cuda|fasta)_[a-z_0-9]+)\s*\(", text)))
     assert declared == sorted(capi.C_ABI_SYMBOLS)
 
 

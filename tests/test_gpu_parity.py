@@ -287,3 +287,28 @@ def test_workspace_reuse_across_scorings(ctx):
         oa, ob, ostart, oend = ora.align(opt, 0, reads, refs)
         assert np.array_equal(start, ostart) and np.array_equal(end, oend), opt
         assert used_region_equal(a, b, start, oa, ob, ostart).size == 0, opt
+
+
+def test_fasta_to_packed_kernels(ctx, tmp_path):
+    """The path a maintainer would wire for a file-driven run: FASTA -> va_fasta_load -> packed entry points,
+    against the oracle on the same sequences padded the reference's way (parse_fasta + pad())."""
+    _, reads, refs = BATCHES[3]
+    paths = []
+    for tag, arr in (("reads", reads), ("refs", refs)):
+        path = str(tmp_path / f"{tag}.fa")
+        with open(path, "wb") as f:
+            for i in range(arr.shape[0]):
+                seq = arr[i].tobytes().rstrip(b"\0")
+                f.write(b">%s%d\n" % (tag.encode(), i))
+                for o in range(0, len(seq), 70):
+                    f.write(seq[o:o + 70] + b"\n")
+        paths.append(path)
+    pr, ro, rmax = capi.fasta_load(paths[0])
+    pf, fo, fmax = capi.fasta_load(paths[1])
+    padded_r = np.ascontiguousarray(reads[:, :rmax])
+    padded_f = np.ascontiguousarray(refs[:, :fmax])
+    for opt in (ora.SW, ora.NW):
+        assert np.array_equal(ctx.score_packed(opt, pr, ro, pf, fo), ora.score(opt, padded_r, padded_f)), opt
+        scores, coords, coff, cigar = ctx.align_packed(opt, 0, pr, ro, pf, fo)
+        want = synth.cigar_from_strings(*ora.align(opt, 0, padded_r, padded_f))
+        assert np.array_equal(coords, want[0]) and np.array_equal(coff, want[1]) and np.array_equal(cigar, want[2]), opt

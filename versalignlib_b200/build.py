@@ -30,7 +30,7 @@ NVCC_FLAGS = [
     "-I", INCLUDE, "-I", CSRC,
 ]
 
-CUDA_SOURCES = ["va_prep.cu", "va_kernels.cu", "va_fast.cu", "va_nw.cu", "va_intra.cu", "va_traceback.cu", "va_cabi.cu", "cuda_kernel_plugin.cpp"]
+CUDA_SOURCES = ["va_prep.cu", "va_kernels.cu", "va_fast.cu", "va_nw.cu", "va_intra.cu", "va_traceback.cu", "va_cabi.cu", "va_fasta.cpp", "cuda_kernel_plugin.cpp"]
 CUDA_HEADERS = ["va_device.cuh", "va_fast.cuh", "va_internal.h"]
 
 
@@ -64,7 +64,8 @@ def build_host(force: bool = False, verbose: bool = False) -> str:
 def build_cuda(force: bool = False, verbose: bool = False, extra: list[str] | None = None) -> str:
     srcs = [os.path.join(CSRC, s) for s in CUDA_SOURCES]
     deps = srcs + [os.path.join(CSRC, h) for h in CUDA_HEADERS] + [
-        os.path.join(INCLUDE, "versalign_cuda.h"), os.path.join(INCLUDE, "versalign_plugin_abi.h")]
+        os.path.join(INCLUDE, "versalign_cuda.h"), os.path.join(INCLUDE, "versalign_fasta.h"),
+        os.path.join(INCLUDE, "versalign_plugin_abi.h")]
     if force or _newer(CUDA_PLUGIN, deps):
         os.makedirs(LIBDIR, exist_ok=True)
         objs = []

@@ -18,7 +18,7 @@ POLICY_DEFAULT_OCL, POLICY_SIMD = 0, 1
 # every symbol include/versalign_cuda.h declares (tests check the .so exports all of them)
 C_ABI_SYMBOLS = [
     "va_cuda_abi_version", "va_cuda_last_error", "va_cuda_device_count", "va_cuda_create", "va_cuda_destroy",
-    "va_cuda_set_host_threads", "va_cuda_get_timings", "va_cuda_score_ptrs", "va_cuda_align_ptrs", "va_cuda_align_alloc", "va_cuda_align_records", "va_cuda_score_packed", "va_cuda_align_packed",
+    "va_cuda_set_host_threads", "va_cuda_get_timings", "va_cuda_score_ptrs", "va_cuda_align_ptrs", "va_cuda_align_alloc", "va_cuda_align_records", "va_cuda_score_packed", "va_cuda_align_packed", "va_fasta_load",
     "va_cuda_score_flat", "va_cuda_align_flat", "va_cuda_score_device", "va_cuda_align_device",
     "va_cuda_max_resident_pairs", "va_cuda_int_peak", "va_cuda_set_profiling", "va_cuda_get_kernel_ms",
     "va_cuda_plugin_timings",
@@ -97,6 +97,30 @@ def plugin_timings() -> dict | None:
     if lib().va_cuda_plugin_timings(ctypes.byref(t)) != 0:
         return None
     return t.as_dict()
+
+
+def fasta_load(path: str):
+    """va_fasta_load (include/versalign_fasta.h): a FASTA file as (bases uint8[total], offsets int64[n+1],
+    max_length) -- the packed layout score_packed / align_packed take.  Host code, no GPU needed."""
+    L = lib()
+    L.va_fasta_load.argtypes = [ctypes.c_char_p, _ALLOC_FN, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
+                                ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]
+    blocks = []
+
+    def _alloc(nbytes, _user):
+        buf = np.empty(max(int(nbytes), 1), dtype=np.uint8)
+        blocks.append(buf)
+        return buf.ctypes.data
+
+    cb = _ALLOC_FN(_alloc)
+    pb, po = ctypes.c_void_p(), ctypes.c_void_p()
+    n, mx = ctypes.c_int64(0), ctypes.c_int64(0)
+    rc = L.va_fasta_load(path.encode(), cb, None, ctypes.byref(pb), ctypes.byref(po), ctypes.byref(n), ctypes.byref(mx))
+    if rc != 0:
+        raise CudaError(f"va_fasta_load({path}) rc={rc}")
+    offsets = blocks[1][: (n.value + 1) * 8].view(np.int64).copy()
+    bases = blocks[0][: int(offsets[-1])]
+    return bases, offsets, int(mx.value)
 
 
 def device_count() -> int:
