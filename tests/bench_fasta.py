@@ -1,6 +1,6 @@
 """Host-side throughput of the FASTA ingest (va_fasta_load -> packed layout) next to the reference's
 parse_fasta (+ the pad() copy it needs before a kernel call), on a synthetic file.
-usage: python tools/bench_fasta.py [records] [length]"""
+usage: python tests/bench_fasta.py [records] [length]"""
 import os
 import sys
 import tempfile

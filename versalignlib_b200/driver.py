@@ -8,8 +8,8 @@ be put next to any other for a parity verdict, and the outcome is one JSON objec
 
   python -m versalignlib_b200.driver --mode nw_align --synthetic 100000,150,150
   python -m versalignlib_b200.driver --mode sw_score --reads reads.fa --refs refs.fa \\
-         --compare oracle/_ref/libDefaultKernel.so --reps 5
-  python -m versalignlib_b200.driver --kernel oracle/_ref/libSSEKernel.so --threads 1 --mode sw_score ...
+         --compare /path/to/libDefaultKernel.so --reps 5
+  python -m versalignlib_b200.driver --kernel /path/to/libSSEKernel.so --threads 1 --mode sw_score ...
 
 --kernel / --compare take the path of any library exporting the reference's four plug-in symbols
 (default --kernel: this package's libCUDAKernel.so).  Sequences come from two FASTA files (record i of
