@@ -312,3 +312,21 @@ def test_fasta_to_packed_kernels(ctx, tmp_path):
         scores, coords, coff, cigar = ctx.align_packed(opt, 0, pr, ro, pf, fo)
         want = synth.cigar_from_strings(*ora.align(opt, 0, padded_r, padded_f))
         assert np.array_equal(coords, want[0]) and np.array_equal(coff, want[1]) and np.array_equal(cigar, want[2]), opt
+
+
+def test_long_pairs_warp_per_pair_general_kernel(ctx):
+    """Long pairs outside the packed kernels' 16-bit domain (alignments with large scores, the SSE/AVX policy,
+    wide scoring, N inside the ref) take the warp-per-pair general kernel (fill_general_intra_kernel): all
+    four functions, both policies, odd sizes, several 512-column passes and a partial last one."""
+    reads, refs = synth.uniform_batch(9, 1100, 1300, p_sub=0.10, q_indel=0.03, seed=41)
+    dirty_refs = synth.sprinkle(5, refs, 0.01)
+    mixed_r, mixed_f, _, _ = synth.mixed_batch(7, 700, 1400, p_sub=0.1, q_indel=0.02, seed=42)
+    for name, r, f in (("uniform", reads, refs), ("dirty", reads, dirty_refs), ("mixed", mixed_r, mixed_f)):
+        for sc in [(2, -1, -3, -3), (20, -30, -50, -20)]:  # 20 x 1100 stays inside int16 (the exactness domain)
+            for opt in (ora.SW, ora.NW):
+                assert np.array_equal(ctx.score_flat(opt, r, f, sc), ora.score(opt, r, f, sc)), (name, sc, opt)
+                for policy in (0, 1):
+                    a, b, start, end = ctx.align_flat(opt, policy, r, f, sc)
+                    oa, ob, ostart, oend = ora.align(opt, policy, r, f, sc)
+                    assert np.array_equal(start, ostart) and np.array_equal(end, oend), (name, sc, opt, policy)
+                    assert used_region_equal(a, b, start, oa, ob, ostart).size == 0, (name, sc, opt, policy)

@@ -155,6 +155,175 @@ __global__ void __launch_bounds__(128) fill_general_kernel(ChunkGeom g, ChunkBuf
 }
 
 // ------------------------------------------------------------------------------------------
+// general fill, intra-task: one WARP per pair for long pairs the packed kernels cannot take (scores
+// past their 16-bit range, SSE/AVX pointer policy, dirty refs).  Same cell, same 32-bit arithmetic,
+// same direction and boundary layouts as fill_general_kernel -- so the traceback kernel does not know
+// the difference -- but the matrix is walked as a skewed wavefront: lane l owns 16 columns of a
+// 512-column pass and computes row t-l at step t, taking its left neighbour's right edge of that row
+// (computed one step earlier) by __shfl_up_sync.  One thread per pair needs seconds for a
+// 10 kbp x 12 kbp matrix; this needs tens of milliseconds.
+// ------------------------------------------------------------------------------------------
+
+template <int MODE, int POLICY>
+__global__ void __launch_bounds__(128) fill_general_intra_kernel(ChunkGeom g, ChunkBuffers b, Scoring sc) {
+    constexpr bool SW = MODE == MODE_SW_SCORE || MODE == MODE_SW_ALIGN;
+    constexpr bool ALIGN = MODE == MODE_SW_ALIGN || MODE == MODE_NW_ALIGN;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int PASS = 32 * GEN_TW;
+
+    __shared__ int sub[64];  // sub[read_code * 8 + ref_code]
+    if (threadIdx.x < 64) {
+        const int r = threadIdx.x >> 3, f = threadIdx.x & 7;
+        sub[threadIdx.x] = (r < 4 && f < 4) ? (r == f ? sc.match : sc.mismatch) : 0;
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (slot >= g.n) return;  // warp-uniform
+    if (slot_owner(g, MODE, slot, b.meta[slot & ~1], b.meta[slot | 1]) != OWN_NONE) return;
+    const PairMeta meta = b.meta[slot];
+    const int m = meta.rows, n = meta.cols;
+    const int gF = sc.gap_ref, gR = sc.gap_read;
+
+    // per-lane trackers, combined at the end (same rules as fill_general_kernel)
+    int best = 0, best_i = 0, best_j = 0;
+    int border = 0;
+    int row_max = m * gF, row_idx = 0;
+    const int pad_cols = MODE == MODE_NW_ALIGN ? g.ref_length - n : 0;
+    const int pad_reach = min(pad_cols, m);
+    int col_max = (pad_reach == m && m > 0) ? 0 : INT_MIN;
+    if (MODE == MODE_NW_ALIGN && n == 0 && pad_reach > 0) col_max = max(col_max, (m - pad_reach) * gF);
+    const uint8_t *rbytes = reinterpret_cast<const uint8_t *>(b.code_reads) + (size_t)slot * 16;
+    const size_t rstride = (size_t)g.slots * 16;
+
+    for (int c_base = 0; c_base < n; c_base += PASS) {
+        const int c0 = c_base + lane * GEN_TW;
+        const bool has_cols = c0 < n;
+        const bool last_pass = c_base + PASS >= n;
+        uint32_t fw[4] = {0, 0, 0, 0};
+        if (has_cols) {
+            const uint4 fq = b.code_refs[(size_t)(c0 >> 4) * g.slots + slot];
+            fw[0] = fq.x; fw[1] = fq.y; fw[2] = fq.z; fw[3] = fq.w;
+        }
+        int H[GEN_TW];
+#pragma unroll
+        for (int k = 0; k < GEN_TW; ++k) H[k] = 0;
+        int diag_in = 0, out_left = 0;
+        __syncwarp();  // the previous pass's boundary stores (lane 31) are visible to lane 0
+        for (int t = 0; t < m + 31; ++t) {
+            const int from_left = __shfl_up_sync(FULL, out_left, 1);  // left neighbour's right edge of my row
+            const int i = t - lane;
+            if (i < 0 || i >= m || !has_cols) continue;
+            const int rc = rbytes[(size_t)(i >> 4) * rstride + (i & 15)];
+            const int *srow = sub + rc * 8;
+            int left;
+            if (lane == 0) {
+                if (c_base == 0) left = MODE == MODE_NW_ALIGN ? (i + 1) * gF : 0;  // matrix column 0
+                else left = b.boundary[(size_t)i * g.slots + slot];
+            } else {
+                left = from_left;
+            }
+            int diag = diag_in;
+            diag_in = left;
+            uint32_t dirbits = 0;
+#pragma unroll
+            for (int k = 0; k < GEN_TW; ++k) {
+                const int fc = (fw[k >> 2] >> (8 * (k & 3))) & 0xFF;
+                const int up = H[k];
+                const int d = diag + srow[fc];
+                const int u = up + gF;
+                const int l = left + gR;
+                int h = max(d, max(u, l));
+                if (SW) h = max(h, 0);
+                if (ALIGN) {
+                    int code;
+                    if (POLICY == 0) {
+                        code = h == d ? DIR_DIAG : (h == u ? DIR_UP : DIR_LEFT);
+                        if (SW && h == 0) code = DIR_START;
+                    } else {
+                        code = DIR_START;
+                        if (h == u) code = DIR_UP;
+                        if (h == l) code = DIR_LEFT;
+                        if (h == d && rc < 4 && fc < 4) code = DIR_DIAG;
+                    }
+                    dirbits |= (uint32_t)code << (2 * k);
+                }
+                const bool in_range = c0 + k < n;
+                if (MODE == MODE_SW_SCORE) {
+                    if (in_range) best = max(best, h);
+                } else if (MODE == MODE_SW_ALIGN) {
+                    if (in_range && (h > best || (h == best && i < best_i))) {
+                        best = h;
+                        best_i = i;
+                        best_j = c0 + k;
+                    }
+                } else if (MODE == MODE_NW_SCORE) {
+                    if (in_range && (c0 + k == n - 1 || i == m - 1)) border = max(border, h);
+                } else {
+                    if (in_range && i == m - 1 && h > row_max) {
+                        row_max = h;
+                        row_idx = c0 + k;
+                    }
+                    if (c0 + k == n - 1 && i < m - 1 && i >= m - 1 - pad_reach) col_max = max(col_max, h);
+                }
+                diag = up;
+                H[k] = h;
+                left = h;
+            }
+            out_left = left;
+            if (lane == 31 && !last_pass) b.boundary[(size_t)i * g.slots + slot] = left;
+            if (ALIGN) {
+                const int seg = c0 >> 3;
+                b.dirs[((size_t)seg * g.rows_alloc + i) * g.slots + slot] = (uint16_t)(dirbits & 0xFFFF);
+                if (seg + 1 < g.segs)
+                    b.dirs[((size_t)(seg + 1) * g.rows_alloc + i) * g.slots + slot] = (uint16_t)(dirbits >> 16);
+            }
+        }
+    }
+    // combine the lanes.  SW align: greatest value, then smallest row, then smallest column (= first strictly
+    // greater cell in row-major order); NW align: greatest value, then smallest column, column 0's seed first.
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const int ob = __shfl_xor_sync(FULL, best, o), oi = __shfl_xor_sync(FULL, best_i, o), oj = __shfl_xor_sync(FULL, best_j, o);
+        if (MODE == MODE_SW_ALIGN) {
+            if (ob > best || (ob == best && (oi < best_i || (oi == best_i && oj < best_j)))) {
+                best = ob;
+                best_i = oi;
+                best_j = oj;
+            }
+        } else {
+            best = max(best, ob);
+        }
+        border = max(border, __shfl_xor_sync(FULL, border, o));
+        const int om = __shfl_xor_sync(FULL, row_max, o), ox = __shfl_xor_sync(FULL, row_idx, o);
+        if (om > row_max || (om == row_max && ox < row_idx)) {
+            row_max = om;
+            row_idx = ox;
+        }
+        col_max = max(col_max, __shfl_xor_sync(FULL, col_max, o));
+    }
+    if (lane == 0) {
+        const int pair = b.pair_of[slot];
+        if (MODE == MODE_SW_SCORE) {
+            b.scores[pair] = (int16_t)best;
+        } else if (MODE == MODE_NW_SCORE) {
+            b.scores[pair] = (int16_t)border;
+        } else if (MODE == MODE_SW_ALIGN) {
+            b.end_cell[2 * pair] = (int16_t)best_i;
+            b.end_cell[2 * pair + 1] = (int16_t)best_j;
+            b.scores[pair] = (int16_t)best;
+        } else {
+            b.end_cell[2 * pair] = (int16_t)(m - 1);
+            const bool pad_wins = pad_cols > 0 && col_max > row_max;
+            b.end_cell[2 * pair + 1] = (int16_t)(pad_wins ? (int)meta.max_ref_pos : min((int)meta.max_ref_pos, row_idx));
+            b.scores[pair] = (int16_t)row_max;
+        }
+        atomicAdd(b.cell_count, (unsigned long long)m * (unsigned long long)n);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // integer-pipe peak: dependent VIADDMNMX / VIMNMX3 chains, registers only
 // ------------------------------------------------------------------------------------------
 
@@ -191,7 +360,15 @@ __global__ void __launch_bounds__(256) int_peak_kernel(int iters, unsigned int s
 
 template <int MODE>
 static void launch_fill_mode(const ChunkGeom &g, const ChunkBuffers &b, int policy, const Scoring &sc, cudaStream_t stream) {
-    const int threads = 128, blocks = (g.n + threads - 1) / threads;
+    const int threads = 128;
+    // long pairs: a warp per pair (a thread per pair would take seconds per matrix)
+    if ((long long)g.read_length * g.ref_length >= (1LL << 20) && (long long)g.n * 32 <= (1LL << 30)) {
+        const int blocks = (int)(((long long)g.n * 32 + threads - 1) / threads);
+        if (policy == 0) fill_general_intra_kernel<MODE, 0><<<blocks, threads, 0, stream>>>(g, b, sc);
+        else fill_general_intra_kernel<MODE, 1><<<blocks, threads, 0, stream>>>(g, b, sc);
+        return;
+    }
+    const int blocks = (g.n + threads - 1) / threads;
     if (policy == 0) fill_general_kernel<MODE, 0><<<blocks, threads, 0, stream>>>(g, b, sc);
     else fill_general_kernel<MODE, 1><<<blocks, threads, 0, stream>>>(g, b, sc);
 }
