@@ -863,9 +863,21 @@ int run_host_call(va_cuda_ctx *ctx, HostCall &c) {
         const int nd = (int)ctx->engines.size();
         std::vector<ShardStats> stats(nd);
         std::vector<std::thread> threads;
-        // uniform padded lengths: equal pair counts == equal padded cells per device
+        // Contiguous slices per device.  Fixed-stride input: equal pair counts (== equal padded cells).
+        // Offset-addressed input knows every length: cut where the running sum of rows x cols crosses
+        // k/nd of the total, so mixed-length batches load the devices evenly.
+        std::vector<int64_t> cut((size_t)nd + 1);
+        for (int d = 0; d <= nd; ++d) cut[(size_t)d] = (int64_t)c.n * d / nd;
+        if (nd > 1 && c.read_off) {
+            std::vector<double> csum((size_t)c.n + 1, 0.0);
+            for (int i = 0; i < c.n; ++i)
+                csum[(size_t)i + 1] = csum[(size_t)i] + (double)(c.read_off[i + 1] - c.read_off[i]) * (double)(c.ref_off[i + 1] - c.ref_off[i]);
+            for (int d = 1; d < nd; ++d)
+                cut[(size_t)d] = std::lower_bound(csum.begin(), csum.end(), csum.back() * d / nd) - csum.begin();
+            for (int d = 1; d <= nd; ++d) cut[(size_t)d] = std::max(cut[(size_t)d], cut[(size_t)d - 1]);
+        }
         for (int d = 0; d < nd; ++d) {
-            const int64_t lo = (int64_t)c.n * d / nd, hi = (int64_t)c.n * (d + 1) / nd;
+            const int64_t lo = cut[(size_t)d], hi = cut[(size_t)d + 1];
             if (hi <= lo) continue;
             const int chunk = pick_chunk_pairs(ctx->engines[d], c.sh, hi - lo);
             if (nd == 1) {
