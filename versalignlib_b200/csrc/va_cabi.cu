@@ -846,8 +846,10 @@ int pick_chunk_pairs(const Engine &e, const Shape &sh, int64_t shard_pairs) {
     int64_t cap = (int64_t)std::max<size_t>(64, budget / std::max<size_t>(per_pair, 1));
     // pinned staging per slot at most ~512 MiB
     cap = std::min<int64_t>(cap, std::max<int64_t>(64, ((int64_t)512 << 20) / (int64_t)std::max<size_t>(sh.per_pair_io(), 1)));
-    // aim for >= 8 chunks per shard so the pipeline overlaps, but keep chunks >= 16k pairs
-    int64_t want = std::max<int64_t>((shard_pairs + 7) / 8, 16384);
+    // aim for >= 8 chunks per shard so the pipeline overlaps, but keep chunks >= min_chunk pairs (a chunk
+    // costs a fixed ~0.3 ms of launches, copies and hand-offs)
+    static const int64_t min_chunk = [] { const char *v = getenv("VERSALIGN_CUDA_MIN_CHUNK"); return v && atoll(v) > 0 ? atoll(v) : 65536LL; }();
+    int64_t want = std::max<int64_t>((shard_pairs + 7) / 8, min_chunk);
     want = std::min<int64_t>(want, cap);
     want = std::min<int64_t>(want, std::max<int64_t>(shard_pairs, 1));
     want = (int64_t)round_up((size_t)want, 64);
