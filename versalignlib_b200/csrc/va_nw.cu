@@ -32,10 +32,13 @@ namespace {
 // LOP3 per cell (~540 -> ~900 instructions per row pair).  The pairs below are the ones whose loops come
 // out clean (tools/check_sass.py asserts it at build time); score kernels are clean under both, 96 x 5
 // measured faster.
-template <bool ALIGN, int TW>
+template <bool ALIGN, int TW, bool SOLO>
 struct Block {
-    static constexpr int NT = (ALIGN && TW == 32) ? 128 : 96;
-    static constexpr int MAXREG = (ALIGN && TW == 32) ? 128 : 136;
+    // align duo kernels: 4 x 128 threads.  TW 30 is compiled under a cap of 136 (ptxas then settles on a clean
+    // 128-register schedule; under a cap of 128 it does not), TW 32 under 128.  Everything else: 5 x 96.
+    static constexpr bool MAIN_ALIGN = ALIGN && !SOLO;
+    static constexpr int NT = MAIN_ALIGN ? 128 : 96;
+    static constexpr int MAXREG = (MAIN_ALIGN && TW == 32) ? 128 : 136;
 };
 constexpr uint32_t NEG2 = 0x80008000u;  // (-32768, -32768): identity of the packed max
 
@@ -59,9 +62,9 @@ __device__ __forceinline__ void cp_async_wait() {
 // halves of the shared words stored with 16-bit stores.  Kept apart so the duo kernel's stores stay
 // unconditional (its schedule sits right at the register budget).
 template <bool ALIGN, int TW, bool SOLO>
-__global__ void __maxnreg__((Block<ALIGN, TW>::MAXREG)) fill_nw_kernel(ChunkGeom g, ChunkBuffers b, FastConsts fc) {
+__global__ void __maxnreg__((Block<ALIGN, TW, SOLO>::MAXREG)) fill_nw_kernel(ChunkGeom g, ChunkBuffers b, FastConsts fc) {
     constexpr int NG = (TW + 15) / 16;
-    constexpr int NT = Block<ALIGN, TW>::NT;
+    constexpr int NT = Block<ALIGN, TW, SOLO>::NT;
     constexpr int MODE = ALIGN ? MODE_NW_ALIGN : MODE_NW_SCORE;
 
     __shared__ uint2 s_T2[256];              // [6*code_a + code_b] -> the two lanes' 4-entry score tables (36 used)
@@ -310,13 +313,17 @@ __global__ void __maxnreg__((Block<ALIGN, TW>::MAXREG)) fill_nw_kernel(ChunkGeom
 
 template <bool ALIGN, int TW>
 void launch_one(const ChunkGeom &g, const ChunkBuffers &b, const FastConsts &fc, cudaStream_t stream) {
-    const int threads = Block<ALIGN, TW>::NT;
     const int duos = (g.n + 1) / 2;
-    const int blocks = (duos + threads - 1) / threads;
-    if (g.n >= 2) fill_nw_kernel<ALIGN, TW, false><<<blocks, threads, 0, stream>>>(g, b, fc);
+    if (g.n >= 2) {
+        const int threads = Block<ALIGN, TW, false>::NT;
+        fill_nw_kernel<ALIGN, TW, false><<<(duos + threads - 1) / threads, threads, 0, stream>>>(g, b, fc);
+    }
     // leftovers of the bucketing: a fixed grid strides over the list the prep kernel compiled (empty on a
     // uniform batch: the blocks read the count and leave)
-    if (g.solo) fill_nw_kernel<ALIGN, TW, true><<<std::min(2 * blocks, 148 * 4), threads, 0, stream>>>(g, b, fc);
+    if (g.solo) {
+        const int threads = Block<ALIGN, TW, true>::NT;
+        fill_nw_kernel<ALIGN, TW, true><<<std::min(2 * ((duos + threads - 1) / threads), 148 * 4), threads, 0, stream>>>(g, b, fc);
+    }
 }
 
 }  // namespace
