@@ -330,3 +330,22 @@ def test_long_pairs_warp_per_pair_general_kernel(ctx):
                     oa, ob, ostart, oend = ora.align(opt, policy, r, f, sc)
                     assert np.array_equal(start, ostart) and np.array_equal(end, oend), (name, sc, opt, policy)
                     assert used_region_equal(a, b, start, oa, ob, ostart).size == 0, (name, sc, opt, policy)
+
+
+def test_nw_align_end_aligned_duos(ctx):
+    """Packed NW align takes duos whose reads differ in length by starting the shorter lane late (CODE_PRE
+    rows): refs of one length, reads of every length from 1 up, odd and even offsets, trimmed and full refs."""
+    rng = np.random.default_rng(77)
+    n, L = 600, 96
+    refs = synth.random_seqs(rng, n, L)
+    reads = synth.mutate_from_ref(rng, refs, L, 0.1, 0.03)
+    lens = rng.integers(1, L + 1, size=n)
+    reads = np.where(np.arange(L)[None, :] < lens[:, None], reads, 0).astype(np.uint8)
+    short_refs = refs.copy()
+    short_refs[:, 80:] = 0  # padded refs: the pad-column rule reads the last true column at shifted rows
+    for f in (refs, short_refs):
+        for sc in PARAM_SETS[:3]:
+            a, b, start, end = ctx.align_flat(ora.NW, 0, reads, f, sc)
+            oa, ob, ostart, oend = ora.align(ora.NW, 0, reads, f, sc)
+            assert np.array_equal(start, ostart) and np.array_equal(end, oend), sc
+            assert used_region_equal(a, b, start, oa, ob, ostart).size == 0, sc

@@ -76,11 +76,11 @@ __global__ void __maxnreg__((FastBlock<MODE, TW, SYM, SOLO>::MAXREG)) fill_fast_
     constexpr int NG = (TW + 15) / 16;
     static_assert(MODE == MODE_SW_ALIGN || MODE == MODE_SW_SCORE, "SW modes only");
 
-    __shared__ uint2 s_T2[256];              // [6*code_a + code_b] -> the two lanes' 4-entry score tables (36 used)
+    __shared__ uint2 s_T2[256];              // [7*code_a + code_b] -> the two lanes' 4-entry score tables (49 used)
     constexpr int NT = FastBlock<MODE, TW, SYM, SOLO>::NT;
     __shared__ uint4 s_idx[3][NT];           // staged row indices: 16 rows per thread and buffer
     __shared__ uint32_t s_bnd[3][16][NT];    // staged right edge of the previous strip, [row][thread]
-    for (int t = threadIdx.x; t < 256; t += NT) s_T2[t] = t < 36 ? make_uint2(fc.tab[t / 6], fc.tab[t % 6]) : make_uint2(0u, 0u);
+    for (int t = threadIdx.x; t < 256; t += NT) s_T2[t] = t < 49 ? make_uint2(fc.tab[t / 7], fc.tab[t % 7]) : make_uint2(0u, 0u);
     __syncthreads();
 
     unsigned long long cells = 0;
@@ -448,6 +448,7 @@ FastConsts make_fast_consts(int mode, const Scoring &sc) {
     const bool nw = mode == MODE_NW_SCORE || mode == MODE_NW_ALIGN;  // shifted recurrence, va_nw.cu
     const int off = nw ? sc.gap_ref + sc.gap_read : align ? sc.gap_ref : 0;
     for (int c = 0; c < 8; ++c) fc.tab[c] = table_word(c, sc.match, sc.mismatch, off);
+    if (nw) fc.tab[CODE_PRE] = 0u;  // rows in front of a late-starting lane: s' = 0 hands matrix row 0 down (va_nw.cu)
     fc.gF = sc.gap_ref;
     fc.gR = sc.gap_read;
     fc.gF2 = ((uint32_t)sc.gap_ref & 0xFFFFu) * 0x00010001u;

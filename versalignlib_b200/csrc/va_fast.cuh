@@ -13,16 +13,16 @@ namespace va {
 // general kernel computes both pairs.  Both kernels evaluate it, so no flag is exchanged.
 //   - the per-column PRMT selector cannot express "scores 0", so no non-ACGT byte may sit inside
 //     the ref columns that are filled (non-ACGT READ bytes are fine: their row table is all zero);
-//   - both lanes sweep the same columns; rows may differ for SW and the score modes (trailing rows
-//     that can only score 0 are neutral) but not for NW align, whose end-cell rule reads one exact row.
+//   - both lanes sweep the same columns; rows may differ: for SW and the score modes trailing rows
+//     that can only score 0 are neutral; NW align end-aligns the lanes (CODE_PRE rows, va_internal.h).
 __device__ __forceinline__ bool duo_is_fast(const ChunkGeom &g, int mode, int slot_a, const PairMeta &a, const PairMeta &b) {
     if (g.fast_tw == 0 || slot_a + 1 >= g.n) return false;
     if ((a.flags & 2) || (b.flags & 2)) return false;
     if (a.cols != b.cols || a.cols <= 0) return false;
     if (a.cols != a.true_cols || b.cols != b.true_cols) return false;  // no padded / N tail inside the sweep
-    // NW align's end-cell rule reads the last valid row, which is taken from the registers after the
-    // sweep: both lanes must end on the same row (the bucketing sort makes that the common case)
-    if (mode == MODE_NW_ALIGN) return a.rows == b.rows && a.rows > 0;
+    // NW align's end-cell rule reads each lane's last valid row from the registers after the sweep: lanes
+    // of different read lengths are end-aligned (nw_row_offset), so both need at least one row
+    if (mode == MODE_NW_ALIGN) return a.rows > 0 && b.rows > 0;
     return max(a.rows, b.rows) > 0;
 }
 
@@ -129,6 +129,9 @@ __device__ __forceinline__ int fast_groups(int tw) { return (tw + 15) >> 4; }
 // Two rows per word keep the fill kernel's stores 16 bytes wide and fully coalesced and halve
 // the number of dependent loads of the traceback walk.
 __device__ __forceinline__ int fast_row_pairs(const ChunkGeom &g) { return (g.rows_alloc + 1) >> 1; }
+
+// Packed NW align, duo lanes of different read lengths: sweep row of a lane's matrix row r is r + this
+__device__ __forceinline__ int nw_row_offset(const PairMeta &me, const PairMeta &other) { return max((int)me.rows, (int)other.rows) - (int)me.rows; }
 
 // index (in uint4 units) of the word holding `row`
 __device__ __forceinline__ size_t fast_dir_index(const ChunkGeom &g, int strip, int row, int group, int duo) {

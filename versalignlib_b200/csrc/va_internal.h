@@ -14,6 +14,10 @@ namespace va {
 // look for the end of a sequence (DefaultKernel.cpp:308,348) while SSE/AVX do not
 // (SSEKernel.cpp:514-518,673-677).
 enum : int { CODE_A = 0, CODE_C = 1, CODE_G = 2, CODE_T = 3, CODE_N = 4, CODE_OTHER = 5 };
+// Row index only (never a base code): a row in front of a lane's first matrix row.  A duo whose reads differ
+// in length is END-aligned in packed NW align -- the shorter lane starts max(rows) - rows sweep rows late --
+// and in the shifted recurrence a row whose table is all zero just hands matrix row 0 down (va_nw.cu).
+enum : int { CODE_PRE = 6 };
 
 // direction codes, shared with the traceback kernel (same numbering as SSEKernel.h:28-31)
 enum : int { DIR_START = 0, DIR_UP = 1, DIR_LEFT = 2, DIR_DIAG = 3 };
@@ -67,7 +71,7 @@ struct ChunkBuffers {
     const uint8_t *raw_refs;   // [n][ref_length]
     uint4 *code_reads;         // [read_chunks][slots]
     uint4 *code_refs;          // [ref_chunks][slots]
-    uint4 *row_idx;            // [read_chunks][duos]: per matrix row 6*code(slot 2u) + code(slot 2u+1), 16 rows per word
+    uint4 *row_idx;            // [read_chunks][duos]: per sweep row 7*code(slot 2u) + code(slot 2u+1), 16 rows per word
                                // (the packed NW kernels' index into their table of score-table pairs)
     PairMeta *meta;            // [slots]
     int32_t *pair_of;          // [slots] pair (position in the caller's batch) computed in this slot, -1 = padding

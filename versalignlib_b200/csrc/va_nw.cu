@@ -15,6 +15,10 @@
 // formed, and the value a cell hands to its right neighbour and to the row below is one register.
 // With both gap scores <= 0 (required here; otherwise the general kernel runs) V is non-negative and
 // non-decreasing along rows and columns, which bounds the 16-bit range check.
+// A duo whose reads differ in length is END-aligned in align mode: the shorter lane's first rows carry the
+// row index CODE_PRE, whose table is all zero -- with s' = 0 a row reproduces the one above it (V(0,.) is
+// non-decreasing), so matrix row 0 is handed down to where that lane really starts, both lanes finish on
+// the last sweep row, and the end-cell rule reads both from the registers.
 // The matrix borders un-shift what they hand out: NW score's last row / last column maxima, the
 // arg-max of the last valid row and the last-true-column values the traceback kernel reads (va_traceback.cu).
 #include <algorithm>
@@ -67,11 +71,11 @@ __global__ void __maxnreg__((Block<ALIGN, TW, SOLO>::MAXREG)) fill_nw_kernel(Chu
     constexpr int NT = Block<ALIGN, TW, SOLO>::NT;
     constexpr int MODE = ALIGN ? MODE_NW_ALIGN : MODE_NW_SCORE;
 
-    __shared__ uint2 s_T2[256];              // [6*code_a + code_b] -> the two lanes' 4-entry score tables (36 used)
+    __shared__ uint2 s_T2[256];              // [7*code_a + code_b] -> the two lanes' 4-entry score tables (49 used)
     __shared__ uint4 s_idx[3][NT];           // staged row indices: 16 rows per thread and buffer
     __shared__ uint32_t s_bnd[3][16][NT];    // staged right edge of the previous strip, [row][thread]
     __shared__ uint32_t s_park[2][NT];        // per-thread values that only live between the strips
-    for (int t = threadIdx.x; t < 256; t += NT) s_T2[t] = t < 36 ? make_uint2(fc.tab[t / 6], fc.tab[t % 6]) : make_uint2(0u, 0u);
+    for (int t = threadIdx.x; t < 256; t += NT) s_T2[t] = t < 49 ? make_uint2(fc.tab[t / 7], fc.tab[t % 7]) : make_uint2(0u, 0u);
     __syncthreads();
 
     unsigned long long cells = 0;
@@ -285,14 +289,14 @@ __global__ void __maxnreg__((Block<ALIGN, TW, SOLO>::MAXREG)) fill_nw_kernel(Chu
             const int key_a = (int)park[0], key_b = (int)park[NT];
             if (!SOLO || fw.lane == 0) {
                 const int pa = b.pair_of[slot_a];
-                b.scores[pa] = (int16_t)((key_a >> 16) + fc.gF * m);
-                b.end_cell[2 * pa] = (int16_t)(m - 1);
+                b.scores[pa] = (int16_t)((key_a >> 16) + fc.gF * (SOLO ? m : (int)fw.ma.rows));
+                b.end_cell[2 * pa] = (int16_t)((SOLO ? m : (int)fw.ma.rows) - 1);
                 b.end_cell[2 * pa + 1] = (int16_t)(0xFFFF - (key_a & 0xFFFF));
             }
             if (!SOLO || fw.lane == 1) {
                 const int pb = b.pair_of[slot_b];
-                b.scores[pb] = (int16_t)((key_b >> 16) + fc.gF * m);
-                b.end_cell[2 * pb] = (int16_t)(m - 1);
+                b.scores[pb] = (int16_t)((key_b >> 16) + fc.gF * (SOLO ? m : (int)fw.mb.rows));
+                b.end_cell[2 * pb] = (int16_t)((SOLO ? m : (int)fw.mb.rows) - 1);
                 b.end_cell[2 * pb + 1] = (int16_t)(0xFFFF - (key_b & 0xFFFF));
             }
         }

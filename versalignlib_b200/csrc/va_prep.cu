@@ -183,10 +183,34 @@ __global__ void __launch_bounds__(256) encode_kernel(ChunkGeom g, ChunkBuffers b
             const uint4 ca = codes_pair_reads[(size_t)c * g.slots + pair];
             b.code_reads[(size_t)c * g.slots + slot] = ca;
             if (b.row_idx && (slot & 1) == 0) {
-                // the duo's row index: 6*code_a + code_b per byte (no carries: codes are <= 5)
+                // the duo's row index: 7*code_a + code_b per byte (no carries: codes are <= 6)
                 uint4 cb = make_uint4(0x05050505u, 0x05050505u, 0x05050505u, 0x05050505u);
-                if (slot + 1 < g.n) cb = codes_pair_reads[(size_t)c * g.slots + order[slot + 1]];
-                b.row_idx[(size_t)c * g.duos + (slot >> 1)] = make_uint4(ca.x * 6u + cb.x, ca.y * 6u + cb.y, ca.z * 6u + cb.z, ca.w * 6u + cb.w);
+                uint4 cx = ca;
+                const bool has_b = slot + 1 < g.n;
+                const int pair_b = has_b ? (int)order[slot + 1] : 0;
+                if (has_b) cb = codes_pair_reads[(size_t)c * g.slots + pair_b];
+                if (mode == MODE_NW_ALIGN && has_b) {
+                    // packed NW align end-aligns a duo's lanes: the lane with fewer rows starts late, behind
+                    // CODE_PRE rows (va_internal.h); only duos the packed kernel takes are ever read back
+                    // (slots that end up solo sweep from their own row 0: no shift for them)
+                    const PairMeta ma = meta_pair[pair], mb = meta_pair[pair_b];
+                    const bool duo = duo_is_fast(g, mode, slot, ma, mb);
+                    const int off_a = duo ? nw_row_offset(ma, mb) : 0, off_b = duo ? nw_row_offset(mb, ma) : 0;
+                    auto shifted = [&](int p, int off) {
+                        uint32_t w[4];
+                        const uint8_t *src = reinterpret_cast<const uint8_t *>(codes_pair_reads);
+                        for (int r = 0; r < 16; ++r) {
+                            const int row = c * 16 + r - off;
+                            const uint32_t code = row < 0 ? (uint32_t)CODE_PRE : (uint32_t)src[((size_t)(row >> 4) * g.slots + p) * 16 + (row & 15)];
+                            if ((r & 3) == 0) w[r >> 2] = 0;
+                            w[r >> 2] |= code << (8 * (r & 3));
+                        }
+                        return make_uint4(w[0], w[1], w[2], w[3]);
+                    };
+                    if (off_a > 0) cx = shifted(pair, off_a);
+                    if (off_b > 0) cb = shifted(pair_b, off_b);
+                }
+                b.row_idx[(size_t)c * g.duos + (slot >> 1)] = make_uint4(cx.x * 7u + cb.x, cx.y * 7u + cb.y, cx.z * 7u + cb.z, cx.w * 7u + cb.w);
             }
         } else b.code_refs[(size_t)(c - g.read_chunks) * g.slots + slot] = codes_pair_refs[(size_t)(c - g.read_chunks) * g.slots + pair];
     }

@@ -79,7 +79,11 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
     const PairMeta meta = b.meta[slot];
     const int rows = meta.rows, cols = meta.cols;
     const int mode = NW ? MODE_NW_ALIGN : MODE_SW_ALIGN;
-    const bool packed = slot_owner(g, mode, slot, b.meta[slot & ~1], b.meta[slot | 1]) != OWN_NONE;
+    const PairMeta meta_other = b.meta[slot ^ 1];
+    const int owner = slot_owner(g, mode, slot, (slot & 1) ? meta_other : meta, (slot & 1) ? meta : meta_other);
+    const bool packed = owner != OWN_NONE;
+    // packed NW align end-aligns the lanes of a duo: this lane's matrix row r is sweep row r + row_off
+    const int row_off = (NW && owner == OWN_DUO) ? nw_row_offset(meta, meta_other) : 0;
     const int duo = slot >> 1, lane_shift = (slot & 1) * 16;
     const int pair = b.pair_of[slot];  // raw bytes and results are indexed in the caller's pair order
 
@@ -99,7 +103,7 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
         if (reach > 0) {
             const uint32_t *bl = b.fboundary + duo;  // last true column (matrix column `cols`), shifted
             for (int r = rows - 2; r >= rows - 1 - reach && r >= 0; --r)
-                col_max = max(col_max, (int)(int16_t)(bl[(size_t)r * g.duos] >> lane_shift) + (r + 1) * gap_ref + cols * sc.gap_read);
+                col_max = max(col_max, (int)(int16_t)(bl[(size_t)(r + row_off) * g.duos] >> lane_shift) + (r + 1) * gap_ref + cols * sc.gap_read);
         }
         j = (pad_cols > 0 && col_max > best) ? (int)meta.max_ref_pos : min((int)meta.max_ref_pos, idx);
         b.end_cell[2 * pair] = (int16_t)i;
@@ -125,7 +129,7 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
                 k += kmin;
             }
             const size_t pair_step = (size_t)ng * g.duos, strip_step = (size_t)fast_row_pairs(g) * pair_step;
-            const uint4 *p = b.fdirs + (size_t)strip * strip_step + (size_t)(max(i, 0) >> 1) * pair_step + duo;
+            const uint4 *p = b.fdirs + (size_t)strip * strip_step + (size_t)((max(i, 0) + row_off) >> 1) * pair_step + duo;
             int have_pair = -1, have_strip = -1, have_grp = -1;
             uint4 w = make_uint4(0, 0, 0, 0);
             // SW: the packed fill stores the pointer a cell would have in NW; a cell whose value is 0 is
@@ -141,14 +145,15 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
                 else if (!NW && hval <= 0) code = DIR_START;
                 else {
                     const int grp = k >> 4;
-                    if ((i >> 1) != have_pair || strip != have_strip || grp != have_grp) {
+                    const int si = i + row_off;  // sweep row: where the fill kernel stored this matrix row
+                    if ((si >> 1) != have_pair || strip != have_strip || grp != have_grp) {
                         w = p[(size_t)grp * g.duos];  // two rows x 16 columns x both lanes
-                        have_pair = i >> 1;
+                        have_pair = si >> 1;
                         have_strip = strip;
                         have_grp = grp;
                     }
                     const int bit = lane_shift + (k & 15);
-                    const uint32_t diag_plane = (i & 1) ? w.z : w.x, up_plane = (i & 1) ? w.w : w.y;
+                    const uint32_t diag_plane = (si & 1) ? w.z : w.x, up_plane = (si & 1) ? w.w : w.y;
                     code = ((diag_plane >> bit) & 1) ? DIR_DIAG : (((up_plane >> bit) & 1) ? DIR_UP : DIR_LEFT);
                 }
                 if (code == DIR_START) break;
@@ -164,7 +169,7 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
                     }
                 }
                 if (code != DIR_LEFT) {
-                    if ((i & 1) == 0) p -= pair_step;  // leaving an even row: the row above is in the previous word
+                    if (((i + row_off) & 1) == 0) p -= pair_step;  // leaving an even sweep row: the row above is in the previous word
                     --i;
                 }
                 if (code != DIR_UP) {
