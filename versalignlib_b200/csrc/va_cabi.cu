@@ -215,7 +215,7 @@ struct PinBuf {
 
 // Device workspace of one chunk in flight.
 struct ChunkSlot {
-    DevBuf raw_reads, raw_refs, code_reads, code_refs, row_idx, solo_list, meta, pair_of, prep_scratch, boundary, dirs, queue, scores, end_cell, aln_read, aln_ref, start, moves;
+    DevBuf raw_reads, raw_refs, code_reads, code_refs, row_idx, solo_list, meta, pair_of, prep_scratch, boundary, dirs, hrow, queue, scores, end_cell, aln_read, aln_ref, start, moves;
     PinBuf h_reads, h_refs, h_scores, h_end_cell, h_aln_read, h_aln_ref, h_start, h_moves;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_done = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
@@ -225,7 +225,7 @@ struct ChunkSlot {
     bool busy = false;
 
     void release() {
-        DevBuf *d[] = {&raw_reads, &raw_refs, &code_reads, &code_refs, &row_idx, &solo_list, &meta, &pair_of, &prep_scratch, &boundary, &dirs, &queue, &scores, &end_cell, &aln_read, &aln_ref, &start, &moves};
+        DevBuf *d[] = {&raw_reads, &raw_refs, &code_reads, &code_refs, &row_idx, &solo_list, &meta, &pair_of, &prep_scratch, &boundary, &dirs, &hrow, &queue, &scores, &end_cell, &aln_read, &aln_ref, &start, &moves};
         for (auto *b : d) b->release();
         PinBuf *h[] = {&h_reads, &h_refs, &h_scores, &h_end_cell, &h_aln_read, &h_aln_ref, &h_start, &h_moves};
         for (auto *b : h) b->release();
@@ -298,7 +298,7 @@ struct Shape {
     size_t per_pair_workspace() const {
         size_t b = (size_t)(read_chunks + ref_chunks) * 32 + (size_t)read_chunks * 8 + 2 * sizeof(PairMeta) + 40 + (size_t)rows_alloc * 6;
         if (align) {
-            b += dir_row_bytes() * (rows_alloc + 1);
+            b += dir_row_bytes() * (rows_alloc + 1) + (size_t)ref_length * 2 + 8;
             const size_t qw = traceback_queue_words(read_length, ref_length);
             if (qw * 128 * 4 > 48 * 1024) b += qw * 4;
         }
@@ -372,6 +372,7 @@ int reserve_slot(ChunkSlot &s, const Shape &sh, int cap_pairs, bool pinned) {
     if ((rc = s.end_cell.reserve(slots * 4))) return rc;
     if (sh.align) {
         if ((rc = s.dirs.reserve(slots * sh.dir_row_bytes() * (sh.rows_alloc + 1) + 512))) return rc;
+        if ((rc = s.hrow.reserve(slots / 2 * (size_t)round_up((size_t)std::max(sh.ref_length, 1), 4) * 4 + 64))) return rc;
         // traceback move queue: shared memory unless the sequences are long
         const size_t qw = traceback_queue_words(sh.read_length, sh.ref_length);
         if (qw * 128 * 4 > 48 * 1024 && (rc = s.queue.reserve(slots * qw * 4 + 64))) return rc;
@@ -436,6 +437,7 @@ int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int
     b.code_reads = (uint4 *)ws.code_reads.p;
     b.code_refs = (uint4 *)ws.code_refs.p;
     b.row_idx = (uint4 *)ws.row_idx.p;
+    b.hrow = (uint32_t *)ws.hrow.p;
     b.solo_count = (int32_t *)ws.solo_list.p;
     b.solo_list = (int32_t *)ws.solo_list.p + 16;
     b.meta = (PairMeta *)ws.meta.p;

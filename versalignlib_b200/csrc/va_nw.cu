@@ -20,7 +20,7 @@
 // non-decreasing), so matrix row 0 is handed down to where that lane really starts, both lanes finish on
 // the last sweep row, and the end-cell rule reads both from the registers.
 // The matrix borders un-shift what they hand out: NW score's last row / last column maxima, the
-// arg-max of the last valid row and the last-true-column values the traceback kernel reads (va_traceback.cu).
+// `hrow` row and the last-true-column values the traceback kernel reads (va_traceback.cu).
 #include <algorithm>
 #include <type_traits>
 
@@ -38,11 +38,10 @@ namespace {
 // measured faster.
 template <bool ALIGN, int TW, bool SOLO>
 struct Block {
-    // align duo kernels: 4 x 128 threads.  TW 30 is compiled under a cap of 136 (ptxas then settles on a clean
-    // 128-register schedule; under a cap of 128 it does not), TW 32 under 128.  Everything else: 5 x 96.
-    static constexpr bool MAIN_ALIGN = ALIGN && !SOLO;
-    static constexpr int NT = MAIN_ALIGN ? 128 : 96;
-    static constexpr int MAXREG = (MAIN_ALIGN && TW == 32) ? 128 : 136;
+    // align duo kernels: 4 x 128 threads under a cap of 128 registers; everything else 5 x 96 under 136
+    static constexpr bool WIDE128 = ALIGN && !SOLO;
+    static constexpr int NT = WIDE128 ? 128 : 96;
+    static constexpr int MAXREG = WIDE128 ? 128 : 136;
 };
 constexpr uint32_t NEG2 = 0x80008000u;  // (-32768, -32768): identity of the packed max
 
@@ -74,7 +73,6 @@ __global__ void __maxnreg__((Block<ALIGN, TW, SOLO>::MAXREG)) fill_nw_kernel(Chu
     __shared__ uint2 s_T2[256];              // [7*code_a + code_b] -> the two lanes' 4-entry score tables (49 used)
     __shared__ uint4 s_idx[3][NT];           // staged row indices: 16 rows per thread and buffer
     __shared__ uint32_t s_bnd[3][16][NT];    // staged right edge of the previous strip, [row][thread]
-    __shared__ uint32_t s_park[2][NT];        // per-thread values that only live between the strips
     for (int t = threadIdx.x; t < 256; t += NT) s_T2[t] = t < 49 ? make_uint2(fc.tab[t / 7], fc.tab[t % 7]) : make_uint2(0u, 0u);
     __syncthreads();
 
@@ -93,11 +91,6 @@ __global__ void __maxnreg__((Block<ALIGN, TW, SOLO>::MAXREG)) fill_nw_kernel(Chu
         uint4 *dirs = b.fdirs;
 
         uint32_t best = 0;  // score mode: max(0, last column, last row) of H
-        // align: best of the last valid row so far (shifted by gap_ref*rows, per lane) and its column per lane.
-        // Parked in shared memory during the sweeps: the row loop runs at the register limit, and anything
-        // that merely lives across it costs the schedule dearly.
-        volatile uint32_t *park = &s_park[0][threadIdx.x];
-        if (ALIGN) park[0] = park[NT] = 0x0000FFFFu;  // matrix column 0: value 0 (= rows*gap_ref), reported as column 0
         const int nstrips = (n + TW - 1) / TW;
         for (int s = 0; s < nstrips; ++s) {
             const int c0 = s * TW;
@@ -258,23 +251,13 @@ __global__ void __maxnreg__((Block<ALIGN, TW, SOLO>::MAXREG)) fill_nw_kernel(Chu
                 cp_async_wait<0>();
             }
             // Pass-through columns hold the value of the column left of the strip, so they are handed out
-            // like that column (no per-column guards: a harmless repeat in the maximum).
+            // like that column (no per-column guards: an idempotent store / a harmless repeat in the maximum).
             if (ALIGN) {
-                // end-cell rule (DefaultKernel.cpp:352-355,381-387): first strictly greater column of the last
-                // valid row, column 0 (= rows*gap_ref) first.  Compared as V + gap_read*J, i.e. H - gap_ref*rows.
-                // Kept as one 32-bit key per lane, (value << 16) | (0xFFFF - column): the signed maximum is the
-                // larger value and, among equals, the smaller column -- no predicates.
-                int key_a = (int)park[0], key_b = (int)park[NT];
+                // the row the end-cell rule scans (DefaultKernel.cpp:352-355,381-387), still shifted: the traceback
+                // kernel finds its arg-max.  [column][duo]: coalesced across the warp.
+                uint32_t *hr = b.hrow + duo;
 #pragma unroll
-                for (int k = 0; k < TW; ++k) {
-                    const int col = max(c0 + k - pad, c0 - 1);  // 0-based ref column of register k
-                    const uint32_t cand = add2(H[k], pk(fc.gR * (col + 1)));
-                    const uint32_t low = 0xFFFFu - (uint32_t)max(col, 0);
-                    key_a = max(key_a, (int)((cand << 16) | low));
-                    key_b = max(key_b, (int)((cand & 0xFFFF0000u) | low));
-                }
-                park[0] = (uint32_t)key_a;
-                park[NT] = (uint32_t)key_b;
+                for (int k = 0; k < TW; ++k) store_lanes<SOLO>(hr + (size_t)max(c0 + k - pad, max(c0 - 1, 0)) * g.duos, H[k], fw);
             } else {  // whole last row (SSEKernel.cpp:1302-1310), un-shifted; column 0 is 0 and `best` starts at 0
 #pragma unroll
                 for (int k = 0; k < TW; ++k)
@@ -284,21 +267,6 @@ __global__ void __maxnreg__((Block<ALIGN, TW, SOLO>::MAXREG)) fill_nw_kernel(Chu
         if (!ALIGN) {
             if (!SOLO || fw.lane == 0) b.scores[b.pair_of[slot_a]] = (int16_t)(best & 0xFFFF);
             if (!SOLO || fw.lane == 1) b.scores[b.pair_of[slot_b]] = (int16_t)(best >> 16);
-        } else {
-            // the traceback kernel applies the pad-column / max_ref_pos clip to the column (va_traceback.cu)
-            const int key_a = (int)park[0], key_b = (int)park[NT];
-            if (!SOLO || fw.lane == 0) {
-                const int pa = b.pair_of[slot_a];
-                b.scores[pa] = (int16_t)((key_a >> 16) + fc.gF * (SOLO ? m : (int)fw.ma.rows));
-                b.end_cell[2 * pa] = (int16_t)((SOLO ? m : (int)fw.ma.rows) - 1);
-                b.end_cell[2 * pa + 1] = (int16_t)(0xFFFF - (key_a & 0xFFFF));
-            }
-            if (!SOLO || fw.lane == 1) {
-                const int pb = b.pair_of[slot_b];
-                b.scores[pb] = (int16_t)((key_b >> 16) + fc.gF * (SOLO ? m : (int)fw.mb.rows));
-                b.end_cell[2 * pb] = (int16_t)((SOLO ? m : (int)fw.mb.rows) - 1);
-                b.end_cell[2 * pb + 1] = (int16_t)(0xFFFF - (key_b & 0xFFFF));
-            }
         }
     };
     const int thread = blockIdx.x * blockDim.x + threadIdx.x;

@@ -9,8 +9,8 @@
 //         in shared memory (global memory when the sequences are too long for that);
 //   emit  one warp per pair, 32 moves per step: replay the queue, fetch the read/ref bytes it names
 //         and write both strings backwards -- consecutive lanes, consecutive bytes.
-// The packed NW fill kernel finds the arg-max of the last valid row (DefaultKernel.cpp:352-355,381-387);
-// the clip to max_ref_pos and the pad-column rule of a trimmed ref are applied here.
+// The packed NW fill kernel leaves the end-cell decision (arg-max of the last valid row,
+// DefaultKernel.cpp:352-355,381-387) to this kernel: `hrow` holds that row.
 #include <climits>
 
 #include "va_fast.cuh"
@@ -90,9 +90,27 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
     // ---- end cell ----------------------------------------------------------------------
     int i, j;
     if (packed && NW) {
-        // the fill kernel left the arg-max of the last valid row (first strictly greater column, column 0 =
-        // rows*gap_ref first) in scores / end_cell; the clip is applied here
-        const int best = b.scores[pair], idx = b.end_cell[2 * pair + 1];
+        // first strictly greater column of matrix row `rows`, starting from column 0 = rows*gap_ref.  hrow holds
+        // that row of both lanes in the fill kernel's shifted form V = H - gap_ref*I - gap_read*J (va_nw.cu),
+        // [column][duo]; eight independent loads per batch (more costs the walk its occupancy)
+        int best = rows * gap_ref, idx = 0;
+        const uint32_t *hr = b.hrow + duo;
+        const int base = rows * gap_ref;
+        for (int c0 = 0; c0 < cols; c0 += 8) {
+            uint32_t v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = c0 + q < cols ? hr[(size_t)(c0 + q) * g.duos] : 0u;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int c = c0 + q;
+                const int h = (int)(int16_t)(v[q] >> lane_shift) + base + (c + 1) * sc.gap_read;
+                if (c < cols && h > best) {
+                    best = h;
+                    idx = c;
+                }
+            }
+        }
+        b.scores[pair] = (int16_t)best;
         i = rows - 1;
         // Pad columns (past `cols`, never filled) take part in the arg-max of the reference.  With both
         // gaps <= 0 one of them beats the best true cell exactly when a value of the last true column in
