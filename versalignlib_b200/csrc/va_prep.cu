@@ -152,7 +152,8 @@ __global__ void __launch_bounds__(128) meta_kernel(ChunkGeom g, const uint8_t *_
 __global__ void __launch_bounds__(256) encode_kernel(ChunkGeom g, ChunkBuffers b, const PairMeta *__restrict__ meta_pair,
                                                      const uint4 *__restrict__ codes_pair_reads,
                                                      const uint4 *__restrict__ codes_pair_refs,
-                                                     const uint32_t *__restrict__ order, int mode) {
+                                                     const uint32_t *__restrict__ order,
+                                                     const uint32_t *__restrict__ sorted_keys, int mode) {
     const int per_slot = g.read_chunks + g.ref_chunks;
     const size_t total = (size_t)g.slots * per_slot;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
@@ -189,7 +190,8 @@ __global__ void __launch_bounds__(256) encode_kernel(ChunkGeom g, ChunkBuffers b
                 const bool has_b = slot + 1 < g.n;
                 const int pair_b = has_b ? (int)order[slot + 1] : 0;
                 if (has_b) cb = codes_pair_reads[(size_t)c * g.slots + pair_b];
-                if (mode == MODE_NW_ALIGN && has_b) {
+                // (equal sort keys = equal extents: nothing to shift, and no need to look at the meta records)
+                if (mode == MODE_NW_ALIGN && has_b && sorted_keys[slot] != sorted_keys[slot + 1]) {
                     // packed NW align end-aligns a duo's lanes: the lane with fewer rows starts late, behind
                     // CODE_PRE rows (va_internal.h); only duos the packed kernel takes are ever read back
                     // (slots that end up solo sweep from their own row 0: no shift for them)
@@ -272,7 +274,7 @@ int launch_prep(const ChunkGeom &g, const ChunkBuffers &b, int mode, int policy,
     cub::DeviceRadixSort::SortPairs(p, temp_bytes, keys_in, keys_out, vals_in, vals_out, g.n, 0, row_bits + 16, stream);
     if (g.solo) cudaMemsetAsync(b.solo_count, 0, sizeof(int32_t), stream);
     encode_kernel<<<enc_blocks, threads, 0, stream>>>(g, b, meta_pair, codes_reads, codes_refs,
-                                                      vals_out, mode);
+                                                      vals_out, keys_out, mode);
     return 2;  // our kernels; the sort is the library's
 }
 
