@@ -219,6 +219,9 @@ struct ChunkSlot {
     PinBuf h_reads, h_refs, h_scores, h_end_cell, h_aln_read, h_aln_ref, h_start, h_moves;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_done = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
+    // side stream of the fill phase: the leftover kernels (solo slots, general) run beside the duo kernel
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // what is currently in flight in this slot
     int64_t first = 0;
     int count = 0;
@@ -233,8 +236,11 @@ struct ChunkSlot {
         if (ev_k0) cudaEventDestroy(ev_k0);
         if (ev_k1) cudaEventDestroy(ev_k1);
         if (stream) cudaStreamDestroy(stream);
-        ev_done = ev_k0 = ev_k1 = nullptr;
-        stream = nullptr;
+        if (side) cudaStreamDestroy(side);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
+        ev_done = ev_k0 = ev_k1 = ev_fork = ev_join = nullptr;
+        stream = side = nullptr;
     }
 };
 
@@ -475,11 +481,22 @@ int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int
     g.solo = (g.fast_tw && !intra && !no_solo) ? 1 : 0;
     launches += launch_prep(g, b, mode, policy, sc, ws.prep_scratch.p, ws.prep_scratch.cap, stream);
     if (pe) cudaEventRecord(pe[1], stream);
+    // The packed duo kernel, the solo kernel and the general kernel own disjoint slots: the general kernel
+    // (usually with nothing to do) runs beside the packed ones on a side stream instead of after them.
+    if (!ws.side) {
+        cudaStreamCreateWithFlags(&ws.side, cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&ws.ev_fork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ws.ev_join, cudaEventDisableTiming);
+    }
+    cudaEventRecord(ws.ev_fork, stream);
+    cudaStreamWaitEvent(ws.side, ws.ev_fork, 0);
+    launches += launch_fill_general(g, b, mode, policy, sc, ws.side);
+    cudaEventRecord(ws.ev_join, ws.side);
     if (intra)
         launches += launch_fill_intra(g, b, mode, make_fast_consts(mode, sc), stream);
     else
         launches += launch_fill_fast(g, b, mode, sc, stream);
-    launches += launch_fill_general(g, b, mode, policy, sc, stream);
+    cudaStreamWaitEvent(stream, ws.ev_join, 0);
     if (pe) cudaEventRecord(pe[2], stream);
     if (sh.align) {
         if (zero_prefix && !moves_out) {  // bytes before start[i] are promised to be zero on this path
