@@ -462,7 +462,6 @@ FastConsts make_fast_consts(int mode, const Scoring &sc) {
         fc.swa_l0 = pk(sc.gap_read + B);   // matrix column 0 / zero floor, as "left"
         fc.swa_g0 = pk(sc.gap_ref + B);    // matrix row 0 / zero floor, as "H + gF"
         fc.swa_off = sc.gap_read + B;      // key>>5 minus this is the cell value
-        fc.swa_key0 = pk(((sc.gap_read + B) << 5) | 31);
         fc.swa_k32 = 32;
     }
     return fc;

@@ -59,10 +59,10 @@ struct ChunkGeom {
 struct FastConsts {
     uint32_t tab[8];   // tab[read_code]: four 8-bit substitution scores vs ref A,C,G,T (NW align: minus gap_ref)
     uint32_t gF2, gR2; // gap scores replicated in both 16-bit lanes
-    uint32_t dFR2;     // NW align: gap_ref - gap_read ; score modes: -gap_read   (boundary -> diagonal conversion)
+    uint32_t dFR2;     // SW: boundary ("left + gR") -> diagonal conversion: gap_ref - gap_read (align), -gap_read (score)
     int gF, gR;
     // SW align only (see va_fast.cu): biased initial values and key constants
-    uint32_t swa_l0, swa_g0, swa_key0, swa_k32;
+    uint32_t swa_l0, swa_g0, swa_k32;
     int swa_off;
 };
 
