@@ -473,11 +473,12 @@ int launch_fill_fast(const ChunkGeom &g, const ChunkBuffers &b, int mode, const 
     switch (mode) {
         case MODE_SW_SCORE: launch_tw<MODE_SW_SCORE>(g, b, fc, stream); break;
         case MODE_NW_SCORE:
-        case MODE_NW_ALIGN: launch_fill_nw(g, b, mode, fc, stream); break;
+        case MODE_NW_ALIGN: return launch_fill_nw(g, b, mode, fc, stream);
         case MODE_SW_ALIGN: launch_tw<MODE_SW_ALIGN>(g, b, fc, stream); break;
         default: return 0;
     }
-    return 1;
+    // kernels launched: the duo kernel (batches of two pairs and more) and the solo kernel
+    return (g.n >= 2 ? 1 : 0) + (g.solo ? 1 : 0);
 }
 
 }  // namespace va

@@ -309,7 +309,7 @@ int launch_fill_nw(const ChunkGeom &g, const ChunkBuffers &b, int mode, const Fa
         if (align) launch_one<true, 32>(g, b, fc, stream);
         else launch_one<false, 32>(g, b, fc, stream);
     }
-    return 1;
+    return (g.n >= 2 ? 1 : 0) + (g.solo ? 1 : 0);
 }
 
 }  // namespace va
