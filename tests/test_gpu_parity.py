@@ -349,3 +349,23 @@ def test_nw_align_end_aligned_duos(ctx):
             oa, ob, ostart, oend = ora.align(ora.NW, 0, reads, f, sc)
             assert np.array_equal(start, ostart) and np.array_equal(end, oend), sc
             assert used_region_equal(a, b, start, oa, ob, ostart).size == 0, sc
+
+
+def test_c2_workload_sample_at_scale(ctx):
+    """The bench workload (C2: NW compute_alignments, 150 x 150) at a size that runs several chunks through the
+    host pipeline: a random sample of pairs must carry exactly the oracle's alignments, and the flat and the
+    packed/CIGAR results must describe the same paths."""
+    n = 300_000
+    reads, refs = synth.uniform_batch(n, 150, 150, p_sub=0.08, q_indel=0.02, seed=synth.BASE_SEED + 2)
+    a, b, start, end = ctx.align_flat(ora.NW, 0, reads, refs)
+    idx = np.sort(np.random.default_rng(1).choice(n, 4000, replace=False))
+    oa, ob, ostart, oend = ora.align(ora.NW, 0, np.ascontiguousarray(reads[idx]), np.ascontiguousarray(refs[idx]))
+    assert np.array_equal(start[idx], ostart) and np.array_equal(end[idx], oend)
+    assert used_region_equal(a[idx], b[idx], start[idx], oa, ob, ostart).size == 0
+    pr, ro = synth.pack_batch(reads)
+    pf, fo = synth.pack_batch(refs)
+    scores, coords, coff, cigar = ctx.align_packed(ora.NW, 0, pr, ro, pf, fo)
+    L = a.shape[1]
+    moves = np.add.reduceat((cigar >> 4).astype(np.int64), coff[:-1]) if cigar.size else np.zeros(n, np.int64)
+    assert np.array_equal(moves, L - 1 - start.astype(np.int64))
+    assert np.array_equal(coords[:, 1], end[:, 0].astype(np.int32) + 1) and np.array_equal(coords[:, 3], end[:, 1].astype(np.int32) + 1)
