@@ -70,21 +70,35 @@ __device__ __forceinline__ SeqScan scan_sequence(const uint8_t *__restrict__ raw
                 }
             }
             uint32_t o = 0;
+            if (wi * 4 + 4 <= L) {
+                // whole word inside the sequence: four look-ups, then the statistics from bit masks
+                // (codes 0..3 = ACGT have bit 2 clear; N = 4; OTHER = 5 has bits 2 and 0)
+                o = (uint32_t)lut[v & 0xFF] | ((uint32_t)lut[(v >> 8) & 0xFF] << 8) | ((uint32_t)lut[(v >> 16) & 0xFF] << 16) |
+                    ((uint32_t)lut[v >> 24] << 24);
+                const uint32_t non = (o >> 2) & 0x01010101u;  // bit 0 of byte t: base t is not ACGT
+                const uint32_t oth = non & o;                 // ... is neither ACGT nor N
+                const uint32_t acgt = non ^ 0x01010101u;
+                s.n_acgt += __popc(acgt);
+                if (acgt) s.last_acgt = wi * 4 + ((31 - __clz(acgt)) >> 3);
+                if (non && s.first_nonacgt == L) s.first_nonacgt = wi * 4 + ((__ffs(non) - 1) >> 3);
+                if (oth && s.first_other == L) s.first_other = wi * 4 + ((__ffs(oth) - 1) >> 3);
+            } else {
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int pos = wi * 4 + t;
-                int code = CODE_OTHER;
-                if (pos < L) {
-                    code = lut[(v >> (8 * t)) & 0xFF];
-                    if (code < 4) {
-                        s.last_acgt = pos;
-                        s.n_acgt++;
-                    } else {
-                        s.first_nonacgt = min(s.first_nonacgt, pos);
-                        if (code == CODE_OTHER) s.first_other = min(s.first_other, pos);
+                for (int t = 0; t < 4; ++t) {
+                    const int pos = wi * 4 + t;
+                    int code = CODE_OTHER;
+                    if (pos < L) {
+                        code = lut[(v >> (8 * t)) & 0xFF];
+                        if (code < 4) {
+                            s.last_acgt = pos;
+                            s.n_acgt++;
+                        } else {
+                            s.first_nonacgt = min(s.first_nonacgt, pos);
+                            if (code == CODE_OTHER) s.first_other = min(s.first_other, pos);
+                        }
                     }
+                    o |= (uint32_t)code << (8 * t);
                 }
-                o |= (uint32_t)code << (8 * t);
             }
             out[q] = o;
         }
