@@ -83,7 +83,7 @@ struct ChunkBuffers {
                                // (separate regions: one chunk can hold pairs of both kinds)
     int32_t *solo_list;        // [slots] slots the packed kernels take on their own (va_fast.cuh), written by the prep
     int32_t *solo_count;       // kernel in no particular order; *solo_count entries
-    uint32_t *hrow;            // packed NW align: [ref_length][duos] last valid matrix row of both lanes, shifted form
+    uint32_t *hrow;            // packed NW align: [strip][duo][2] arg-max key of the last valid matrix row per strip and lane
     int16_t *scores;           // [n]
     int16_t *end_cell;         // [n][2]
     // traceback outputs

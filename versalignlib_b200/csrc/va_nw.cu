@@ -255,9 +255,22 @@ __global__ void __maxnreg__((Block<ALIGN, TW, SOLO>::MAXREG)) fill_nw_kernel(Chu
             if (ALIGN) {
                 // the row the end-cell rule scans (DefaultKernel.cpp:352-355,381-387), still shifted: the traceback
                 // kernel finds its arg-max.  [column][duo]: coalesced across the warp.
-                uint32_t *hr = b.hrow + duo;
+                // per strip: best of its columns as one 32-bit key per lane, (value << 16) | (0xFFFF - column), value =
+                // V + gap_read*J (= H - gap_ref*rows): the signed maximum is the larger value and, among equals, the
+                // smaller column.  No predicates, nothing carried between strips: the traceback kernel reduces the
+                // (at most a few dozen) strip keys of a pair.
+                int key_a = (int)0x80000000, key_b = (int)0x80000000;
 #pragma unroll
-                for (int k = 0; k < TW; ++k) store_lanes<SOLO>(hr + (size_t)max(c0 + k - pad, max(c0 - 1, 0)) * g.duos, H[k], fw);
+                for (int k = 0; k < TW; ++k) {
+                    const int col = max(c0 + k - pad, max(c0 - 1, 0));  // 0-based ref column of register k
+                    const uint32_t cand = add2(H[k], pk(fc.gR * (col + 1)));
+                    const uint32_t low = 0xFFFFu - (uint32_t)col;
+                    key_a = max(key_a, (int)((cand << 16) | low));
+                    key_b = max(key_b, (int)((cand & 0xFFFF0000u) | low));
+                }
+                uint32_t *hk = b.hrow + ((size_t)s * g.duos + duo) * 2;
+                if (!SOLO || fw.lane == 0) hk[0] = (uint32_t)key_a;
+                if (!SOLO || fw.lane == 1) hk[1] = (uint32_t)key_b;
             } else {  // whole last row (SSEKernel.cpp:1302-1310), un-shifted; column 0 is 0 and `best` starts at 0
 #pragma unroll
                 for (int k = 0; k < TW; ++k)

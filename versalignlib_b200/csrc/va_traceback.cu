@@ -90,26 +90,17 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
     // ---- end cell ----------------------------------------------------------------------
     int i, j;
     if (packed && NW) {
-        // first strictly greater column of matrix row `rows`, starting from column 0 = rows*gap_ref.  hrow holds
-        // that row of both lanes in the fill kernel's shifted form V = H - gap_ref*I - gap_read*J (va_nw.cu),
-        // [column][duo]; eight independent loads per batch (more costs the walk its occupancy)
-        int best = rows * gap_ref, idx = 0;
-        const uint32_t *hr = b.hrow + duo;
-        const int base = rows * gap_ref;
-        for (int c0 = 0; c0 < cols; c0 += 8) {
-            uint32_t v[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = c0 + q < cols ? hr[(size_t)(c0 + q) * g.duos] : 0u;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int c = c0 + q;
-                const int h = (int)(int16_t)(v[q] >> lane_shift) + base + (c + 1) * sc.gap_read;
-                if (c < cols && h > best) {
-                    best = h;
-                    idx = c;
-                }
-            }
+        // First strictly greater column of matrix row `rows`, starting from column 0 = rows*gap_ref.  The fill
+        // kernel left, per strip, the best of its columns as one key per lane: (value << 16) | (0xFFFF - column)
+        // with value = H - gap_ref*rows, so the signed maximum over the strips (and over column 0's own key) is
+        // the greatest value and, among equals, the smallest column (va_nw.cu).
+        int key = 0x0000FFFF;  // matrix column 0: value 0, reported as column 0
+        {
+            const int nstrips = (cols + g.fast_tw - 1) / g.fast_tw;
+            const uint32_t *hk = b.hrow + (size_t)duo * 2 + (slot & 1);
+            for (int st = 0; st < nstrips; ++st) key = max(key, (int)hk[(size_t)st * g.duos * 2]);
         }
+        const int best = (key >> 16) + rows * gap_ref, idx = 0xFFFF - (key & 0xFFFF);
         b.scores[pair] = (int16_t)best;
         i = rows - 1;
         // Pad columns (past `cols`, never filled) take part in the arg-max of the reference.  With both
