@@ -322,7 +322,9 @@ __global__ void __maxnreg__((FastBlock<MODE, TW, SYM, SOLO>::MAXREG)) fill_fast_
     };
     const int thread = blockIdx.x * blockDim.x + threadIdx.x;
     if constexpr (!SOLO) {  // thread t takes duo t
-        const FastWork fw = fast_work_duo(g, b.meta, MODE, thread);
+        // slots are sorted by ascending extents: blocks are taken from the far end so the longest pairs start
+        // first and the last wave is made of the short ones
+        const FastWork fw = fast_work_duo(g, b.meta, MODE, (int)(gridDim.x - 1 - blockIdx.x) * (int)blockDim.x + (int)threadIdx.x);
         if (fw.own == OWN_DUO) run(fw);
     } else {  // grid-stride loop over the slots the prep kernel listed
         const int count = *b.solo_count;
