@@ -168,11 +168,10 @@ __global__ void __launch_bounds__(256) encode_kernel(ChunkGeom g, ChunkBuffers b
                                                      const uint4 *__restrict__ codes_pair_refs,
                                                      const uint32_t *__restrict__ order,
                                                      const uint32_t *__restrict__ sorted_keys, int mode) {
-    const int per_slot = g.read_chunks + g.ref_chunks;
-    const size_t total = (size_t)g.slots * per_slot;
-    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-        // consecutive threads = consecutive slots of the same chunk: coalesced 16-byte stores
-        const int c = (int)(t / g.slots), slot = (int)(t - (size_t)c * g.slots);
+    // grid: x over the slots, y over the 16-base chunks (reads first, then refs) -- consecutive threads =
+    // consecutive slots of the same chunk: coalesced 16-byte stores, no index division
+    const int c = blockIdx.y;
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < g.slots; slot += gridDim.x * blockDim.x) {
         if (slot >= g.n) {  // padding slots: only their meta is ever looked at (as a duo partner)
             if (c == 0) {
                 PairMeta z{};
@@ -228,7 +227,9 @@ __global__ void __launch_bounds__(256) encode_kernel(ChunkGeom g, ChunkBuffers b
                 }
                 b.row_idx[(size_t)c * g.duos + (slot >> 1)] = make_uint4(cx.x * 7u + cb.x, cx.y * 7u + cb.y, cx.z * 7u + cb.z, cx.w * 7u + cb.w);
             }
-        } else b.code_refs[(size_t)(c - g.read_chunks) * g.slots + slot] = codes_pair_refs[(size_t)(c - g.read_chunks) * g.slots + pair];
+        } else if (c - g.read_chunks < g.ref_chunks) {
+            b.code_refs[(size_t)(c - g.read_chunks) * g.slots + slot] = codes_pair_refs[(size_t)(c - g.read_chunks) * g.slots + pair];
+        }
     }
 }
 
@@ -280,8 +281,7 @@ int launch_prep(const ChunkGeom &g, const ChunkBuffers &b, int mode, int policy,
     const int threads = 256;
     const int grid_cap = 148 * 8;
     const int meta_blocks = (g.n + 127) / 128;
-    const size_t enc_items = (size_t)g.slots * (g.read_chunks + g.ref_chunks);
-    const int enc_blocks = (int)std::min<size_t>((enc_items + threads - 1) / threads, grid_cap * 4);
+    const dim3 enc_blocks((unsigned)std::min((g.slots + threads - 1) / threads, grid_cap * 4), (unsigned)std::max(1, g.read_chunks + g.ref_chunks));  // y >= 1: chunk 0 also moves the meta records
     meta_kernel<<<meta_blocks, 128, 0, stream>>>(g, b.raw_reads, b.raw_refs, meta_pair, codes_reads, codes_refs, keys_in,
                                                      vals_in, mode, policy, trim, row_bits);
     // only the bits that can differ are sorted: rows, cols and the "dirty" flag above them
