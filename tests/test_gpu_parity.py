@@ -369,3 +369,15 @@ def test_c2_workload_sample_at_scale(ctx):
     moves = np.add.reduceat((cigar >> 4).astype(np.int64), coff[:-1]) if cigar.size else np.zeros(n, np.int64)
     assert np.array_equal(moves, L - 1 - start.astype(np.int64))
     assert np.array_equal(coords[:, 1], end[:, 0].astype(np.int32) + 1) and np.array_equal(coords[:, 3], end[:, 1].astype(np.int32) + 1)
+
+
+@pytest.mark.parametrize("rl,fl", [(700, 700), (735, 740), (745, 745), (760, 775)])
+def test_traceback_queue_shared_to_global_boundary(ctx, rl, fl):
+    """Around read+ref = 1.5 k the traceback's move queues stop fitting into shared memory next to the
+    kernel's static arrays and move to global memory (regression: the switch ignored the static part)."""
+    reads, refs = synth.uniform_batch(70, rl, fl, p_sub=0.1, q_indel=0.02, seed=rl)
+    for opt in (ora.SW, ora.NW):
+        a, b, start, end = ctx.align_flat(opt, 0, reads, refs)
+        oa, ob, ostart, oend = ora.align(opt, 0, reads, refs)
+        assert np.array_equal(start, ostart) and np.array_equal(end, oend), opt
+        assert used_region_equal(a, b, start, oa, ob, ostart).size == 0, opt

@@ -306,7 +306,7 @@ struct Shape {
         if (align) {
             b += dir_row_bytes() * (rows_alloc + 1) + (size_t)ref_length * 2 + 8;
             const size_t qw = traceback_queue_words(read_length, ref_length);
-            if (qw * 128 * 4 > 48 * 1024) b += qw * 4;
+            if (traceback_needs_global_queue(read_length, ref_length)) b += qw * 4;
         }
         return b;
     }
@@ -381,7 +381,7 @@ int reserve_slot(ChunkSlot &s, const Shape &sh, int cap_pairs, bool pinned) {
         if ((rc = s.hrow.reserve(slots / 2 * (size_t)round_up((size_t)std::max(sh.ref_length, 1), 4) * 4 + 64))) return rc;
         // traceback move queue: shared memory unless the sequences are long
         const size_t qw = traceback_queue_words(sh.read_length, sh.ref_length);
-        if (qw * 128 * 4 > 48 * 1024 && (rc = s.queue.reserve(slots * qw * 4 + 64))) return rc;
+        if (traceback_needs_global_queue(sh.read_length, sh.ref_length) && (rc = s.queue.reserve(slots * qw * 4 + 64))) return rc;
         if (pinned) {
             if (sh.moves) {
                 if ((rc = s.moves.reserve((size_t)cap_pairs * (sh.queue_words() + 1) * 4 + 16))) return rc;

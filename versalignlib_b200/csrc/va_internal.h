@@ -115,6 +115,7 @@ int launch_fill_nw(const ChunkGeom &g, const ChunkBuffers &b, int mode, const Fa
 bool intra_preferred(int mode, int n_pairs, int read_length, int ref_length, int sm_count);
 int launch_fill_intra(const ChunkGeom &g, const ChunkBuffers &b, int mode, const FastConsts &fc, cudaStream_t stream);
 size_t traceback_queue_words(int read_length, int ref_length);
+bool traceback_needs_global_queue(int read_length, int ref_length);
 int launch_traceback(const ChunkGeom &g, const ChunkBuffers &b, int mode, const Scoring &sc, uint32_t *global_queue,
                      cudaStream_t stream);
 int launch_int_peak(int kind, int sm_count, int iters, unsigned int *sink, cudaStream_t stream, double *lane_ops);

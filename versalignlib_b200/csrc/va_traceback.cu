@@ -318,9 +318,13 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
 
 }  // namespace
 
-// Shared-memory move queue while it fits (<= 48 KB per block), else `global_queue`
-// (slots * queue_words words, provided by the caller).
 size_t traceback_queue_words(int read_length, int ref_length) { return (size_t)(read_length + ref_length + 15) / 16 + 1; }
+
+// The per-thread move queues live in dynamic shared memory while they fit beside the kernel's static arrays
+// (48 KB per block without opt-in); beyond that the caller provides slots * queue_words words of global memory.
+bool traceback_needs_global_queue(int read_length, int ref_length) {
+    return traceback_queue_words(read_length, ref_length) * TB_THREADS * sizeof(uint32_t) + 4 * TB_THREADS * sizeof(int) > 48 * 1024;
+}
 
 int launch_traceback(const ChunkGeom &g, const ChunkBuffers &b, int mode, const Scoring &sc, uint32_t *global_queue,
                      cudaStream_t stream) {
@@ -328,7 +332,7 @@ int launch_traceback(const ChunkGeom &g, const ChunkBuffers &b, int mode, const 
     const int blocks = (g.n + TB_THREADS - 1) / TB_THREADS;
     const int qw = (int)traceback_queue_words(g.read_length, g.ref_length);
     const size_t smem = (size_t)qw * TB_THREADS * sizeof(uint32_t);
-    const bool use_shared = smem <= 48 * 1024 && !b.moves_out;
+    const bool use_shared = !traceback_needs_global_queue(g.read_length, g.ref_length) && !b.moves_out;
     uint32_t *gq = use_shared ? nullptr : global_queue;
     if (mode == MODE_NW_ALIGN) traceback_kernel<true><<<blocks, TB_THREADS, use_shared ? smem : 0, stream>>>(g, b, sc, gq, qw);
     else traceback_kernel<false><<<blocks, TB_THREADS, use_shared ? smem : 0, stream>>>(g, b, sc, gq, qw);
