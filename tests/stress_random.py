@@ -55,6 +55,25 @@ def main():
                 oa, ob, ostart, oend = ora.align(opt, policy, reads, refs, sc)
                 if not (np.array_equal(start, ostart) and np.array_equal(end, oend) and used_region_equal(a, b, start, oa, ob, ostart).size == 0):
                     failures.append(("align", opt, policy) + tag)
+            # the packed / CIGAR entry points on the same batch (sequences trimmed of their '\0' padding; the
+            # semantics are the reference's on the batch padded to ITS maximum lengths)
+            # (not the dirty decks: their junk alphabet contains '-', which the string -> CIGAR derivation of the
+            # expected result cannot tell from a gap)
+            if kind != "dirty" and reads.shape[0] <= 2000 and rng.random() < 0.5:
+                pr, ro = synth.pack_batch(reads)
+                pf, fo = synth.pack_batch(refs)
+                tr = np.ascontiguousarray(reads[:, :max(int(np.diff(ro).max()), 1)])
+                tf = np.ascontiguousarray(refs[:, :max(int(np.diff(fo).max()), 1)])
+                # interior '\0' bytes would change the trimmed lengths' meaning: only clean tails
+                if (np.diff(ro) == (tr != 0).sum(axis=1)).all() and (np.diff(fo) == (tf != 0).sum(axis=1)).all() and np.diff(ro).min() > 0 and np.diff(fo).min() > 0:
+                    for opt in (ora.SW, ora.NW):
+                        if not np.array_equal(ctx.score_packed(opt, pr, ro, pf, fo, sc), ora.score(opt, tr, tf, sc)):
+                            failures.append(("score_packed", opt) + tag)
+                        policy = int(rng.integers(2))
+                        scores, coords, coff, cigar = ctx.align_packed(opt, policy, pr, ro, pf, fo, sc)
+                        want = synth.cigar_from_strings(*ora.align(opt, policy, tr, tf, sc))
+                        if not (np.array_equal(coords, want[0]) and np.array_equal(coff, want[1]) and np.array_equal(cigar, want[2])):
+                            failures.append(("align_packed", opt, policy) + tag)
             cases += 1
             if failures:
                 break
