@@ -15,15 +15,18 @@ from versalignlib_b200 import capi, synth  # noqa: E402
 
 
 def random_case(rng):
-    kind = rng.choice(["uniform", "mixed", "mixed_reads", "dirty", "long"], p=[0.3, 0.3, 0.15, 0.15, 0.1])
-    if kind == "long":
-        n = int(rng.integers(1, 12))
-        rl, fl = int(rng.integers(300, 1500)), int(rng.integers(300, 1800))
+    kind = rng.choice(["uniform", "mixed", "mixed_reads", "dirty", "long", "many"], p=[0.28, 0.28, 0.14, 0.14, 0.12, 0.04])
+    if kind == "long":  # intra-task kernels, global traceback queues
+        n = int(rng.integers(1, 24))
+        rl, fl = int(rng.integers(300, 2600)), int(rng.integers(300, 3200))
+    elif kind == "many":  # several chunks through the host pipeline
+        n = int(rng.integers(70_000, 150_000))
+        rl, fl = int(rng.integers(8, 48)), int(rng.integers(8, 48))
     else:
         n = int(rng.choice([1, 2, 3, 31, 64, 65, 127, 500, 2000, 9000]))
         rl, fl = int(rng.integers(1, 260)), int(rng.integers(1, 260))
     seed = int(rng.integers(1 << 30))
-    if kind in ("uniform", "long"):
+    if kind in ("uniform", "long", "many"):
         reads, refs = synth.uniform_batch(n, rl, fl, p_sub=float(rng.choice([0.05, 0.3, 0.75])), q_indel=float(rng.choice([0, 0.03])), seed=seed)
     else:
         lo = max(1, min(rl, fl) // 3)
