@@ -381,3 +381,54 @@ def test_traceback_queue_shared_to_global_boundary(ctx, rl, fl):
         oa, ob, ostart, oend = ora.align(opt, 0, reads, refs)
         assert np.array_equal(start, ostart) and np.array_equal(end, oend), opt
         assert used_region_equal(a, b, start, oa, ob, ostart).size == 0, opt
+
+
+def test_align_alloc_allocator_boundary(ctx):
+    """va_cuda_align_alloc: result blocks come from the caller's allocator on the staging threads; same
+    alignments as the oracle; an allocator that runs dry fails the call with VA_ERR_MEMORY."""
+    _, reads, refs = BATCHES[1]
+    for opt in (ora.SW, ora.NW):
+        a, b, start, end = ctx.align_alloc(opt, 0, reads, refs)
+        oa, ob, ostart, oend = ora.align(opt, 0, reads, refs)
+        assert np.array_equal(start, ostart) and np.array_equal(end, oend), opt
+        assert used_region_equal(a, b, start, oa, ob, ostart).size == 0, opt
+    with pytest.raises(capi.CudaError, match="allocator"):
+        ctx.align_alloc(ora.NW, 0, reads, refs, fail_after=100)
+    # the context stays usable after the failed call
+    assert np.array_equal(ctx.score_flat(ora.SW, reads, refs), ora.score(ora.SW, reads, refs))
+
+
+def test_mismatch_score_above_match(ctx):
+    """A 'mismatch' score above the match score makes cells grow by the mismatch score: the packed kernels'
+    16-bit range checks must use the larger of the two (else the general kernel takes the call)."""
+    r, f = synth.uniform_batch(300, 250, 250, independent=True, seed=91)
+    for sc in [(1, 4, -3, -3), (2, 5, -1, -2), (1, 120, -3, -3)]:
+        for opt in (ora.SW, ora.NW):
+            assert np.array_equal(ctx.score_flat(opt, r, f, sc), ora.score(opt, r, f, sc)), (sc, opt)
+            a, b, start, end = ctx.align_flat(opt, 0, r, f, sc)
+            oa, ob, ostart, oend = ora.align(opt, 0, r, f, sc)
+            assert np.array_equal(start, ostart) and np.array_equal(end, oend), (sc, opt)
+            assert used_region_equal(a, b, start, oa, ob, ostart).size == 0, (sc, opt)
+
+
+def test_packed_inputs_in_pinned_memory(ctx):
+    """Offset-addressed inputs in page-locked memory are read in place by the copy engines (no staging copy):
+    same results as from pageable memory, on a batch big enough for several chunks and both devices' paths."""
+    import torch
+    reads, refs, _, _ = synth.mixed_batch(150_000, 60, 150, p_sub=0.08, q_indel=0.02, seed=77)
+    pr, ro = synth.pack_batch(reads)
+    pf, fo = synth.pack_batch(refs)
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+    want = ctx.align_packed(ora.NW, 0, pr, ro, pf, fo)
+    got = ctx.align_packed(ora.NW, 0, pin(pr), pin(ro), pin(pf), pin(fo))
+    for w, g in zip(want, got):
+        assert np.array_equal(w, g)
+    assert np.array_equal(ctx.score_packed(ora.SW, pin(pr), pin(ro), pin(pf), pin(fo)), ctx.score_packed(ora.SW, pr, ro, pf, fo))
+    # against the oracle on a sample
+    idx = np.arange(0, reads.shape[0], 37)
+    oa, ob, ostart, oend = ora.align(ora.NW, 0, np.ascontiguousarray(reads[idx]), np.ascontiguousarray(refs[idx]))
+    wc, woff, wcig = synth.cigar_from_strings(oa, ob, ostart, oend)
+    scores, coords, coff, cigar = got
+    assert np.array_equal(coords[idx], wc)
+    for k, i in enumerate(idx[:500]):
+        assert np.array_equal(cigar[coff[i]:coff[i + 1]], wcig[woff[k]:woff[k + 1]]), i

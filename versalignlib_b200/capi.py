@@ -76,6 +76,8 @@ def lib():
         sp = ctypes.POINTER(Scoring)
         L.va_cuda_score_ptrs.argtypes = [vp, ci, sp, ci, vp, ci, vp, ci, vp]
         L.va_cuda_align_ptrs.argtypes = [vp, ci, ci, sp, ci, vp, ci, vp, ci, vp, vp, vp, vp]
+        L.va_cuda_align_alloc.argtypes = [vp, ci, ci, sp, ci, vp, ci, vp, ci, _ALLOC_FN, vp, vp, vp, vp, vp]
+        L.va_cuda_align_records.argtypes = [vp, ci, ci, sp, ci, vp, ci, vp, ci, _ALLOC_FN, vp, vp, ctypes.c_size_t, vp]
         L.va_cuda_score_flat.argtypes = [vp, ci, sp, ci, vp, ci, vp, ci, vp]
         L.va_cuda_align_flat.argtypes = [vp, ci, ci, sp, ci, vp, ci, vp, ci, vp, vp, vp, vp]
         L.va_cuda_score_packed.argtypes = [vp, ci, sp, ci, vp, vp, vp, vp, vp]
@@ -232,6 +234,38 @@ class CudaContext:
         self._check(self._L.va_cuda_align_ptrs(self._h, opt, policy, ctypes.byref(sc), n, rp.ctypes.data, reads.shape[1],
                                                fp.ctypes.data, refs.shape[1], ap.ctypes.data, bp.ctypes.data,
                                                start.ctypes.data, end.ctypes.data), "va_cuda_align_ptrs")
+        return a, b, start, end
+
+    def align_alloc(self, opt: int, policy: int, reads: np.ndarray, refs: np.ndarray, scoring=(2, -1, -3, -3),
+                    fail_after: int | None = None):
+        """va_cuda_align_alloc with a Python allocator (blocks are numpy arrays kept alive here).  Returns
+        (aln_read[n,L], aln_ref[n,L], start[n], end_cell[n,2]) assembled from the blocks; fail_after = k makes
+        the allocator return NULL from its k-th call on (the call must then fail with VA_ERR_MEMORY)."""
+        import threading
+        reads, refs = _u8(reads), _u8(refs)
+        n, L = reads.shape[0], reads.shape[1] + refs.shape[1]
+        blocks, lock, calls = {}, threading.Lock(), [0]
+
+        def _alloc(nbytes, _user):
+            with lock:
+                calls[0] += 1
+                if fail_after is not None and calls[0] > fail_after:
+                    return None
+                buf = np.zeros(max(int(nbytes), 1), dtype=np.uint8)
+                blocks[buf.ctypes.data] = buf
+                return buf.ctypes.data
+
+        cb = _ALLOC_FN(_alloc)
+        pa, pb = np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint64)
+        start = np.zeros(n, dtype=np.int16)
+        end = np.zeros((n, 2), dtype=np.int16)
+        rp, fp = _row_pointers(reads), _row_pointers(refs)
+        sc = Scoring(*scoring)
+        self._check(self._L.va_cuda_align_alloc(self._h, opt, policy, ctypes.byref(sc), n, rp.ctypes.data, reads.shape[1],
+                                                fp.ctypes.data, refs.shape[1], cb, None, pa.ctypes.data, pb.ctypes.data,
+                                                start.ctypes.data, end.ctypes.data), "va_cuda_align_alloc")
+        a = np.stack([blocks[int(x)][:L] for x in pa]) if n else np.zeros((0, L), np.uint8)
+        b = np.stack([blocks[int(x)][:L] for x in pb]) if n else np.zeros((0, L), np.uint8)
         return a, b, start, end
 
     # ---- batch-friendly: offset-addressed sequences, CIGAR out -------------------------

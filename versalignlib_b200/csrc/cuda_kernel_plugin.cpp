@@ -11,6 +11,7 @@
 //
 // All device work goes through the flat C ABI (versalign_cuda.h); there is no CPU path.
 #include <cstddef>
+#include <malloc.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -55,34 +56,52 @@ void log_info(const std::string &msg) {
 // The library is never dlclose()d by the reference driver (main.cpp:217-225 re-dlopens to find
 // delete_alignment_kernel), and it spawns a fresh kernel per timing run (main.cpp:261-265), so
 // the CUDA context (streams, pinned staging, device workspace) is shared by all instances.
+// One context per (cuda_devices, cuda_device_first) combination, created on first use and kept for
+// the life of the process: instances spawned earlier with another combination keep a valid ctx_.
 struct SharedContext {
     std::mutex mu;
-    va_cuda_ctx *ctx = nullptr;
-    int n_devices = -1;
-    int first = 0;
+    struct Entry {
+        int n_devices, first;
+        va_cuda_ctx *ctx;
+    };
+    std::vector<Entry> entries;
+    va_cuda_ctx *last = nullptr;  // context of the most recent call (va_cuda_plugin_timings)
 };
 SharedContext g_shared;
 
 va_cuda_ctx *acquire_context(int n_devices, int first) {
     std::lock_guard<std::mutex> lk(g_shared.mu);
-    if (g_shared.ctx && g_shared.n_devices == n_devices && g_shared.first == first) return g_shared.ctx;
-    if (g_shared.ctx) {
-        va_cuda_destroy(g_shared.ctx);
-        g_shared.ctx = nullptr;
-    }
+    for (const auto &e : g_shared.entries)
+        if (e.n_devices == n_devices && e.first == first) return g_shared.last = e.ctx;
     int visible = 0;
     if (va_cuda_device_count(&visible) != VA_OK) fatal(std::string("Cannot instantiate Kernel. ") + va_cuda_last_error());
     std::vector<int> devs;
-    if (first < 0 || first >= visible) first = 0;
-    const int use = (n_devices <= 0 || first + n_devices > visible) ? visible - first : n_devices;
-    for (int d = 0; d < use; ++d) devs.push_back(first + d);
+    int f = first;
+    if (f < 0 || f >= visible) f = 0;
+    const int use = (n_devices <= 0 || f + n_devices > visible) ? visible - f : n_devices;
+    for (int d = 0; d < use; ++d) devs.push_back(f + d);
     va_cuda_ctx *ctx = nullptr;
     if (va_cuda_create(&ctx, devs.data(), (int)devs.size(), 0) != VA_OK)
         fatal(std::string("Cannot instantiate Kernel. ") + va_cuda_last_error());
-    g_shared.ctx = ctx;
-    g_shared.n_devices = n_devices;
-    g_shared.first = first;
-    return ctx;
+    g_shared.entries.push_back({n_devices, first, ctx});
+    return g_shared.last = ctx;
+}
+
+// compute_alignments hands back two new char[] blocks per pair (the interface demands it:
+// AlignmentKernel.h:20-23 delete[]s them one by one), and the caller frees them after every call.  With
+// glibc's defaults every freed heap top goes back to the kernel at once and the next call page-faults
+// hundreds of MB in again -- on the staging threads, serialised on the process's mmap lock: with 4
+// threads that is 4-5x the cost of the allocation itself (tools/malloc_probe.cpp).  So the plug-in asks
+// glibc once to keep freed pages in its arenas.  VERSALIGN_CUDA_MALLOC_TUNE=0 leaves the allocator alone.
+void tune_host_malloc_once() {
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char *v = getenv("VERSALIGN_CUDA_MALLOC_TUNE");
+        if (v && atoi(v) == 0) return;
+        mallopt(M_TRIM_THRESHOLD, 1 << 30);
+        mallopt(M_TOP_PAD, 64 << 20);
+        mallopt(M_MMAP_THRESHOLD, 1 << 30);
+    });
 }
 
 class CUDAKernel : public AlignmentKernel {
@@ -104,13 +123,13 @@ public:
         read_length_ = need("read_length");
         ref_length_ = need("ref_length");
         if (missing) throw "Cannot instantiate Kernel. Lacking parameters";
-        aln_length_ = read_length_ + ref_length_;
         policy_ = optional_param("cuda_traceback_policy", "VERSALIGN_CUDA_POLICY", VA_POLICY_DEFAULT_OCL);
         if (policy_ != VA_POLICY_DEFAULT_OCL && policy_ != VA_POLICY_SIMD) fatal("cuda_traceback_policy must be 0 (Default/OpenCL) or 1 (SSE/AVX)");
         const int n_devices = optional_param("cuda_devices", "VERSALIGN_CUDA_DEVICES", 0);
         // one process per GPU (torchrun): rank r passes cuda_device_first = r, cuda_devices = 1
         const int first = optional_param("cuda_device_first", "VERSALIGN_CUDA_DEVICE_FIRST", 0);
         ctx_ = acquire_context(n_devices, first);
+        tune_host_malloc_once();
         log_info("Successfully instantiated CUDA Kernel.");
     }
 
@@ -130,7 +149,7 @@ public:
                             char const *const *const refs, Alignment *const alignments) override {
         const int alg = opt & 0xF;
         if (alg != VA_OPT_SW && alg != VA_OPT_NW) return;
-        const int threads = apply_threads();
+        apply_threads();
         log_info("Running CUDAKernel align.");
         const int n = aln_number;
         if (n <= 0) return;
@@ -155,33 +174,18 @@ public:
 private:
     // num_threads is read on every call like the reference (DefaultKernel.cpp:45); here it sizes
     // the host staging pool.
-    int apply_threads() {
+    void apply_threads() {
         int t = 0;
         if (_parameters && Parameters.has_key("num_threads")) t = Parameters.param_int("num_threads");
         const int env = optional_param("cuda_host_threads", "VERSALIGN_CUDA_HOST_THREADS", 0);
         if (env > 0) t = env;
         va_cuda_set_host_threads(ctx_, t);
-        int hw = (int)std::thread::hardware_concurrency();
-        if (hw <= 0) hw = 1;
-        return t > 0 ? (t < hw ? t : hw) : (hw < 32 ? hw : 32);
-    }
-
-    template <class F>
-    static void parallel_blocks(int n, int threads, F fn) {
-        if (threads <= 1 || n < 65536) {
-            fn(0, n);
-            return;
-        }
-        std::vector<std::thread> pool;
-        for (int t = 0; t < threads; ++t) {
-            const int b = (int)((long long)n * t / threads), e = (int)((long long)n * (t + 1) / threads);
-            if (e > b) pool.emplace_back([=] { fn(b, e); });
-        }
-        for (auto &th : pool) th.join();
+        std::lock_guard<std::mutex> lk(g_shared.mu);
+        g_shared.last = ctx_;
     }
 
     va_cuda_scoring scoring_{};
-    int read_length_ = 0, ref_length_ = 0, aln_length_ = 0;
+    int read_length_ = 0, ref_length_ = 0;
     int policy_ = VA_POLICY_DEFAULT_OCL;
     va_cuda_ctx *ctx_ = nullptr;
 };
@@ -190,8 +194,8 @@ private:
 
 extern "C" int va_cuda_plugin_timings(va_cuda_timings *out) {
     std::lock_guard<std::mutex> lk(g_shared.mu);
-    if (!g_shared.ctx || !out) return VA_ERR_ARG;
-    return va_cuda_get_timings(g_shared.ctx, out);
+    if (!g_shared.last || !out) return VA_ERR_ARG;
+    return va_cuda_get_timings(g_shared.last, out);
 }
 
 extern "C" AlignmentKernel *spawn_alignment_kernel() { return new CUDAKernel(); }

@@ -215,8 +215,10 @@ struct PinBuf {
 
 // Device workspace of one chunk in flight.
 struct ChunkSlot {
-    DevBuf raw_reads, raw_refs, code_reads, code_refs, row_idx, solo_list, meta, pair_of, prep_scratch, boundary, dirs, hrow, queue, scores, end_cell, aln_read, aln_ref, start, moves;
-    PinBuf h_reads, h_refs, h_scores, h_end_cell, h_aln_read, h_aln_ref, h_start, h_moves;
+    DevBuf raw_reads, raw_refs, read_off, ref_off, code_reads, code_refs, row_idx, solo_list, meta, pair_of, prep_scratch, boundary, dirs, hrow, queue,
+        scores, end_cell, start, moves, compact, compact_off, cursor, coords, run_count, run_offs, cigar, scan_tmp;
+    PinBuf h_reads, h_refs, h_read_off, h_ref_off, h_scores, h_end_cell, h_start, h_compact, h_compact_off, h_cursor, h_coords, h_run_offs,
+        h_cigar, h_moves;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_done = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
     // side stream of the fill phase: the leftover kernels (solo slots, general) run beside the duo kernel
@@ -226,11 +228,15 @@ struct ChunkSlot {
     int64_t first = 0;
     int count = 0;
     bool busy = false;
+    size_t sent = 0;  // units of the variable-size result (string bytes / CIGAR runs) whose D2H copy is already enqueued
 
     void release() {
-        DevBuf *d[] = {&raw_reads, &raw_refs, &code_reads, &code_refs, &row_idx, &solo_list, &meta, &pair_of, &prep_scratch, &boundary, &dirs, &hrow, &queue, &scores, &end_cell, &aln_read, &aln_ref, &start, &moves};
+        DevBuf *d[] = {&raw_reads, &raw_refs, &read_off, &ref_off, &code_reads, &code_refs, &row_idx, &solo_list, &meta, &pair_of, &prep_scratch,
+                       &boundary, &dirs, &hrow, &queue, &scores, &end_cell, &start, &moves, &compact, &compact_off, &cursor, &coords,
+                       &run_count, &run_offs, &cigar, &scan_tmp};
         for (auto *b : d) b->release();
-        PinBuf *h[] = {&h_reads, &h_refs, &h_scores, &h_end_cell, &h_aln_read, &h_aln_ref, &h_start, &h_moves};
+        PinBuf *h[] = {&h_reads, &h_refs, &h_read_off, &h_ref_off, &h_scores, &h_end_cell, &h_start, &h_compact, &h_compact_off, &h_cursor,
+                       &h_coords, &h_run_offs, &h_cigar, &h_moves};
         for (auto *b : h) b->release();
         if (ev_done) cudaEventDestroy(ev_done);
         if (ev_k0) cudaEventDestroy(ev_k0);
@@ -258,6 +264,10 @@ struct Engine {
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;  // 4 per sub-chunk: before prep, after prep, after fill, after traceback
     size_t prof_used = 0;
+    // Size of the variable-length results (compact strings / CIGAR runs) per pair seen in the last chunk of this
+    // shape: the D2H copy of the next chunk is enqueued for that much (plus a margin) without a host round trip.
+    int est_key[4] = {-1, -1, -1, -1};  // read_length, ref_length, mode, moves
+    double est_per_pair = 0;
 
     int init(int dev) {
         device = dev;
@@ -295,7 +305,9 @@ struct Shape {
     int read_length, ref_length, L;
     int read_chunks, ref_chunks, segs, rows_alloc;
     bool align;
-    bool moves = false;  // align results leave the device as 2-bit move queues (packed entry points), not as strings
+    bool moves = false;    // align results leave the device as CIGAR runs (packed entry points), not as strings
+    bool offsets = false;  // inputs are offset-addressed (packed entry points): per-pair lengths, no padding
+    bool stage_reads = true, stage_refs = true, stage_offs = true;  // false: that input is page-locked, no staging copy
     size_t queue_words() const { return traceback_queue_words(read_length, ref_length); }
     // direction bytes per matrix row and pair: the general and the packed kernel keep separate
     // regions because one chunk can hold pairs of both kinds
@@ -310,9 +322,11 @@ struct Shape {
         }
         return b;
     }
+    // worst-case bytes of one pair's compact strings: two strings of at most L moves + NUL
+    size_t compact_bytes() const { return 2 * ((size_t)L + 1); }
     size_t per_pair_io() const {
-        size_t b = (size_t)read_length + ref_length + 2 + 4;
-        if (align) b += (moves ? (queue_words() + 1) * 4 : 2 * (size_t)L) + 2;
+        size_t b = (size_t)read_length + ref_length + 2 + 4 + (offsets ? 16 : 0);
+        if (align) b += (moves ? 2 * (queue_words() + 1) * 4 + 24 : compact_bytes() + 4) + 2;
         return b;
     }
 };
@@ -348,6 +362,21 @@ int check_domain(const va_cuda_scoring *sc, int read_length, int ref_length) {
     return VA_OK;
 }
 
+// true when [p, p + bytes) is page-locked memory CUDA knows about (cudaHostAlloc / cudaHostRegister): the copy
+// engines can read it in place, no staging copy needed
+bool host_range_is_pinned(const void *p, size_t bytes) {
+    if (!p || bytes == 0) return false;
+    auto pinned = [](const void *q) {
+        cudaPointerAttributes a{};
+        if (cudaPointerGetAttributes(&a, q) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        return a.type == cudaMemoryTypeHost;
+    };
+    return pinned(p) && pinned((const char *)p + bytes - 1);
+}
+
 }  // namespace
 
 struct va_cuda_ctx {
@@ -355,16 +384,25 @@ struct va_cuda_ctx {
     WorkerPool *pool = nullptr;
     int host_threads = 1;
     va_cuda_timings timings{};
-    std::mutex call_mu;  // one host-buffer call at a time per context (the reference's callers are single threaded)
+    std::mutex call_mu;  // one call at a time per context (the reference's callers are single threaded)
 };
 
 namespace {
 
-int reserve_slot(ChunkSlot &s, const Shape &sh, int cap_pairs, bool pinned) {
+enum SlotKind { SLOT_RESIDENT = 0, SLOT_HOST = 1 };
+
+int reserve_slot(ChunkSlot &s, const Shape &sh, int cap_pairs, SlotKind kind) {
+    const bool pinned = kind == SLOT_HOST;
     const size_t slots = round_up((size_t)cap_pairs, 64);
     int rc;
-    if ((rc = s.raw_reads.reserve((size_t)cap_pairs * sh.read_length + 16))) return rc;
-    if ((rc = s.raw_refs.reserve((size_t)cap_pairs * sh.ref_length + 16))) return rc;
+    if (pinned) {  // the resident entry points read the caller's device buffers
+        if ((rc = s.raw_reads.reserve((size_t)cap_pairs * sh.read_length + 16))) return rc;
+        if ((rc = s.raw_refs.reserve((size_t)cap_pairs * sh.ref_length + 16))) return rc;
+        if (sh.offsets) {
+            if ((rc = s.read_off.reserve((slots + 1) * 8))) return rc;
+            if ((rc = s.ref_off.reserve((slots + 1) * 8))) return rc;
+        }
+    }
     if ((rc = s.code_reads.reserve(slots * sh.read_chunks * 16 + 16))) return rc;
     if ((rc = s.code_refs.reserve(slots * sh.ref_chunks * 16 + 16))) return rc;
     if ((rc = s.row_idx.reserve(slots / 2 * sh.read_chunks * 16 + 16))) return rc;
@@ -383,29 +421,43 @@ int reserve_slot(ChunkSlot &s, const Shape &sh, int cap_pairs, bool pinned) {
         const size_t qw = traceback_queue_words(sh.read_length, sh.ref_length);
         if (traceback_needs_global_queue(sh.read_length, sh.ref_length) && (rc = s.queue.reserve(slots * qw * 4 + 64))) return rc;
         if (pinned) {
-            if (sh.moves) {
-                if ((rc = s.moves.reserve((size_t)cap_pairs * (sh.queue_words() + 1) * 4 + 16))) return rc;
-            } else {
-                if ((rc = s.aln_read.reserve((size_t)cap_pairs * sh.L + 16))) return rc;
-                if ((rc = s.aln_ref.reserve((size_t)cap_pairs * sh.L + 16))) return rc;
-            }
             if ((rc = s.start.reserve(slots * 2))) return rc;
+            if (sh.moves) {
+                const size_t mv = (size_t)cap_pairs * (sh.queue_words() + 1) * 4 + 16;
+                if ((rc = s.moves.reserve(mv))) return rc;
+                if ((rc = s.cigar.reserve(mv))) return rc;
+                if ((rc = s.coords.reserve(slots * 16))) return rc;
+                if ((rc = s.run_count.reserve((slots + 1) * 4))) return rc;
+                if ((rc = s.run_offs.reserve((slots + 1) * 4))) return rc;
+                if ((rc = s.scan_tmp.reserve(cigar_compact_scratch_bytes((int)slots)))) return rc;
+            } else {
+                if ((rc = s.compact.reserve((size_t)cap_pairs * sh.compact_bytes() + 64))) return rc;
+                if ((rc = s.compact_off.reserve(slots * 4))) return rc;
+                if ((rc = s.cursor.reserve(64))) return rc;
+            }
         }
     }
     if (pinned) {
         static const bool wc = [] { const char *v = getenv("VERSALIGN_CUDA_WC"); return v && atoi(v) != 0; }();
-        if ((rc = s.h_reads.reserve((size_t)cap_pairs * sh.read_length + 16, wc))) return rc;
-        if ((rc = s.h_refs.reserve((size_t)cap_pairs * sh.ref_length + 16, wc))) return rc;
+        if (sh.stage_reads && (rc = s.h_reads.reserve((size_t)cap_pairs * sh.read_length + 16, wc))) return rc;
+        if (sh.stage_refs && (rc = s.h_refs.reserve((size_t)cap_pairs * sh.ref_length + 16, wc))) return rc;
+        if (sh.offsets && sh.stage_offs) {
+            if ((rc = s.h_read_off.reserve((slots + 1) * 8, wc))) return rc;
+            if ((rc = s.h_ref_off.reserve((slots + 1) * 8, wc))) return rc;
+        }
         if ((rc = s.h_scores.reserve(slots * 2))) return rc;
         if ((rc = s.h_end_cell.reserve(slots * 4))) return rc;
         if (sh.align) {
-            if (sh.moves) {
-                if ((rc = s.h_moves.reserve((size_t)cap_pairs * (sh.queue_words() + 1) * 4 + 16))) return rc;
-            } else {
-                if ((rc = s.h_aln_read.reserve((size_t)cap_pairs * sh.L + 16))) return rc;
-                if ((rc = s.h_aln_ref.reserve((size_t)cap_pairs * sh.L + 16))) return rc;
-            }
             if ((rc = s.h_start.reserve(slots * 2))) return rc;
+            if (sh.moves) {
+                if ((rc = s.h_cigar.reserve((size_t)cap_pairs * (sh.queue_words() + 1) * 4 + 16))) return rc;
+                if ((rc = s.h_coords.reserve(slots * 16))) return rc;
+                if ((rc = s.h_run_offs.reserve((slots + 1) * 4))) return rc;
+            } else {
+                if ((rc = s.h_compact.reserve((size_t)cap_pairs * sh.compact_bytes() + 64))) return rc;
+                if ((rc = s.h_compact_off.reserve(slots * 4))) return rc;
+                if ((rc = s.h_cursor.reserve(64))) return rc;
+            }
         }
     }
     return VA_OK;
@@ -425,12 +477,26 @@ void fill_geom(ChunkGeom &g, const Shape &sh, int n) {
     g.solo = 0;
 }
 
-// Enqueue prep + fill (+ traceback) for n pairs whose raw bytes are at raw_reads/raw_refs on
-// the device.  Outputs go to the given device pointers.  Returns kernels launched (or < 0).
+// Where one chunk's device work reads and writes.
+struct DeviceIO {
+    const uint8_t *raw_reads = nullptr, *raw_refs = nullptr;
+    const int64_t *read_off = nullptr, *ref_off = nullptr;  // offset-addressed input (device copies of the caller's offsets)
+    int16_t *scores = nullptr, *end_cell = nullptr, *start = nullptr;
+    uint8_t *aln_read = nullptr, *aln_ref = nullptr;  // fixed-stride strings (device-resident entry points)
+    bool zero_prefix = false;                         // ... with the bytes before start[i] zeroed
+    bool compact = false;                             // strings into ws.compact instead (host pipeline)
+    bool moves = false;                               // CIGAR runs into ws.cigar + coordinates instead (packed entry points)
+};
+
+// Enqueue prep + fill (+ traceback) for n pairs.  Returns kernels launched (or < 0).
 int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int policy, const Scoring &sc, int n,
-                        const uint8_t *raw_reads, const uint8_t *raw_refs, int16_t *scores, int16_t *end_cell,
-                        uint8_t *aln_read, uint8_t *aln_ref, int16_t *start, bool zero_prefix, cudaStream_t stream,
-                        bool profile = false, uint32_t *moves_out = nullptr) {
+                        const DeviceIO &io, cudaStream_t stream, bool profile = false) {
+#define ENQ_TRY(expr)                                                                                                  \
+    do {                                                                                                               \
+        cudaError_t _e = (expr);                                                                                       \
+        if (_e != cudaSuccess)                                                                                         \
+            return set_error(VA_ERR_DEVICE, "device %d: %s failed: %s", e.device, #expr, cudaGetErrorString(_e));       \
+    } while (0)
     ChunkGeom g;
     fill_geom(g, sh, n);
     // VERSALIGN_CUDA_GENERAL_ONLY=1 keeps every pair on the 32-bit kernel (parity tests use it to
@@ -438,8 +504,10 @@ int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int
     static const bool general_only = [] { const char *v = getenv("VERSALIGN_CUDA_GENERAL_ONLY"); return v && atoi(v) != 0; }();
     if (!general_only && fast_scoring_ok(mode, policy, sc, sh.read_length, sh.ref_length)) g.fast_tw = fast_pick_tw(mode, sh.ref_length);
     ChunkBuffers b{};
-    b.raw_reads = raw_reads;
-    b.raw_refs = raw_refs;
+    b.raw_reads = io.raw_reads;
+    b.raw_refs = io.raw_refs;
+    b.read_off = io.read_off;
+    b.ref_off = io.ref_off;
     b.code_reads = (uint4 *)ws.code_reads.p;
     b.code_refs = (uint4 *)ws.code_refs.p;
     b.row_idx = (uint4 *)ws.row_idx.p;
@@ -452,12 +520,21 @@ int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int
     b.fboundary = (uint32_t *)((char *)ws.boundary.p + round_up((size_t)g.slots * sh.rows_alloc * 4, 256));
     b.dirs = (uint16_t *)ws.dirs.p;
     b.fdirs = (uint4 *)((char *)ws.dirs.p + round_up((size_t)g.slots * sh.gen_dir_row_bytes() * sh.rows_alloc, 256));
-    b.scores = scores;
-    b.end_cell = end_cell;
-    b.aln_read = aln_read;
-    b.aln_ref = aln_ref;
-    b.start = start;
-    b.moves_out = moves_out;
+    b.scores = io.scores;
+    b.end_cell = io.end_cell;
+    b.aln_read = io.aln_read;
+    b.aln_ref = io.aln_ref;
+    b.start = io.start;
+    if (io.moves) {
+        b.moves_out = (uint32_t *)ws.moves.p;
+        b.coords = (int32_t *)ws.coords.p;
+        b.run_count = (uint32_t *)ws.run_count.p;
+    }
+    if (io.compact) {
+        b.aln_compact = (uint8_t *)ws.compact.p;
+        b.compact_off = (uint32_t *)ws.compact_off.p;
+        b.compact_cursor = (unsigned long long *)ws.cursor.p;
+    }
     b.cell_count = e.d_cells;
     int launches = 0;
     cudaEvent_t *pe = nullptr;
@@ -465,13 +542,13 @@ int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int
         if (e.prof_used + 4 > e.prof_events.size()) {
             for (int k = 0; k < 4; ++k) {
                 cudaEvent_t ev;
-                cudaEventCreate(&ev);
+                ENQ_TRY(cudaEventCreate(&ev));
                 e.prof_events.push_back(ev);
             }
         }
         pe = &e.prof_events[e.prof_used];
         e.prof_used += 4;
-        cudaEventRecord(pe[0], stream);
+        ENQ_TRY(cudaEventRecord(pe[0], stream));
     }
     static const bool no_intra = [] { const char *v = getenv("VERSALIGN_CUDA_NO_INTRA"); return v && atoi(v) != 0; }();
     const bool intra = g.fast_tw && !no_intra && intra_preferred(mode, n, sh.read_length, sh.ref_length, e.sm_count);
@@ -480,40 +557,47 @@ int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int
     static const bool no_solo = [] { const char *v = getenv("VERSALIGN_CUDA_NO_SOLO"); return v && atoi(v) != 0; }();
     g.solo = (g.fast_tw && !intra && !no_solo) ? 1 : 0;
     launches += launch_prep(g, b, mode, policy, sc, ws.prep_scratch.p, ws.prep_scratch.cap, stream);
-    if (pe) cudaEventRecord(pe[1], stream);
+    if (pe) ENQ_TRY(cudaEventRecord(pe[1], stream));
     // The packed duo kernel, the solo kernel and the general kernel own disjoint slots: the general kernel
     // (usually with nothing to do) runs beside the packed ones on a side stream instead of after them.
     if (!ws.side) {
-        cudaStreamCreateWithFlags(&ws.side, cudaStreamNonBlocking);
-        cudaEventCreateWithFlags(&ws.ev_fork, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&ws.ev_join, cudaEventDisableTiming);
+        ENQ_TRY(cudaStreamCreateWithFlags(&ws.side, cudaStreamNonBlocking));
+        ENQ_TRY(cudaEventCreateWithFlags(&ws.ev_fork, cudaEventDisableTiming));
+        ENQ_TRY(cudaEventCreateWithFlags(&ws.ev_join, cudaEventDisableTiming));
     }
-    cudaEventRecord(ws.ev_fork, stream);
-    cudaStreamWaitEvent(ws.side, ws.ev_fork, 0);
+    ENQ_TRY(cudaEventRecord(ws.ev_fork, stream));
+    ENQ_TRY(cudaStreamWaitEvent(ws.side, ws.ev_fork, 0));
     launches += launch_fill_general(g, b, mode, policy, sc, ws.side);
-    cudaEventRecord(ws.ev_join, ws.side);
+    ENQ_TRY(cudaEventRecord(ws.ev_join, ws.side));
     if (intra)
         launches += launch_fill_intra(g, b, mode, make_fast_consts(mode, sc), stream);
     else
         launches += launch_fill_fast(g, b, mode, sc, stream);
-    cudaStreamWaitEvent(stream, ws.ev_join, 0);
-    if (pe) cudaEventRecord(pe[2], stream);
+    ENQ_TRY(cudaStreamWaitEvent(stream, ws.ev_join, 0));
+    if (pe) ENQ_TRY(cudaEventRecord(pe[2], stream));
     if (sh.align) {
-        if (zero_prefix && !moves_out) {  // bytes before start[i] are promised to be zero on this path
-            cudaMemsetAsync(aln_read, 0, (size_t)n * sh.L, stream);
-            cudaMemsetAsync(aln_ref, 0, (size_t)n * sh.L, stream);
+        if (io.zero_prefix && io.aln_read) {  // bytes before start[i] are promised to be zero on this path
+            ENQ_TRY(cudaMemsetAsync(io.aln_read, 0, (size_t)n * sh.L, stream));
+            ENQ_TRY(cudaMemsetAsync(io.aln_ref, 0, (size_t)n * sh.L, stream));
         }
+        if (io.compact) ENQ_TRY(cudaMemsetAsync(ws.cursor.p, 0, 8, stream));
+        if (io.moves) ENQ_TRY(cudaMemsetAsync((uint32_t *)ws.run_count.p + n, 0, 4, stream));  // the scan's sentinel entry
         launches += launch_traceback(g, b, mode, sc, (uint32_t *)ws.queue.p, stream);
+        if (io.moves)
+            launches += launch_cigar_compact(n, (int)sh.queue_words(), (const uint32_t *)ws.moves.p, (const uint32_t *)ws.run_count.p,
+                                             (uint32_t *)ws.run_offs.p, (uint32_t *)ws.cigar.p, ws.cigar.cap / 4, ws.scan_tmp.p,
+                                             ws.scan_tmp.cap, stream);
     }
-    if (pe) cudaEventRecord(pe[3], stream);
-    cudaError_t err = cudaGetLastError();
-    if (err != cudaSuccess) return set_error(VA_ERR_DEVICE, "kernel launch failed: %s", cudaGetErrorString(err));
+    if (pe) ENQ_TRY(cudaEventRecord(pe[3], stream));
+    ENQ_TRY(cudaGetLastError());
     return launches;
+#undef ENQ_TRY
 }
 
 // CIGAR runs of one chunk of a packed align call
 struct CigarPart {
     int64_t first = 0;
+    int count = 0;
     size_t words = 0;
     std::unique_ptr<uint32_t[]> data;
 };
@@ -529,6 +613,7 @@ struct HostCall {
     const char *const *refs_p = nullptr;
     const char *reads_f = nullptr;
     const char *refs_f = nullptr;
+    bool reads_pinned = false, refs_pinned = false, offs_pinned = false;  // flat inputs the copy engines can read in place
     // outputs
     int16_t *scores = nullptr;
     char *const *out_read_p = nullptr;
@@ -548,9 +633,10 @@ struct HostCall {
     const int64_t *read_off = nullptr;
     const int64_t *ref_off = nullptr;
     int32_t *coords = nullptr;                        // [n][4]: read_begin, read_end, ref_begin, ref_end (0-based, half open)
-    int64_t *cigar_off = nullptr;                     // [n+1]; filled with per-pair op counts first, prefix-summed at the end
+    int64_t *cigar_off = nullptr;                     // [n+1]; while the call runs: chunk-relative offsets, made global at the end
     std::vector<CigarPart> *cigar_parts = nullptr;  // one per chunk, any order
     std::mutex *cigar_mu = nullptr;
+    std::atomic<int> *cancel = nullptr;  // set by the first shard that fails: the others stop at their next chunk
 };
 
 struct ShardStats {
@@ -562,33 +648,27 @@ struct ShardStats {
     std::string err;
 };
 
+// Inputs of pairs [first, first + count) -> pinned staging.  Returns false when there is nothing to stage
+// (flat inputs in page-locked memory: the H2D copies read the caller's buffers in place).
 void gather_chunk(va_cuda_ctx *ctx, const HostCall &c, ChunkSlot &s, int64_t first, int count) {
     char *hr = (char *)s.h_reads.p, *hf = (char *)s.h_refs.p;
     const int RL = c.sh.read_length, FL = c.sh.ref_length;
     if (c.read_off) {
-        // offset-addressed sequences -> the kernels' fixed-stride, '\0'-padded staging layout
-        ctx->pool->parallel_for(count, 2048, [&](int64_t b, int64_t e) {
-            // no sequence is longer than RL / FL, so a block whose bytes add up to (e-b)*RL holds full-length
-            // sequences only and already IS the staging layout
-            const bool full_r = c.read_off[first + e] - c.read_off[first + b] == (e - b) * (int64_t)RL;
-            const bool full_f = c.ref_off[first + e] - c.ref_off[first + b] == (e - b) * (int64_t)FL;
-            if (full_r) memcpy(hr + b * RL, c.reads_f + c.read_off[first + b], (size_t)(e - b) * RL);
-            if (full_f) memcpy(hf + b * FL, c.refs_f + c.ref_off[first + b], (size_t)(e - b) * FL);
-            if (full_r && full_f) return;
-            for (int64_t i = b; i < e; ++i) {
-                const int64_t r0 = c.read_off[first + i], r1 = c.read_off[first + i + 1];
-                const int64_t f0 = c.ref_off[first + i], f1 = c.ref_off[first + i + 1];
-                memcpy(hr + i * RL, c.reads_f + r0, (size_t)(r1 - r0));
-                memset(hr + i * RL + (r1 - r0), 0, (size_t)(RL - (r1 - r0)));
-                memcpy(hf + i * FL, c.refs_f + f0, (size_t)(f1 - f0));
-                memset(hf + i * FL + (f1 - f0), 0, (size_t)(FL - (f1 - f0)));
-            }
-        });
+        // offset-addressed sequences travel as they are: one block of bases per side + the offsets
+        const int64_t r0 = c.read_off[first], r1 = c.read_off[first + count], f0 = c.ref_off[first], f1 = c.ref_off[first + count];
+        if (!c.reads_pinned)
+            ctx->pool->parallel_for(r1 - r0, 1 << 20, [&](int64_t b, int64_t e) { memcpy(hr + b, c.reads_f + r0 + b, (size_t)(e - b)); });
+        if (!c.refs_pinned)
+            ctx->pool->parallel_for(f1 - f0, 1 << 20, [&](int64_t b, int64_t e) { memcpy(hf + b, c.refs_f + f0 + b, (size_t)(e - b)); });
+        if (!c.offs_pinned) {
+            memcpy(s.h_read_off.p, c.read_off + first, (size_t)(count + 1) * 8);
+            memcpy(s.h_ref_off.p, c.ref_off + first, (size_t)(count + 1) * 8);
+        }
     } else if (c.reads_f) {
-        ctx->pool->parallel_for(count, 4096, [&](int64_t b, int64_t e) {
-            memcpy(hr + b * RL, c.reads_f + (first + b) * RL, (size_t)(e - b) * RL);
-            memcpy(hf + b * FL, c.refs_f + (first + b) * FL, (size_t)(e - b) * FL);
-        });
+        if (!c.reads_pinned)
+            ctx->pool->parallel_for((int64_t)count * RL, 1 << 20, [&](int64_t b, int64_t e) { memcpy(hr + b, c.reads_f + first * RL + b, (size_t)(e - b)); });
+        if (!c.refs_pinned)
+            ctx->pool->parallel_for((int64_t)count * FL, 1 << 20, [&](int64_t b, int64_t e) { memcpy(hf + b, c.refs_f + first * FL + b, (size_t)(e - b)); });
     } else {
         ctx->pool->parallel_for(count, 2048, [&](int64_t b, int64_t e) {
             // the blocks are scattered over the caller's heap: ask for the ones a few pairs ahead now
@@ -606,17 +686,11 @@ void gather_chunk(va_cuda_ctx *ctx, const HostCall &c, ChunkSlot &s, int64_t fir
     }
 }
 
-// Packed entry points: a pair's result arrives as its moves in walk order (last alignment column first),
-// normally already run-length encoded by the traceback kernel, else as the raw 2-bit queue
-// (va_traceback.cu).  Reversed it is the CIGAR (BAM encoding: length << 4 | op; M = 0 read and ref base,
-// I = 1 read base against a gap, D = 2 ref base against a gap) and the aligned coordinate ranges.
-void scatter_moves(va_cuda_ctx *ctx, const HostCall &c, ChunkSlot &s, int64_t first, int count) {
+// Packed entry points, fallback: a chunk whose CIGARs do not fit the device-side compaction buffer (pairs with
+// more runs than move slots) comes back as per-pair moves in walk order -- runs or the raw 2-bit queue
+// (va_traceback.cu) -- and is replayed here.
+void replay_moves_on_host(va_cuda_ctx *ctx, const HostCall &c, const uint32_t *mv, int64_t first, int count, CigarPart &cp) {
     const size_t qw = c.sh.queue_words() + 1;
-    const int16_t *ec = (const int16_t *)s.h_end_cell.p;
-    const int16_t *sc = (const int16_t *)s.h_scores.p;
-    const uint32_t *mv = (const uint32_t *)s.h_moves.p;
-    if (c.scores) memcpy(c.scores + first, sc, (size_t)count * sizeof(int16_t));
-    if (c.end_cell) memcpy(c.end_cell + 2 * first, ec, (size_t)count * 2 * sizeof(int16_t));
     // forward replay of pair i: fn(op, run length) per CIGAR run; returns the number of runs
     auto replay = [&](int64_t i, auto &&fn) -> int {
         const uint32_t *q = mv + (size_t)i * qw;
@@ -642,163 +716,240 @@ void scatter_moves(va_cuda_ctx *ctx, const HostCall &c, ChunkSlot &s, int64_t fi
         if (len) { fn(cur, len); ++runs; }
         return runs;
     };
-    // pass 1: runs per pair (the header says it unless the pair came back as raw moves)
     std::unique_ptr<int64_t[]> offs(new int64_t[(size_t)count + 1]);
     offs[0] = 0;
     ctx->pool->parallel_for(count, 8192, [&](int64_t b, int64_t e) {
         for (int64_t i = b; i < e; ++i) {
             const uint32_t head = mv[(size_t)i * qw];
-            const int runs = (head & 0x80000000u) ? replay(i, [](int, int) {}) : (int)head;
-            offs[(size_t)i + 1] = runs;
-            if (c.cigar_off) c.cigar_off[first + i + 1] = runs;
+            offs[(size_t)i + 1] = (head & 0x80000000u) ? replay(i, [](int, int) {}) : (int)head;
         }
     });
     for (int64_t i = 0; i < count; ++i) offs[(size_t)i + 1] += offs[(size_t)i];
-    // pass 2: coordinates and the runs themselves
-    std::unique_ptr<uint32_t[]> part;
-    uint32_t *pout = nullptr;
-    if (c.cigar_parts) {
-        part.reset(new uint32_t[(size_t)offs[(size_t)count] + 1]);  // not zero filled: every word is written below
-        pout = part.get();
-    }
+    if (c.cigar_off)
+        for (int64_t i = 0; i < count; ++i) c.cigar_off[first + i + 1] = offs[(size_t)i + 1];
+    cp.words = (size_t)offs[(size_t)count];
+    if (!c.cigar_parts) return;
+    cp.data.reset(new uint32_t[cp.words + 1]);
+    uint32_t *pout = cp.data.get();
     ctx->pool->parallel_for(count, 4096, [&](int64_t b, int64_t e) {
         for (int64_t i = b; i < e; ++i) {
-            int used_read = 0, used_ref = 0;
-            uint32_t *out = pout ? pout + offs[(size_t)i] : nullptr;
-            replay(i, [&](int op, int len) {
-                if (op != 2) used_read += len;
-                if (op != 1) used_ref += len;
-                if (out) *out++ = ((uint32_t)len << 4) | (uint32_t)op;
-            });
-            if (c.coords) {
-                int32_t *co = c.coords + 4 * (first + i);
-                co[1] = (int32_t)ec[2 * i] + 1;
-                co[0] = co[1] - used_read;
-                co[3] = (int32_t)ec[2 * i + 1] + 1;
-                co[2] = co[3] - used_ref;
-            }
+            uint32_t *out = pout + offs[(size_t)i];
+            replay(i, [&](int op, int len) { *out++ = ((uint32_t)len << 4) | (uint32_t)op; });
         }
     });
-    if (!c.cigar_parts) return;
-    std::lock_guard<std::mutex> lk(*c.cigar_mu);
-    c.cigar_parts->emplace_back();
-    CigarPart &cp = c.cigar_parts->back();
-    cp.first = first;
-    cp.words = (size_t)offs[(size_t)count];
-    cp.data = std::move(part);
 }
 
-void scatter_chunk(va_cuda_ctx *ctx, const HostCall &c, ChunkSlot &s, int64_t first, int count) {
+// Results of a packed align chunk -> the caller's arrays: everything was laid out on the device, the host only copies.
+int scatter_packed(va_cuda_ctx *ctx, Engine &e, const HostCall &c, ChunkSlot &s, int64_t first, int count, ShardStats &st) {
+    if (c.scores) memcpy(c.scores + first, s.h_scores.p, (size_t)count * sizeof(int16_t));
+    if (c.end_cell) memcpy(c.end_cell + 2 * first, s.h_end_cell.p, (size_t)count * 2 * sizeof(int16_t));
+    if (c.coords) {
+        const char *src = (const char *)s.h_coords.p;
+        ctx->pool->parallel_for((int64_t)count * 16, 1 << 20, [&](int64_t b, int64_t e2) { memcpy((char *)(c.coords + 4 * first) + b, src + b, (size_t)(e2 - b)); });
+    }
+    const uint32_t *ro = (const uint32_t *)s.h_run_offs.p;
+    const size_t total = ro[count];
+    CigarPart cp;
+    cp.first = first;
+    cp.count = count;
+    if (total > s.cigar.cap / 4) {
+        // does not fit the compaction buffer (nothing was written past it): fetch the per-pair moves instead
+        const size_t mv_bytes = (size_t)count * (c.sh.queue_words() + 1) * 4;
+        int rc = s.h_moves.reserve(mv_bytes + 16);
+        if (rc) return rc;
+        cudaError_t err = cudaMemcpyAsync(s.h_moves.p, s.moves.p, mv_bytes, cudaMemcpyDeviceToHost, s.stream);
+        if (err == cudaSuccess) err = cudaStreamSynchronize(s.stream);
+        if (err != cudaSuccess) return set_error(VA_ERR_DEVICE, "device %d: fetching moves failed: %s", e.device, cudaGetErrorString(err));
+        st.d2h += (int64_t)mv_bytes;
+        replay_moves_on_host(ctx, c, (const uint32_t *)s.h_moves.p, first, count, cp);
+    } else {
+        if (total > s.sent) {  // more runs than the estimate the first copy was sized by: fetch the rest
+            cudaError_t err = cudaMemcpyAsync((uint32_t *)s.h_cigar.p + s.sent, (const uint32_t *)s.cigar.p + s.sent, (total - s.sent) * 4,
+                                              cudaMemcpyDeviceToHost, s.stream);
+            if (err == cudaSuccess) err = cudaStreamSynchronize(s.stream);
+            if (err != cudaSuccess) return set_error(VA_ERR_DEVICE, "device %d: fetching CIGAR runs failed: %s", e.device, cudaGetErrorString(err));
+            st.d2h += (int64_t)(total - s.sent) * 4;
+        }
+        e.est_per_pair = (double)total / std::max(count, 1);
+        if (c.cigar_off)
+            ctx->pool->parallel_for(count, 1 << 16, [&](int64_t b, int64_t e2) {
+                for (int64_t i = b; i < e2; ++i) c.cigar_off[first + i + 1] = (int64_t)ro[i + 1];
+            });
+        cp.words = total;
+        if (c.cigar_parts) {
+            cp.data.reset(new uint32_t[total + 1]);
+            uint32_t *dst = cp.data.get();
+            const uint32_t *src = (const uint32_t *)s.h_cigar.p;
+            ctx->pool->parallel_for((int64_t)total, 1 << 18, [&](int64_t b, int64_t e2) { memcpy(dst + b, src + b, (size_t)(e2 - b) * 4); });
+        }
+    }
+    if (c.cigar_parts) {
+        std::lock_guard<std::mutex> lk(*c.cigar_mu);
+        c.cigar_parts->push_back(std::move(cp));
+    }
+    return VA_OK;
+}
+
+// Results of a legacy align chunk: the two strings of pair i lie back to back in the compact block at off[i], each
+// (moves + 1) bytes with its NUL; they go right-aligned into the caller's L-byte blocks (DefaultKernel.cpp:441-451).
+int scatter_strings(va_cuda_ctx *ctx, Engine &e, const HostCall &c, ChunkSlot &s, int64_t first, int count, ShardStats &st) {
     const int L = c.sh.L;
-    if (!c.sh.align) {
-        memcpy(c.scores + first, s.h_scores.p, (size_t)count * sizeof(int16_t));
-        return;
+    const int16_t *stt = (const int16_t *)s.h_start.p;
+    const uint32_t *off = (const uint32_t *)s.h_compact_off.p;
+    const char *hc = (const char *)s.h_compact.p;
+    const size_t total = (size_t) * (const unsigned long long *)s.h_cursor.p;
+    if (total > s.sent) {  // longer alignments than the estimate the first copy was sized by: fetch the rest
+        cudaError_t err = cudaMemcpyAsync((char *)s.h_compact.p + s.sent, (const char *)s.compact.p + s.sent, total - s.sent,
+                                          cudaMemcpyDeviceToHost, s.stream);
+        if (err == cudaSuccess) err = cudaStreamSynchronize(s.stream);
+        if (err != cudaSuccess) return set_error(VA_ERR_DEVICE, "device %d: fetching alignment strings failed: %s", e.device, cudaGetErrorString(err));
+        st.d2h += (int64_t)(total - s.sent);
     }
-    const int16_t *st = (const int16_t *)s.h_start.p;
-    const int16_t *ec = (const int16_t *)s.h_end_cell.p;
-    if (c.sh.moves) {
-        scatter_moves(ctx, c, s, first, count);
-        return;
-    }
-    const char *ha = (const char *)s.h_aln_read.p, *hb = (const char *)s.h_aln_ref.p;
-    if (c.start) memcpy(c.start + first, st, (size_t)count * sizeof(int16_t));
-    if (c.end_cell) memcpy(c.end_cell + 2 * first, ec, (size_t)count * 2 * sizeof(int16_t));
+    e.est_per_pair = (double)total / std::max(count, 1);
+    if (c.start) memcpy(c.start + first, stt, (size_t)count * sizeof(int16_t));
+    if (c.end_cell) memcpy(c.end_cell + 2 * first, s.h_end_cell.p, (size_t)count * 2 * sizeof(int16_t));
+    // pair i: where the kept part of each string starts in the compact block, how many bytes (with the NUL), and
+    // the index it goes to in the caller's block
+    struct Piece {
+        const char *a, *b;
+        int s0, bytes;
+    };
+    auto piece = [&](int64_t i) {
+        const int moves = L - 1 - (int)stt[i];
+        int s0 = stt[i];
+        if (s0 < 0) s0 = 0;  // a walk longer than the block (only when every move is a gap): its head is cut, like the fixed layout
+        const int keep = L - 1 - s0;
+        const char *a = hc + off[i] + (moves - keep);
+        return Piece{a, a + moves + 1, s0, keep + 1};
+    };
     if (c.out_read_f) {
-        ctx->pool->parallel_for(count, 2048, [&](int64_t b, int64_t e) {
-            for (int64_t i = b; i < e; ++i) {
-                int s0 = st[i];
-                if (s0 < 0) s0 = 0;
-                if (s0 > L) s0 = L;
+        ctx->pool->parallel_for(count, 2048, [&](int64_t b, int64_t e2) {
+            for (int64_t i = b; i < e2; ++i) {
+                const Piece p = piece(i);
                 char *da = c.out_read_f + (first + i) * L, *db = c.out_ref_f + (first + i) * L;
-                memset(da, 0, (size_t)s0);
-                memset(db, 0, (size_t)s0);
-                memcpy(da + s0, ha + i * L + s0, (size_t)(L - s0));
-                memcpy(db + s0, hb + i * L + s0, (size_t)(L - s0));
-            }
-        });
-    } else if (c.alloc && c.records) {
-        ctx->pool->parallel_for(count, 1024, [&](int64_t b, int64_t e) {
-            for (int64_t i = b; i < e; ++i) {
-                int s0 = st[i];
-                if (s0 < 0) s0 = 0;
-                if (s0 > L) s0 = L;
-                char *da = c.alloc((size_t)(L > 0 ? L : 1), c.alloc_user);
-                char *db = c.alloc((size_t)(L > 0 ? L : 1), c.alloc_user);
-                va_cuda_alignment_record *rec = reinterpret_cast<va_cuda_alignment_record *>(c.records + (size_t)(first + i) * c.record_stride);
-                rec->read = da;
-                rec->ref = db;
-                rec->read_start = rec->ref_start = st[i];
-                rec->read_end = rec->ref_end = (int16_t)(L - 1);
-                if (!da || !db) {
-                    c.alloc_failed->store(1);
-                    continue;
-                }
-                memcpy(da + s0, ha + i * L + s0, (size_t)(L - s0));
-                memcpy(db + s0, hb + i * L + s0, (size_t)(L - s0));
+                memset(da, 0, (size_t)p.s0);
+                memset(db, 0, (size_t)p.s0);
+                memcpy(da + p.s0, p.a, (size_t)p.bytes);
+                memcpy(db + p.s0, p.b, (size_t)p.bytes);
             }
         });
     } else if (c.alloc) {
-        ctx->pool->parallel_for(count, 1024, [&](int64_t b, int64_t e) {
-            for (int64_t i = b; i < e; ++i) {
-                int s0 = st[i];
-                if (s0 < 0) s0 = 0;
-                if (s0 > L) s0 = L;
+        ctx->pool->parallel_for(count, 1024, [&](int64_t b, int64_t e2) {
+            constexpr int AHEAD = 4;
+            for (int64_t i = b; i < e2; ++i) {
+                if (i + AHEAD < e2) __builtin_prefetch(hc + off[i + AHEAD], 0, 0);
+                const Piece p = piece(i);
                 char *da = c.alloc((size_t)(L > 0 ? L : 1), c.alloc_user);
                 char *db = c.alloc((size_t)(L > 0 ? L : 1), c.alloc_user);
-                c.out_read_w[first + i] = da;
-                c.out_ref_w[first + i] = db;
+                if (c.records) {
+                    va_cuda_alignment_record *rec = reinterpret_cast<va_cuda_alignment_record *>(c.records + (size_t)(first + i) * c.record_stride);
+                    rec->read = da;
+                    rec->ref = db;
+                    rec->read_start = rec->ref_start = stt[i];
+                    rec->read_end = rec->ref_end = (int16_t)(L - 1);
+                } else {
+                    c.out_read_w[first + i] = da;
+                    c.out_ref_w[first + i] = db;
+                }
                 if (!da || !db) {
                     c.alloc_failed->store(1);
                     continue;
                 }
-                memcpy(da + s0, ha + i * L + s0, (size_t)(L - s0));
-                memcpy(db + s0, hb + i * L + s0, (size_t)(L - s0));
+                memcpy(da + p.s0, p.a, (size_t)p.bytes);
+                memcpy(db + p.s0, p.b, (size_t)p.bytes);
             }
         });
     } else {
-        ctx->pool->parallel_for(count, 1024, [&](int64_t b, int64_t e) {
-            for (int64_t i = b; i < e; ++i) {
-                int s0 = st[i];
-                if (s0 < 0) s0 = 0;
-                if (s0 > L) s0 = L;
-                memcpy(c.out_read_p[first + i] + s0, ha + i * L + s0, (size_t)(L - s0));
-                memcpy(c.out_ref_p[first + i] + s0, hb + i * L + s0, (size_t)(L - s0));
+        ctx->pool->parallel_for(count, 1024, [&](int64_t b, int64_t e2) {
+            for (int64_t i = b; i < e2; ++i) {
+                const Piece p = piece(i);
+                memcpy(c.out_read_p[first + i] + p.s0, p.a, (size_t)p.bytes);
+                memcpy(c.out_ref_p[first + i] + p.s0, p.b, (size_t)p.bytes);
             }
         });
     }
+    return VA_OK;
+}
+
+int scatter_chunk(va_cuda_ctx *ctx, Engine &e, const HostCall &c, ChunkSlot &s, int64_t first, int count, ShardStats &st) {
+    if (!c.sh.align) {
+        memcpy(c.scores + first, s.h_scores.p, (size_t)count * sizeof(int16_t));
+        return VA_OK;
+    }
+    return c.sh.moves ? scatter_packed(ctx, e, c, s, first, count, st) : scatter_strings(ctx, e, c, s, first, count, st);
 }
 
 // One device's share [lo, hi) of the batch, chunked through the ring.
 void run_shard(va_cuda_ctx *ctx, Engine &e, const HostCall &c, int64_t lo, int64_t hi, int chunk_pairs, ShardStats &st) {
+    // On any failure: remember the message (with the device), tell the sibling shards to stop, and leave nothing
+    // in flight -- the ring's pinned buffers and the caller's outputs must not be written after the call returns.
+    auto quiesce = [&] {
+        for (auto &s : e.ring) {
+            if (s.stream) cudaStreamSynchronize(s.stream);
+            if (s.side) cudaStreamSynchronize(s.side);
+            s.busy = false;
+        }
+        cudaGetLastError();
+    };
     auto fail = [&](int rc) {
         st.rc = rc;
         st.err = g_last_error;
+        if (c.cancel) c.cancel->store(1);
+        quiesce();
     };
-    if (cudaSetDevice(e.device) != cudaSuccess) return fail(set_error(VA_ERR_DEVICE, "cudaSetDevice(%d) failed", e.device));
+#define SHARD_TRY(expr)                                                                                                      \
+    do {                                                                                                                     \
+        cudaError_t _e = (expr);                                                                                             \
+        if (_e != cudaSuccess)                                                                                               \
+            return fail(set_error(_e == cudaErrorMemoryAllocation ? VA_ERR_MEMORY : VA_ERR_DEVICE, "device %d: %s failed: %s", \
+                                  e.device, #expr, cudaGetErrorString(_e)));                                                 \
+    } while (0)
+    SHARD_TRY(cudaSetDevice(e.device));
     for (auto &s : e.ring) {
-        int rc = reserve_slot(s, c.sh, chunk_pairs, true);
+        int rc = reserve_slot(s, c.sh, chunk_pairs, SLOT_HOST);
         if (rc) return fail(rc);
         s.busy = false;
     }
-    cudaMemsetAsync(e.d_cells, 0, sizeof(unsigned long long), e.ring[0].stream);
-    cudaStreamSynchronize(e.ring[0].stream);
+    SHARD_TRY(cudaMemsetAsync(e.d_cells, 0, sizeof(unsigned long long), e.ring[0].stream));
+    SHARD_TRY(cudaStreamSynchronize(e.ring[0].stream));
 
-    const int RL = c.sh.read_length, FL = c.sh.ref_length, L = c.sh.L;
+    const int RL = c.sh.read_length, FL = c.sh.ref_length;
+    const bool strings = c.sh.align && !c.sh.moves, moves = c.sh.align && c.sh.moves;
+    // per-pair size of the variable-length result, remembered from the last chunk of the same kind
+    const int key[4] = {RL, FL, c.mode, c.sh.moves ? 1 : 0};
+    if (memcmp(key, e.est_key, sizeof(key)) != 0) {
+        memcpy(e.est_key, key, sizeof(key));
+        e.est_per_pair = 0;  // unknown: the first chunk fetches its worst case
+    }
+    // VERSALIGN_CUDA_TRACE=1: host-side timeline of the shard on stderr (ms since the shard started)
+    static const bool trace = [] { const char *v = getenv("VERSALIGN_CUDA_TRACE"); return v && atoi(v) != 0; }();
+    const auto t_shard = Clock::now();
+    auto mark = [&](const char *what, int64_t first) {
+        if (trace) fprintf(stderr, "[va trace] dev %d %8.3f ms  %s %lld\n", e.device, seconds_since(t_shard) * 1e3, what, (long long)first);
+    };
     auto drain = [&](ChunkSlot &s) -> int {
         if (!s.busy) return VA_OK;
+        mark("wait", s.first);
         cudaError_t err = cudaEventSynchronize(s.ev_done);
-        if (err != cudaSuccess) return set_error(VA_ERR_DEVICE, "device work failed: %s", cudaGetErrorString(err));
+        mark("done", s.first);
+        if (err != cudaSuccess) return set_error(VA_ERR_DEVICE, "device %d: device work failed: %s", e.device, cudaGetErrorString(err));
         float ms = 0;
         if (cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1) == cudaSuccess) st.kernel_ms += ms;
         auto t0 = Clock::now();
-        scatter_chunk(ctx, c, s, s.first, s.count);
+        int rc = scatter_chunk(ctx, e, c, s, s.first, s.count, st);
         st.scatter_s += seconds_since(t0);
+        mark("scattered", s.first);
         s.busy = false;
-        return VA_OK;
+        if (rc == VA_OK && c.alloc_failed && c.alloc_failed->load()) rc = set_error(VA_ERR_MEMORY, "the caller's allocator returned NULL");
+        return rc;
     };
 
     int k = 0;
     for (int64_t first = lo; first < hi; first += chunk_pairs, ++k) {
+        if (c.cancel && c.cancel->load()) {  // another device's shard failed
+            quiesce();
+            return;
+        }
         const int count = (int)std::min<int64_t>(chunk_pairs, hi - first);
         ChunkSlot &s = e.ring[k % kRing];
         int rc = drain(s);  // the slot's previous chunk must be out before its pinned buffers are reused
@@ -806,37 +957,63 @@ void run_shard(va_cuda_ctx *ctx, Engine &e, const HostCall &c, int64_t lo, int64
         auto t0 = Clock::now();
         gather_chunk(ctx, c, s, first, count);
         st.gather_s += seconds_since(t0);
+        mark("gathered", first);
 
-        cudaMemcpyAsync(s.raw_reads.p, s.h_reads.p, (size_t)count * RL, cudaMemcpyHostToDevice, s.stream);
-        cudaMemcpyAsync(s.raw_refs.p, s.h_refs.p, (size_t)count * FL, cudaMemcpyHostToDevice, s.stream);
-        st.h2d += (int64_t)count * (RL + FL);
-        cudaEventRecord(s.ev_k0, s.stream);
-        const bool zero_prefix = false;  // the host scatter zero-fills prefixes of the flat outputs itself
-        int launches = enqueue_device_work(e, s, c.sh, c.mode, c.policy, c.sc, count, (const uint8_t *)s.raw_reads.p,
-                                           (const uint8_t *)s.raw_refs.p, (int16_t *)s.scores.p, (int16_t *)s.end_cell.p,
-                                           (uint8_t *)s.aln_read.p, (uint8_t *)s.aln_ref.p, (int16_t *)s.start.p,
-                                           zero_prefix, s.stream, false, c.sh.moves ? (uint32_t *)s.moves.p : nullptr);
+        DeviceIO io;
+        io.raw_reads = (const uint8_t *)s.raw_reads.p;
+        io.raw_refs = (const uint8_t *)s.raw_refs.p;
+        if (c.read_off) {
+            const int64_t r0 = c.read_off[first], r1 = c.read_off[first + count], f0 = c.ref_off[first], f1 = c.ref_off[first + count];
+            SHARD_TRY(cudaMemcpyAsync(s.raw_reads.p, c.reads_pinned ? (const void *)(c.reads_f + r0) : s.h_reads.p, (size_t)(r1 - r0), cudaMemcpyHostToDevice, s.stream));
+            SHARD_TRY(cudaMemcpyAsync(s.raw_refs.p, c.refs_pinned ? (const void *)(c.refs_f + f0) : s.h_refs.p, (size_t)(f1 - f0), cudaMemcpyHostToDevice, s.stream));
+            SHARD_TRY(cudaMemcpyAsync(s.read_off.p, c.offs_pinned ? (const void *)(c.read_off + first) : s.h_read_off.p, (size_t)(count + 1) * 8, cudaMemcpyHostToDevice, s.stream));
+            SHARD_TRY(cudaMemcpyAsync(s.ref_off.p, c.offs_pinned ? (const void *)(c.ref_off + first) : s.h_ref_off.p, (size_t)(count + 1) * 8, cudaMemcpyHostToDevice, s.stream));
+            st.h2d += (r1 - r0) + (f1 - f0) + (int64_t)(count + 1) * 16;
+            io.read_off = (const int64_t *)s.read_off.p;
+            io.ref_off = (const int64_t *)s.ref_off.p;
+        } else {
+            const bool rp = c.reads_f && c.reads_pinned, fp = c.refs_f && c.refs_pinned;
+            SHARD_TRY(cudaMemcpyAsync(s.raw_reads.p, rp ? (const void *)(c.reads_f + first * RL) : s.h_reads.p, (size_t)count * RL, cudaMemcpyHostToDevice, s.stream));
+            SHARD_TRY(cudaMemcpyAsync(s.raw_refs.p, fp ? (const void *)(c.refs_f + first * FL) : s.h_refs.p, (size_t)count * FL, cudaMemcpyHostToDevice, s.stream));
+            st.h2d += (int64_t)count * (RL + FL);
+        }
+        SHARD_TRY(cudaEventRecord(s.ev_k0, s.stream));
+        io.scores = (int16_t *)s.scores.p;
+        io.end_cell = (int16_t *)s.end_cell.p;
+        io.start = (int16_t *)s.start.p;
+        io.compact = strings;
+        io.moves = moves;
+        int launches = enqueue_device_work(e, s, c.sh, c.mode, c.policy, c.sc, count, io, s.stream);
         if (launches < 0) return fail(launches);
         st.launches += launches;
-        cudaEventRecord(s.ev_k1, s.stream);
+        SHARD_TRY(cudaEventRecord(s.ev_k1, s.stream));
         if (!c.sh.align) {
-            cudaMemcpyAsync(s.h_scores.p, s.scores.p, (size_t)count * 2, cudaMemcpyDeviceToHost, s.stream);
+            SHARD_TRY(cudaMemcpyAsync(s.h_scores.p, s.scores.p, (size_t)count * 2, cudaMemcpyDeviceToHost, s.stream));
             st.d2h += (int64_t)count * 2;
-        } else if (c.sh.moves) {
-            const size_t qb = (c.sh.queue_words() + 1) * 4;
-            cudaMemcpyAsync(s.h_moves.p, s.moves.p, (size_t)count * qb, cudaMemcpyDeviceToHost, s.stream);
-            cudaMemcpyAsync(s.h_start.p, s.start.p, (size_t)count * 2, cudaMemcpyDeviceToHost, s.stream);
-            cudaMemcpyAsync(s.h_end_cell.p, s.end_cell.p, (size_t)count * 4, cudaMemcpyDeviceToHost, s.stream);
-            cudaMemcpyAsync(s.h_scores.p, s.scores.p, (size_t)count * 2, cudaMemcpyDeviceToHost, s.stream);
-            st.d2h += (int64_t)count * (int64_t)(qb + 8);
+        } else if (moves) {
+            // scores, coordinates, run offsets; the runs themselves for as many as the last chunk had per pair (+ margin)
+            const size_t cap_words = s.cigar.cap / 4;
+            const size_t want = e.est_per_pair > 0 ? (size_t)(e.est_per_pair * 1.05 * count) + 1024 : cap_words;
+            s.sent = std::min(cap_words, std::min(want, (size_t)count * (c.sh.queue_words() + 1)));
+            SHARD_TRY(cudaMemcpyAsync(s.h_run_offs.p, s.run_offs.p, (size_t)(count + 1) * 4, cudaMemcpyDeviceToHost, s.stream));
+            SHARD_TRY(cudaMemcpyAsync(s.h_coords.p, s.coords.p, (size_t)count * 16, cudaMemcpyDeviceToHost, s.stream));
+            SHARD_TRY(cudaMemcpyAsync(s.h_end_cell.p, s.end_cell.p, (size_t)count * 4, cudaMemcpyDeviceToHost, s.stream));
+            SHARD_TRY(cudaMemcpyAsync(s.h_scores.p, s.scores.p, (size_t)count * 2, cudaMemcpyDeviceToHost, s.stream));
+            SHARD_TRY(cudaMemcpyAsync(s.h_cigar.p, s.cigar.p, s.sent * 4, cudaMemcpyDeviceToHost, s.stream));
+            st.d2h += (int64_t)count * 26 + 4 + (int64_t)s.sent * 4;
         } else {
-            cudaMemcpyAsync(s.h_aln_read.p, s.aln_read.p, (size_t)count * L, cudaMemcpyDeviceToHost, s.stream);
-            cudaMemcpyAsync(s.h_aln_ref.p, s.aln_ref.p, (size_t)count * L, cudaMemcpyDeviceToHost, s.stream);
-            cudaMemcpyAsync(s.h_start.p, s.start.p, (size_t)count * 2, cudaMemcpyDeviceToHost, s.stream);
-            cudaMemcpyAsync(s.h_end_cell.p, s.end_cell.p, (size_t)count * 4, cudaMemcpyDeviceToHost, s.stream);
-            st.d2h += (int64_t)count * (2 * L + 6);
+            const size_t cap_bytes = (size_t)count * c.sh.compact_bytes();
+            const size_t want = e.est_per_pair > 0 ? (size_t)(e.est_per_pair * 1.03 * count) + 4096 : cap_bytes;
+            s.sent = std::min(cap_bytes, want);
+            SHARD_TRY(cudaMemcpyAsync(s.h_cursor.p, s.cursor.p, 8, cudaMemcpyDeviceToHost, s.stream));
+            SHARD_TRY(cudaMemcpyAsync(s.h_start.p, s.start.p, (size_t)count * 2, cudaMemcpyDeviceToHost, s.stream));
+            SHARD_TRY(cudaMemcpyAsync(s.h_compact_off.p, s.compact_off.p, (size_t)count * 4, cudaMemcpyDeviceToHost, s.stream));
+            SHARD_TRY(cudaMemcpyAsync(s.h_end_cell.p, s.end_cell.p, (size_t)count * 4, cudaMemcpyDeviceToHost, s.stream));
+            SHARD_TRY(cudaMemcpyAsync(s.h_compact.p, s.compact.p, s.sent, cudaMemcpyDeviceToHost, s.stream));
+            st.d2h += (int64_t)count * 10 + 8 + (int64_t)s.sent;
         }
-        cudaEventRecord(s.ev_done, s.stream);
+        SHARD_TRY(cudaEventRecord(s.ev_done, s.stream));
+        mark("enqueued", first);
         s.first = first;
         s.count = count;
         s.busy = true;
@@ -853,9 +1030,10 @@ void run_shard(va_cuda_ctx *ctx, Engine &e, const HostCall &c, int64_t lo, int64
         if (rc) return fail(rc);
     }
     unsigned long long cells = 0;
-    if (cudaMemcpy(&cells, e.d_cells, sizeof(cells), cudaMemcpyDeviceToHost) == cudaSuccess) st.cells = cells;
-    cudaError_t err = cudaGetLastError();
-    if (err != cudaSuccess) fail(set_error(VA_ERR_DEVICE, "CUDA error after shard: %s", cudaGetErrorString(err)));
+    SHARD_TRY(cudaMemcpy(&cells, e.d_cells, sizeof(cells), cudaMemcpyDeviceToHost));
+    st.cells = cells;
+    SHARD_TRY(cudaGetLastError());
+#undef SHARD_TRY
 }
 
 int pick_chunk_pairs(const Engine &e, const Shape &sh, int64_t shard_pairs) {
@@ -884,6 +1062,19 @@ int run_host_call(va_cuda_ctx *ctx, HostCall &c) {
         const int nd = (int)ctx->engines.size();
         std::vector<ShardStats> stats(nd);
         std::vector<std::thread> threads;
+        std::atomic<int> cancel{0};
+        c.cancel = &cancel;
+        // flat inputs in page-locked memory are read in place by the copy engines
+        if (c.reads_f && !c.reads_p) {
+            const size_t rbytes = c.read_off ? (size_t)(c.read_off[c.n] - c.read_off[0]) : (size_t)c.n * c.sh.read_length;
+            const size_t fbytes = c.ref_off ? (size_t)(c.ref_off[c.n] - c.ref_off[0]) : (size_t)c.n * c.sh.ref_length;
+            c.reads_pinned = host_range_is_pinned(c.reads_f + (c.read_off ? c.read_off[0] : 0), rbytes);
+            c.refs_pinned = host_range_is_pinned(c.refs_f + (c.ref_off ? c.ref_off[0] : 0), fbytes);
+            c.offs_pinned = c.read_off && host_range_is_pinned(c.read_off, (size_t)(c.n + 1) * 8) && host_range_is_pinned(c.ref_off, (size_t)(c.n + 1) * 8);
+            c.sh.stage_reads = !c.reads_pinned;
+            c.sh.stage_refs = !c.refs_pinned;
+            c.sh.stage_offs = !c.offs_pinned;
+        }
         // Contiguous slices per device.  Fixed-stride input: equal pair counts (== equal padded cells).
         // Offset-addressed input knows every length: cut where the running sum of rows x cols crosses
         // k/nd of the total, so mixed-length batches load the devices evenly.
@@ -908,6 +1099,7 @@ int run_host_call(va_cuda_ctx *ctx, HostCall &c) {
             }
         }
         for (auto &th : threads) th.join();
+        c.cancel = nullptr;
         for (auto &s : stats) {
             if (s.rc != VA_OK) {
                 g_last_error = s.err;
@@ -1136,17 +1328,29 @@ int va_cuda_align_flat(va_cuda_ctx *ctx, int opt, int policy, const va_cuda_scor
 }
 
 // ---- batch-friendly entry points: offset-addressed sequences in, scores / coordinates / CIGARs out ----
-static int packed_lengths(int n, const int64_t *read_off, const int64_t *ref_off, int *read_length, int *ref_length) {
-    int64_t rl = 0, fl = 0;
-    for (int i = 0; i < n; ++i) {
-        const int64_t a = read_off[i + 1] - read_off[i], b = ref_off[i + 1] - ref_off[i];
-        if (a < 0 || b < 0) return set_error(VA_ERR_ARG, "offsets of pair %d decrease", i);
-        rl = std::max(rl, a);
-        fl = std::max(fl, b);
-    }
-    if (rl > 32000 || fl > 32000) return set_error(VA_ERR_RANGE, "a sequence is longer than 32000 bases");
-    *read_length = (int)rl;
-    *ref_length = (int)fl;
+static int packed_lengths(va_cuda_ctx *ctx, int n, const int64_t *read_off, const int64_t *ref_off, int *read_length, int *ref_length) {
+    if (!ctx) return set_error(VA_ERR_ARG, "context is null");
+    std::atomic<int64_t> rl{0}, fl{0};
+    std::atomic<int> bad{-1};
+    ctx->pool->parallel_for(n, 1 << 16, [&](int64_t b, int64_t e) {
+        int64_t r = 0, f = 0;
+        for (int64_t i = b; i < e; ++i) {
+            const int64_t a = read_off[i + 1] - read_off[i], c = ref_off[i + 1] - ref_off[i];
+            if (a < 0 || c < 0) bad.store((int)i);
+            r = std::max(r, a);
+            f = std::max(f, c);
+        }
+        int64_t cur = rl.load();
+        while (r > cur && !rl.compare_exchange_weak(cur, r)) {
+        }
+        cur = fl.load();
+        while (f > cur && !fl.compare_exchange_weak(cur, f)) {
+        }
+    });
+    if (bad.load() >= 0) return set_error(VA_ERR_ARG, "offsets of pair %d decrease", bad.load());
+    if (rl.load() > 32000 || fl.load() > 32000) return set_error(VA_ERR_RANGE, "a sequence is longer than 32000 bases");
+    *read_length = (int)rl.load();
+    *ref_length = (int)fl.load();
     return VA_OK;
 }
 
@@ -1155,12 +1359,13 @@ int va_cuda_score_packed(va_cuda_ctx *ctx, int opt, const va_cuda_scoring *sc, i
     if (n < 0) return set_error(VA_ERR_ARG, "n < 0");
     if (n > 0 && (!reads || !refs || !read_off || !ref_off || !scores)) return set_error(VA_ERR_ARG, "null buffer");
     int rl = 0, fl = 0;
-    int rc = packed_lengths(n, read_off, ref_off, &rl, &fl);
+    int rc = packed_lengths(ctx, n, read_off, ref_off, &rl, &fl);
     if (rc) return rc;
     HostCall c;
     bool noop;
     rc = prepare_call(ctx, c, opt, false, 0, sc, n, rl, fl, &noop);
     if (rc || noop) return rc;
+    c.sh.offsets = true;
     c.reads_f = reads;
     c.refs_f = refs;
     c.read_off = read_off;
@@ -1177,13 +1382,14 @@ int va_cuda_align_packed(va_cuda_ctx *ctx, int opt, int policy, const va_cuda_sc
     if (cigar && (!alloc || !cigar_off)) return set_error(VA_ERR_ARG, "cigar output needs alloc and cigar_off");
     if (cigar) *cigar = nullptr;
     int rl = 0, fl = 0;
-    int rc = packed_lengths(n, read_off, ref_off, &rl, &fl);
+    int rc = packed_lengths(ctx, n, read_off, ref_off, &rl, &fl);
     if (rc) return rc;
     HostCall c;
     bool noop;
     rc = prepare_call(ctx, c, opt, true, policy, sc, n, rl, fl, &noop);
     if (rc || noop) return rc;
     c.sh.moves = true;
+    c.sh.offsets = true;
     c.reads_f = reads;
     c.refs_f = refs;
     c.read_off = read_off;
@@ -1193,24 +1399,35 @@ int va_cuda_align_packed(va_cuda_ctx *ctx, int opt, int policy, const va_cuda_sc
     c.cigar_off = cigar_off;
     std::vector<CigarPart> parts;
     std::mutex mu;
-    if (cigar) {
+    if (cigar || cigar_off) {
         c.cigar_parts = &parts;
         c.cigar_mu = &mu;
     }
     if (cigar_off) cigar_off[0] = 0;
     rc = run_host_call(ctx, c);
     if (rc) return rc;
+    // every chunk left its pairs' offsets relative to its own first run: line the chunks up in pair order
+    std::sort(parts.begin(), parts.end(), [](const CigarPart &a, const CigarPart &b) { return a.first < b.first; });
+    std::vector<int64_t> base(parts.size() + 1, 0);
+    for (size_t k = 0; k < parts.size(); ++k) base[k + 1] = base[k] + (int64_t)parts[k].words;
     if (cigar_off) {
-        for (int i = 0; i < n; ++i) cigar_off[i + 1] += cigar_off[i];  // per-pair counts -> offsets
+        for (size_t k = 1; k < parts.size(); ++k) {  // chunk 0 starts at run 0 already
+            int64_t *o = cigar_off + parts[k].first + 1;
+            const int64_t add = base[k];
+            ctx->pool->parallel_for(parts[k].count, 1 << 16, [&](int64_t b, int64_t e) {
+                for (int64_t i = b; i < e; ++i) o[i] += add;
+            });
+        }
     }
     if (cigar) {
-        const int64_t total = cigar_off[n];
+        const int64_t total = base[parts.size()];
         uint32_t *out = (uint32_t *)alloc((size_t)std::max<int64_t>(total, 1) * sizeof(uint32_t), user);
         if (!out) return set_error(VA_ERR_MEMORY, "the caller's allocator returned NULL");
-        ctx->pool->parallel_for((int64_t)parts.size(), 1, [&](int64_t b, int64_t e) {
-            for (int64_t k = b; k < e; ++k)
-                if (parts[k].words) memcpy(out + cigar_off[parts[k].first], parts[k].data.get(), parts[k].words * sizeof(uint32_t));
-        });
+        for (size_t k = 0; k < parts.size(); ++k) {
+            const uint32_t *src = parts[k].data.get();
+            uint32_t *dst = out + base[k];
+            ctx->pool->parallel_for((int64_t)parts[k].words, 1 << 18, [&](int64_t b, int64_t e) { memcpy(dst + b, src + b, (size_t)(e - b) * 4); });
+        }
         *cigar = out;
     }
     return VA_OK;
@@ -1220,7 +1437,8 @@ int va_cuda_max_resident_pairs(va_cuda_ctx *ctx, int align, int read_length, int
     if (!ctx || !max_n) return set_error(VA_ERR_ARG, "null argument");
     const Shape sh = make_shape(read_length, ref_length, align != 0);
     const Engine &e = ctx->engines[0];
-    const size_t budget = std::min<size_t>(e.total_mem / 2, (size_t)80 << 30);
+    // (an align sub-chunk's direction region stays below 2^32 eight-byte words: the traceback walk's offsets are 32-bit)
+    const size_t budget = std::min<size_t>(e.total_mem / 2, align ? (size_t)30 << 30 : (size_t)80 << 30);
     *max_n = (int64_t)(budget / std::max<size_t>(sh.per_pair_workspace(), 1));
     return VA_OK;
 }
@@ -1234,12 +1452,14 @@ static int resident_call(va_cuda_ctx *ctx, int opt, bool align, int policy, cons
     if (rc || noop) return rc;
     if (n == 0) return VA_OK;
     if (!d_reads || !d_refs) return set_error(VA_ERR_ARG, "null device buffer");
+    // the resident workspace, the side stream and the profiling events are shared by all calls on the context
+    std::lock_guard<std::mutex> lk(ctx->call_mu);
     Engine &e = ctx->engines[0];
     CUDA_TRY(cudaSetDevice(e.device));
     int64_t max_n = 0;
     va_cuda_max_resident_pairs(ctx, align, read_length, ref_length, &max_n);
     const int sub = (int)std::min<int64_t>(n, std::max<int64_t>(64, max_n / 64 * 64));
-    rc = reserve_slot(e.resident, c.sh, sub, false);
+    rc = reserve_slot(e.resident, c.sh, sub, SLOT_RESIDENT);
     if (rc) return rc;
     ChunkSlot &ws = e.resident;
     // outputs the caller did not ask for still need somewhere to go
@@ -1255,14 +1475,18 @@ static int resident_call(va_cuda_ctx *ctx, int opt, bool align, int policy, cons
     e.prof_used = 0;
     for (int64_t first = 0; first < n; first += sub) {
         const int count = (int)std::min<int64_t>(sub, n - first);
-        int16_t *scores = d_scores ? (int16_t *)d_scores + first : (int16_t *)ws.scores.p + first;
-        int16_t *endc = d_end_cell ? (int16_t *)d_end_cell + 2 * first : (int16_t *)ws.end_cell.p + (align ? 2 * first : 0);
-        int k = enqueue_device_work(e, ws, c.sh, c.mode, c.policy, c.sc, count,
-                                    (const uint8_t *)d_reads + first * read_length,
-                                    (const uint8_t *)d_refs + first * ref_length, scores, endc,
-                                    align ? (uint8_t *)d_aln_read + first * L : nullptr,
-                                    align ? (uint8_t *)d_aln_ref + first * L : nullptr,
-                                    align ? (int16_t *)d_start + first : nullptr, true, st, e.profiling);
+        DeviceIO io;
+        io.raw_reads = (const uint8_t *)d_reads + first * read_length;
+        io.raw_refs = (const uint8_t *)d_refs + first * ref_length;
+        io.scores = d_scores ? (int16_t *)d_scores + first : (int16_t *)ws.scores.p + first;
+        io.end_cell = d_end_cell ? (int16_t *)d_end_cell + 2 * first : (int16_t *)ws.end_cell.p + (align ? 2 * first : 0);
+        if (align) {
+            io.aln_read = (uint8_t *)d_aln_read + first * L;
+            io.aln_ref = (uint8_t *)d_aln_ref + first * L;
+            io.start = (int16_t *)d_start + first;
+            io.zero_prefix = true;
+        }
+        int k = enqueue_device_work(e, ws, c.sh, c.mode, c.policy, c.sc, count, io, st, e.profiling);
         if (k < 0) return k;
         launches += k;
     }
@@ -1294,6 +1518,7 @@ int va_cuda_set_profiling(va_cuda_ctx *ctx, int on) {
 
 int va_cuda_get_kernel_ms(va_cuda_ctx *ctx, float ms[3]) {
     if (!ctx || !ms) return set_error(VA_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->call_mu);
     Engine &e = ctx->engines[0];
     ms[0] = ms[1] = ms[2] = 0.f;
     for (size_t k = 0; k + 4 <= e.prof_used; k += 4) {
@@ -1310,6 +1535,7 @@ int va_cuda_get_kernel_ms(va_cuda_ctx *ctx, float ms[3]) {
 int va_cuda_int_peak(va_cuda_ctx *ctx, int kind, double *lane_ops_per_s, void *stream) {
     if (!ctx || !lane_ops_per_s) return set_error(VA_ERR_ARG, "null argument");
     if (kind < 0 || kind > 3) return set_error(VA_ERR_ARG, "kind must be 0..3");
+    std::lock_guard<std::mutex> lk(ctx->call_mu);
     Engine &e = ctx->engines[0];
     CUDA_TRY(cudaSetDevice(e.device));
     cudaStream_t st = (cudaStream_t)stream;

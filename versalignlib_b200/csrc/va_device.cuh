@@ -17,5 +17,14 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     return r;
 }
 
+// Start of raw sequence `pair`: fixed stride, or through the caller's offsets (packed entry points).
+__device__ __forceinline__ const uint8_t *seq_ptr(const uint8_t *raw, const int64_t *off, int pair, int stride) {
+    return off ? raw + (off[pair] - off[0]) : raw + (size_t)pair * (size_t)stride;
+}
+// One past the last byte of the whole raw buffer of an n-pair chunk.
+__device__ __forceinline__ const uint8_t *seq_end(const uint8_t *raw, const int64_t *off, int n, int stride) {
+    return off ? raw + (off[n] - off[0]) : raw + (size_t)n * (size_t)stride;
+}
+
 }  // namespace va
 #endif

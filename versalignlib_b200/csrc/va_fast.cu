@@ -392,21 +392,23 @@ bool fast_scoring_ok(int mode, int policy, const Scoring &sc, int read_length, i
     if (align && policy != 0) return false;  // SSE/AVX pointer rule: general kernel
     int mx = 1;
     for (int v : {sc.match, sc.mismatch, sc.gap_read, sc.gap_ref}) mx = max(mx, v < 0 ? -v : v);
+    // the most one diagonal step can add: a "mismatch" score above the match score counts too
+    const long long gain = max(max(sc.match, sc.mismatch), 0);
+    const long long min_len = read_length < ref_length ? read_length : ref_length;
     if (mode == MODE_NW_SCORE || mode == MODE_NW_ALIGN) {
         // shifted recurrence (va_nw.cu): gap scores <= 0, table entries s - gap_ref - gap_read, and
-        // 0 <= V <= match*min(rows,cols) + |gap_ref|*rows + |gap_read|*cols
+        // 0 <= V <= gain*min(rows,cols) + |gap_ref|*rows + |gap_read|*cols
         if (sc.gap_read > 0 || sc.gap_ref > 0) return false;
         const int off = sc.gap_ref + sc.gap_read;
         if (!fits8(sc.match - off) || !fits8(sc.mismatch - off) || !fits8(-off)) return false;
-        const long long top = (long long)(sc.match > 0 ? sc.match : 0) * (read_length < ref_length ? read_length : ref_length) -
-                              (long long)sc.gap_ref * (read_length + 2) - (long long)sc.gap_read * (ref_length + 2);
+        const long long top = gain * min_len - (long long)sc.gap_ref * (read_length + 2) - (long long)sc.gap_read * (ref_length + 2);
         return top + 256 <= 32000;
     }
     if (sc.gap_read > 0 || sc.gap_ref > 0) return false;  // the columns past n of a partial strip rely on it
     const int off = align ? sc.gap_ref : 0;
     if (!fits8(sc.match - off) || !fits8(sc.mismatch - off) || !fits8(-off)) return false;
-    // every cell is floored at 0: values stay within [-mx, match * min(rows, cols)]
-    const long long top = (long long)(sc.match > 0 ? sc.match : 0) * (read_length < ref_length ? read_length : ref_length);
+    // every cell is floored at 0: values stay within [-mx, gain * min(rows, cols)]
+    const long long top = gain * min_len;
     // SW align packs (value + bias) * 32 + column into a 16-bit lane: value + 128 + gap must stay below 1024
     if (mode == MODE_SW_ALIGN) return top + 2 * 128 < 1024 && mx <= 100;
     return top + mx <= 32000 && mx <= 8000;

@@ -67,8 +67,12 @@ struct FastConsts {
 };
 
 struct ChunkBuffers {
-    const uint8_t *raw_reads;  // [n][read_length]
+    const uint8_t *raw_reads;  // [n][read_length], or -- with read_off -- the chunk's sequences back to back
     const uint8_t *raw_refs;   // [n][ref_length]
+    // offset-addressed input (packed entry points): sequence i = raw_reads + (read_off[i] - read_off[0]), length
+    // read_off[i+1] - read_off[i] <= read_length; n+1 entries, the caller's own offsets (any base).  NULL = fixed stride.
+    const int64_t *read_off;
+    const int64_t *ref_off;
     uint4 *code_reads;         // [read_chunks][slots]
     uint4 *code_refs;          // [ref_chunks][slots]
     uint4 *row_idx;            // [read_chunks][duos]: per sweep row 7*code(slot 2u) + code(slot 2u+1), 16 rows per word
@@ -93,6 +97,15 @@ struct ChunkBuffers {
     uint32_t *moves_out;       // when set: the traceback stops after the walk and leaves pair i's moves at
                                // moves_out[i * (queue_words + 1) ..): CIGAR runs in walk order or the raw 2-bit queue
                                // (va_traceback.cu); start[i] = L - 1 - moves as usual, aln_read / aln_ref are not written
+    // packed entry points, beside moves_out (all optional)
+    int32_t *coords;           // [n][4] aligned region in sequence coordinates: read_begin, read_end, ref_begin, ref_end
+    uint32_t *run_count;       // [n] CIGAR runs of the pair (also of pairs whose moves left as the raw queue)
+    // compact string output (host pipeline of the legacy boundary): when aln_compact is set the two strings of pair i,
+    // each NUL terminated, (moves + 1) bytes, lie back to back at aln_compact + compact_off[i]; *compact_cursor
+    // (zeroed by the caller) ends up as the bytes used.  aln_read / aln_ref are not written then.
+    uint8_t *aln_compact;
+    uint32_t *compact_off;
+    unsigned long long *compact_cursor;
     unsigned long long *cell_count;  // device counter: DP cells computed
 };
 
@@ -118,6 +131,11 @@ size_t traceback_queue_words(int read_length, int ref_length);
 bool traceback_needs_global_queue(int read_length, int ref_length);
 int launch_traceback(const ChunkGeom &g, const ChunkBuffers &b, int mode, const Scoring &sc, uint32_t *global_queue,
                      cudaStream_t stream);
+// packed entry points: per-pair CIGAR runs (walk order, fixed slots) -> one forward-order block (va_traceback.cu).
+// run_count has n+1 entries (the last one 0); run_offs receives its exclusive prefix sum (run_offs[n] = total runs).
+size_t cigar_compact_scratch_bytes(int n);
+int launch_cigar_compact(int n, int queue_words, const uint32_t *moves, const uint32_t *run_count, uint32_t *run_offs,
+                         uint32_t *cigar_out, size_t out_cap_words, void *scratch, size_t scratch_bytes, cudaStream_t stream);
 int launch_int_peak(int kind, int sm_count, int iters, unsigned int *sink, cudaStream_t stream, double *lane_ops);
 
 }  // namespace va

@@ -44,12 +44,15 @@ struct SeqScan {
 // shared-memory look-up per byte, and one coalesced uint4 store of 16 codes to the pair-interleaved
 // scratch array codes[chunk][pair].  Bytes past L become OTHER.
 __device__ __forceinline__ SeqScan scan_sequence(const uint8_t *__restrict__ raw, int L, int chunks, uint4 *__restrict__ codes,
-                                                 size_t chunk_stride, const uint8_t *lut, bool last_pair) {
+                                                 size_t chunk_stride, const uint8_t *lut, const uint8_t *buf_end) {
     SeqScan s{-1, L, L, 0};
     const uintptr_t addr = reinterpret_cast<uintptr_t>(raw);
     const uint32_t *words = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
     const int shift = (int)(addr & 3) * 8;
-    const int nwords_safe = last_pair ? 0 : (L + 3) / 4;  // the last pair of the buffer reads byte-wise: no overrun
+    // Word wi of the sequence is funnel-shifted out of words[wi] and words[wi + 1]: the word path is taken only
+    // while words[wi + 1] lies wholly inside the raw buffer (it ends at buf_end); the tail reads byte-wise.
+    const long long whole = ((long long)(reinterpret_cast<uintptr_t>(buf_end) - reinterpret_cast<uintptr_t>(words)) >> 2) - 1;
+    const int nwords_safe = (int)max(0LL, min((long long)((L + 3) / 4), whole));
     uint32_t carry = nwords_safe ? words[0] : 0;
     for (int c = 0; c < chunks; ++c) {
         uint32_t out[4];
@@ -108,7 +111,8 @@ __device__ __forceinline__ SeqScan scan_sequence(const uint8_t *__restrict__ raw
 }
 
 __global__ void __launch_bounds__(128) meta_kernel(ChunkGeom g, const uint8_t *__restrict__ raw_reads,
-                                                   const uint8_t *__restrict__ raw_refs, PairMeta *__restrict__ meta_pair,
+                                                   const uint8_t *__restrict__ raw_refs, const int64_t *__restrict__ read_off,
+                                                   const int64_t *__restrict__ ref_off, PairMeta *__restrict__ meta_pair,
                                                    uint4 *__restrict__ codes_pair_reads, uint4 *__restrict__ codes_pair_refs,
                                                    uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, int mode,
                                                    int policy, int trim, int key_row_bits) {
@@ -118,11 +122,14 @@ __global__ void __launch_bounds__(128) meta_kernel(ChunkGeom g, const uint8_t *_
     const int pair = blockIdx.x * blockDim.x + threadIdx.x;
     if (pair >= g.n) return;
     {
-        const bool last_pair = pair == g.n - 1;
-        const SeqScan rd = scan_sequence(raw_reads + (size_t)pair * g.read_length, g.read_length, g.read_chunks,
-                                         codes_pair_reads + pair, (size_t)g.slots, lut, last_pair);
-        const SeqScan rf = scan_sequence(raw_refs + (size_t)pair * g.ref_length, g.ref_length, g.ref_chunks,
-                                         codes_pair_refs + pair, (size_t)g.slots, lut, last_pair);
+        // offset-addressed sequences carry their own lengths; bytes past them count as the '\0' pad of the
+        // fixed-stride layout (code OTHER)
+        const int read_len = read_off ? (int)(read_off[pair + 1] - read_off[pair]) : g.read_length;
+        const int ref_len = ref_off ? (int)(ref_off[pair + 1] - ref_off[pair]) : g.ref_length;
+        const SeqScan rd = scan_sequence(seq_ptr(raw_reads, read_off, pair, g.read_length), read_len, g.read_chunks,
+                                   codes_pair_reads + pair, (size_t)g.slots, lut, seq_end(raw_reads, read_off, g.n, g.read_length));
+        const SeqScan rf = scan_sequence(seq_ptr(raw_refs, ref_off, pair, g.ref_length), ref_len, g.ref_chunks,
+                                   codes_pair_refs + pair, (size_t)g.slots, lut, seq_end(raw_refs, ref_off, g.n, g.ref_length));
         PairMeta m;
         m.true_rows = (int16_t)(rd.last_acgt + 1);
         m.true_cols = (int16_t)(rf.last_acgt + 1);
@@ -282,7 +289,7 @@ int launch_prep(const ChunkGeom &g, const ChunkBuffers &b, int mode, int policy,
     const int grid_cap = 148 * 8;
     const int meta_blocks = (g.n + 127) / 128;
     const dim3 enc_blocks((unsigned)std::min((g.slots + threads - 1) / threads, grid_cap * 4), (unsigned)std::max(1, g.read_chunks + g.ref_chunks));  // y >= 1: chunk 0 also moves the meta records
-    meta_kernel<<<meta_blocks, 128, 0, stream>>>(g, b.raw_reads, b.raw_refs, meta_pair, codes_reads, codes_refs, keys_in,
+    meta_kernel<<<meta_blocks, 128, 0, stream>>>(g, b.raw_reads, b.raw_refs, b.read_off, b.ref_off, meta_pair, codes_reads, codes_refs, keys_in,
                                                      vals_in, mode, policy, trim, row_bits);
     // only the bits that can differ are sorted: rows, cols and the "dirty" flag above them
     cub::DeviceRadixSort::SortPairs(p, temp_bytes, keys_in, keys_out, vals_in, vals_out, g.n, 0, row_bits + 16, stream);

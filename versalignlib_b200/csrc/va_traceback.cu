@@ -4,14 +4,25 @@
 // alignment_kernels.cl:146-192,370-414).
 //
 // Two phases, so that the only dependent chain through HBM is the walk:
-//   walk  one thread per pair: follow the pointers from the end cell to START, one direction word per
-//         step (L2/HBM latency bound, hidden by occupancy); the moves go into a per-thread 2-bit queue
-//         in shared memory (global memory when the sequences are too long for that);
+//   walk  one thread per pair: follow the pointers from the end cell to START (L2/HBM latency hidden by
+//         occupancy); the moves go into a per-thread 2-bit queue in shared memory (global memory when the
+//         sequences are too long for that).  The walk over the packed kernels' bit planes is written for
+//         instruction count -- the kernel is issue bound, not latency bound: one 8-byte load per matrix
+//         row (the row's DIAG and UP planes of 16 columns x both lanes), moves derived from the two bits
+//         without branches, the slow path (leaving a 16-column group / a strip) out of line;
 //   emit  one warp per pair, 32 moves per step: replay the queue, fetch the read/ref bytes it names
 //         and write both strings backwards -- consecutive lanes, consecutive bytes.
+// Three result containers:
+//   strings, fixed stride    aln_read / aln_ref [pair][L], right aligned (the reference's layout)
+//   strings, compact         (host pipeline of the legacy boundary) each pair's two strings back to back,
+//                            NUL terminated, at an offset handed out by one atomic per block: half the
+//                            D2H bytes of the fixed-stride layout and nothing for the host to skip over
+//   moves                    (packed entry points) CIGAR runs / raw 2-bit moves + sequence coordinates
 // The packed NW fill kernel leaves the end-cell decision (arg-max of the last valid row,
-// DefaultKernel.cpp:352-355,381-387) to this kernel: `hrow` holds that row.
+// DefaultKernel.cpp:352-355,381-387) to this kernel: `hrow` holds that row's per-strip keys.
 #include <climits>
+
+#include <cub/device/device_scan.cuh>
 
 #include "va_fast.cuh"
 
@@ -59,11 +70,16 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
                                                                int queue_words) {
     const int gap_ref = sc.gap_ref;
     extern __shared__ uint32_t sq[];
-    __shared__ int s_moves[TB_THREADS], s_end_i[TB_THREADS], s_end_j[TB_THREADS], s_pair[TB_THREADS];
+    __shared__ int s_moves[TB_THREADS], s_pair[TB_THREADS];
+    __shared__ const uint8_t *s_rd[TB_THREADS], *s_rf[TB_THREADS];  // the bases the first move of each pair reads
+    __shared__ unsigned long long s_base;
+    __shared__ uint32_t s_warp_sum[TB_THREADS / 32];
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     const bool moves_only = b.moves_out != nullptr;
+    const bool compact = b.aln_compact != nullptr;
     const int L = g.read_length + g.ref_length;
     s_moves[threadIdx.x] = -1;
+    int my_moves = -1;
     if (slot < g.n) {
     MoveQueue mq;
     if (moves_only) {  // set below: the result region of the pair
@@ -125,10 +141,14 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
 
     // ---- walk ----------------------------------------------------------------------------
     // One walk from the end cell to START; every move goes to `sink(code, t)` (t = moves so far).
+    // final_i / final_j: the cell the walk stopped in (0-based sequence coordinates, -1 = matrix row / column 0)
+    int final_i = end_i, final_j = end_j;
     auto walk = [&](auto &&sink) -> int {
         int i = end_i, j = end_j;
         int n_moves = 0;
         if (packed) {
+            // The packed kernels' direction words: uint4 per (strip, ROW PAIR, group of 16 columns, duo), viewed
+            // here as two uint2 halves (even row, odd row): .x = DIAG plane, .y = UP plane, low 16 bits lane A.
             const int tw = g.fast_tw, ng = fast_groups(tw);
             int strip = j >= 0 ? j / tw : 0, k = j >= 0 ? j - strip * tw : 0;
             // NW: a partial last strip keeps its true columns in the LAST registers of the strip (va_nw.cu)
@@ -137,58 +157,69 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
                 kmin = tw - (cols - strip * tw);
                 k += kmin;
             }
-            const size_t pair_step = (size_t)ng * g.duos, strip_step = (size_t)fast_row_pairs(g) * pair_step;
-            const uint4 *p = b.fdirs + (size_t)strip * strip_step + (size_t)((max(i, 0) + row_off) >> 1) * pair_step + duo;
-            int have_pair = -1, have_strip = -1, have_grp = -1;
-            uint4 w = make_uint4(0, 0, 0, 0);
-            // SW: the packed fill stores the pointer a cell would have in NW; a cell whose value is 0 is
-            // START (DefaultKernel.cpp:240-241).  The value is known along the path: it starts at the best
-            // score and every move gives back what it added.
-            int hval = NW ? 1 : (int)b.scores[pair];
-            ByteWindow wread(b.raw_reads + (size_t)pair * g.read_length, b.raw_reads + (size_t)g.n * g.read_length);
-            ByteWindow wref(b.raw_refs + (size_t)pair * g.ref_length, b.raw_refs + (size_t)g.n * g.ref_length);
-            while (true) {
-                int code;
-                if (i < 0 || i >= rows || j >= cols) code = DIR_START;
-                else if (j < 0) code = NW ? DIR_UP : DIR_START;  // matrix column 0 (DefaultKernel.cpp:304)
-                else if (!NW && hval <= 0) code = DIR_START;
-                else {
-                    const int grp = k >> 4;
-                    const int si = i + row_off;  // sweep row: where the fill kernel stored this matrix row
-                    if ((si >> 1) != have_pair || strip != have_strip || grp != have_grp) {
-                        w = p[(size_t)grp * g.duos];  // two rows x 16 columns x both lanes
-                        have_pair = si >> 1;
-                        have_strip = strip;
-                        have_grp = grp;
+            const bool in_range = i >= 0 && i < rows && j < cols;
+            if (in_range && j >= 0 && (NW || (int)b.scores[pair] > 0)) {
+                // 32-bit offsets in uint2 units (the host keeps a chunk's direction region below 2^32 of them)
+                const uint32_t group_step2 = 2u * (uint32_t)g.duos;                      // next group
+                const uint32_t pair_step2 = (uint32_t)ng * group_step2;                  // next row pair
+                const uint32_t strip_step2 = (uint32_t)fast_row_pairs(g) * pair_step2;   // next strip
+                int si = i + row_off;  // sweep row: where the fill kernel stored this matrix row
+                const uint2 *base2 = reinterpret_cast<const uint2 *>(b.fdirs) + 2 * (size_t)duo;
+                uint32_t off = (uint32_t)strip * strip_step2 + (uint32_t)(si >> 1) * pair_step2 + (uint32_t)(k >> 4) * group_step2 + (uint32_t)(si & 1);
+                const uint32_t up_even = pair_step2 - 1u;  // from an even sweep row to the odd row above it
+                const uint32_t strip_back = strip_step2 - (uint32_t)((tw - 1) >> 4) * group_step2;  // to the last group of the strip before
+                int bit = lane_shift + (k & 15);
+                uint2 w = __ldg(base2 + off);
+                // SW: the packed fill stores the pointer a cell would have in NW; a cell whose value is 0 is
+                // START (DefaultKernel.cpp:240-241).  The value is known along the path: it starts at the best
+                // score and every move gives back what it added.
+                int hval = NW ? 1 : (int)b.scores[pair];
+                ByteWindow wread(seq_ptr(b.raw_reads, b.read_off, pair, g.read_length), seq_end(b.raw_reads, b.read_off, g.n, g.read_length));
+                ByteWindow wref(seq_ptr(b.raw_refs, b.ref_off, pair, g.ref_length), seq_end(b.raw_refs, b.ref_off, g.n, g.ref_length));
+                while (true) {
+                    const uint32_t dbit = (w.x >> bit) & 1u, ubit = (w.y >> bit) & 1u;
+                    const int code = dbit ? DIR_DIAG : (ubit ? DIR_UP : DIR_LEFT);
+                    sink(code, n_moves);
+                    ++n_moves;
+                    if (!NW) {
+                        if (code == DIR_UP) hval -= sc.gap_ref;
+                        else if (code == DIR_LEFT) hval -= sc.gap_read;
+                        else {
+                            const unsigned ca = wread.get(i) & 0xDFu, cb = wref.get(j) & 0xDFu;
+                            const bool va = ca == 'A' || ca == 'C' || ca == 'G' || ca == 'T', vb = cb == 'A' || cb == 'C' || cb == 'G' || cb == 'T';
+                            hval -= (va && vb) ? (ca == cb ? sc.match : sc.mismatch) : 0;
+                        }
                     }
-                    const int bit = lane_shift + (k & 15);
-                    const uint32_t diag_plane = (si & 1) ? w.z : w.x, up_plane = (si & 1) ? w.w : w.y;
-                    code = ((diag_plane >> bit) & 1) ? DIR_DIAG : (((up_plane >> bit) & 1) ? DIR_UP : DIR_LEFT);
-                }
-                if (code == DIR_START) break;
-                sink(code, n_moves);
-                ++n_moves;
-                if (!NW) {
-                    if (code == DIR_UP) hval -= sc.gap_ref;
-                    else if (code == DIR_LEFT) hval -= sc.gap_read;
-                    else {
-                        const unsigned ca = wread.get(i) & 0xDFu, cb = wref.get(j) & 0xDFu;
-                        const bool va = ca == 'A' || ca == 'C' || ca == 'G' || ca == 'T', vb = cb == 'A' || cb == 'C' || cb == 'G' || cb == 'T';
-                        hval -= (va && vb) ? (ca == cb ? sc.match : sc.mismatch) : 0;
+                    if (code != DIR_LEFT) {  // one matrix row up
+                        off -= (si & 1) ? 1u : up_even;
+                        --si;
+                        --i;
                     }
-                }
-                if (code != DIR_LEFT) {
-                    if (((i + row_off) & 1) == 0) p -= pair_step;  // leaving an even sweep row: the row above is in the previous word
-                    --i;
-                }
-                if (code != DIR_UP) {
-                    --j;
-                    if (--k < kmin) {
-                        k = tw - 1;
-                        kmin = 0;
-                        --strip;
-                        p -= strip_step;
+                    if (code != DIR_UP) {  // one column left
+                        --j;
+                        if (k == kmin) {  // leaving the strip
+                            kmin = 0;
+                            off -= strip_back + (uint32_t)(k >> 4) * group_step2;
+                            k = tw - 1;
+                            bit = lane_shift + (k & 15);
+                        } else {
+                            if ((k & 15) == 0) {  // leaving the 16-column group
+                                off -= group_step2;
+                                bit += 16;
+                            }
+                            --k;
+                            --bit;
+                        }
                     }
+                    if ((i | j) < 0 || (!NW && hval <= 0)) break;
+                    w = __ldg(base2 + off);
+                }
+            }
+            // matrix column 0 (DefaultKernel.cpp:304): NW walks up to row 0, SW stops
+            if (NW && i >= 0 && i < rows && j < 0) {
+                for (; i >= 0; --i) {
+                    sink(DIR_UP, n_moves);
+                    ++n_moves;
                 }
             }
         } else {
@@ -204,14 +235,18 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
                 if (code != DIR_UP) --j;
             }
         }
+        final_i = i;
+        final_j = j;
         return n_moves;
     };
     // 2-bit queue sink: 16 moves per word
     uint32_t acc = 0;
+    uint32_t *qcur = mq.q;  // where the word being filled goes
     auto queue_sink = [&](int code, int t) {
         acc |= (uint32_t)code << (2 * (t & 15));
         if ((t & 15) == 15) {
-            mq.q[(size_t)(t >> 4) * mq.stride] = acc;
+            *qcur = acc;
+            qcur += mq.stride;
             acc = 0;
         }
     };
@@ -243,50 +278,91 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
         if (nruns <= queue_words) {
             out[0] = (uint32_t)nruns;
         } else {
-            mq.q = out + 1;
+            mq.q = qcur = out + 1;
             mq.stride = 1;
             n_moves = walk(queue_sink);
-            if (n_moves & 15) mq.q[(size_t)(n_moves >> 4)] = acc;
+            if (n_moves & 15) *qcur = acc;
             out[0] = 0x80000000u | (uint32_t)n_moves;
         }
+        if (b.coords) {  // aligned region in sequence coordinates, 0-based, half open
+            int32_t *co = b.coords + 4 * (size_t)pair;
+            co[0] = final_i + 1;
+            co[1] = end_i + 1;
+            co[2] = final_j + 1;
+            co[3] = end_j + 1;
+        }
+        if (b.run_count) b.run_count[pair] = (uint32_t)nruns;
     } else {
         n_moves = walk(queue_sink);
-        if (n_moves & 15) mq.q[(size_t)(n_moves >> 4) * mq.stride] = acc;
+        if (n_moves & 15) *qcur = acc;
     }
 
     if (moves_only) {
         b.start[pair] = (int16_t)(L - 1 - n_moves);
     } else {
+        my_moves = n_moves;
         s_moves[threadIdx.x] = n_moves;
-        s_end_i[threadIdx.x] = end_i;
-        s_end_j[threadIdx.x] = end_j;
+        s_rd[threadIdx.x] = seq_ptr(b.raw_reads, b.read_off, pair, g.read_length) + end_i;
+        s_rf[threadIdx.x] = seq_ptr(b.raw_refs, b.ref_off, pair, g.ref_length) + end_j;
         s_pair[threadIdx.x] = pair;
     }
     }  // slot < g.n
     if (moves_only) return;
-    __syncthreads();
+    // compact strings: this block's pairs take one contiguous piece of the output, 2 * (moves + 1) bytes each
+    __shared__ uint32_t s_off[TB_THREADS];
+    if (compact) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const uint32_t bytes = my_moves >= 0 ? 2u * (uint32_t)(my_moves + 1) : 0u;
+        uint32_t incl = bytes;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) s_warp_sum[warp] = incl;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t total = 0;
+            for (int wv = 0; wv < TB_THREADS / 32; ++wv) {
+                const uint32_t v = s_warp_sum[wv];
+                s_warp_sum[wv] = total;
+                total += v;
+            }
+            s_base = atomicAdd(b.compact_cursor, (unsigned long long)total);
+        }
+        __syncthreads();
+        const uint32_t rel = s_warp_sum[warp] + (incl - bytes);  // offset inside the block's piece
+        s_off[threadIdx.x] = rel;
+        if (my_moves >= 0) b.compact_off[s_pair[threadIdx.x]] = (uint32_t)(s_base + rel);
+        __syncwarp();
+    } else {
+        __syncthreads();
+    }
 
     // ---- emit ----------------------------------------------------------------------------
     // Warp-cooperative: the walks of the block are done, their move queues sit in shared (or global)
     // memory.  Each warp replays the queues of its 32 threads one pair at a time, 32 moves per step: lane l
     // takes move t0+l, two ballots give every lane how many read / ref bases the moves before it consumed,
     // so consecutive lanes fetch consecutive bases and write consecutive bytes of both gapped strings --
-    // every load and store of the step is one or two sectors.  (One thread per pair wrote its two strings
-    // with scattered 16-byte stores and spent most of the kernel doing so.)
+    // every load and store of the step is one or two sectors.
     const int lane = threadIdx.x & 31, warp_first = threadIdx.x & ~31;
     const unsigned lt_mask = (1u << lane) - 1u;
     for (int q = warp_first; q < warp_first + 32; ++q) {
         const int n_moves = s_moves[q];
         if (n_moves < 0) continue;  // past the end of the chunk
         const int pair = s_pair[q];
-        const int end_i = s_end_i[q], end_j = s_end_j[q];
         const uint32_t *qq = gq ? gq + (blockIdx.x * blockDim.x + q) : sq + q;
         const size_t qstride = gq ? (size_t)g.slots : (size_t)TB_THREADS;
-        const uint8_t *rd = b.raw_reads + (size_t)pair * g.read_length;
-        const uint8_t *rf = b.raw_refs + (size_t)pair * g.ref_length;
-        uint8_t *oa = b.aln_read + (size_t)pair * L;
-        uint8_t *ob = b.aln_ref + (size_t)pair * L;
-        int used_r = 0, used_f = 0;  // bases consumed by the moves before this step
+        // cursors: the base this step's first move reads / the NUL byte behind each string (move t goes to [-1 - t])
+        const uint8_t *rd = s_rd[q], *rf = s_rf[q];
+        uint8_t *oa, *ob;
+        if (compact) {
+            oa = b.aln_compact + (size_t)(s_base + s_off[q]) + n_moves;
+            ob = oa + n_moves + 1;
+        } else {
+            oa = b.aln_read + (size_t)pair * L + (L - 1);
+            ob = b.aln_ref + (size_t)pair * L + (L - 1);
+        }
         for (int t0 = 0; t0 < n_moves; t0 += 32) {
             const int t = t0 + lane;
             const bool valid = t < n_moves;
@@ -295,35 +371,82 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
             const bool takes_r = valid && code != DIR_LEFT, takes_f = valid && code != DIR_UP;
             const unsigned mr = __ballot_sync(0xffffffffu, takes_r), mf = __ballot_sync(0xffffffffu, takes_f);
             uint8_t a = '-', c = '-';
-            if (takes_r) a = rd[end_i - used_r - __popc(mr & lt_mask)];
-            if (takes_f) c = rf[end_j - used_f - __popc(mf & lt_mask)];
-            const int pos = L - 2 - t;
-            if (valid && pos >= 0) {
-                oa[pos] = a;
-                ob[pos] = c;
+            if (takes_r) a = *(rd - __popc(mr & lt_mask));
+            if (takes_f) c = *(rf - __popc(mf & lt_mask));
+            // fixed stride: a walk longer than L - 1 moves (only when every move is a gap) is cut at the block start
+            if (valid && (compact || t <= L - 2)) {
+                oa[-1 - t] = a;
+                ob[-1 - t] = c;
             }
-            used_r += __popc(mr);
-            used_f += __popc(mf);
+            rd -= __popc(mr);
+            rf -= __popc(mf);
         }
         if (lane == 0) {
             // start may be negative only when every move was a gap (never with gap scores < 0)
             b.start[pair] = (int16_t)(L - 1 - n_moves);
-            if (L >= 1) {
-                oa[L - 1] = 0;
-                ob[L - 1] = 0;
+            if (compact || L >= 1) {
+                *oa = 0;
+                *ob = 0;
             }
         }
     }
 }
 
+// Packed entry points: pair i's runs leave the traceback in walk order in its fixed slot (or as the raw 2-bit
+// queue when there were more runs than slots); here they become the forward-order BAM CIGAR at run_offs[i].
+__global__ void __launch_bounds__(256) cigar_compact_kernel(int n, int queue_words, const uint32_t *__restrict__ moves,
+                                                            const uint32_t *__restrict__ run_offs, uint32_t *__restrict__ out,
+                                                            size_t out_cap) {
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair >= n) return;
+    // a chunk whose runs do not fit the block is replayed on the host instead (the caller checks run_offs[n])
+    if ((size_t)run_offs[pair + 1] > out_cap) return;
+    const uint32_t *q = moves + (size_t)pair * (queue_words + 1);
+    uint32_t *o = out + run_offs[pair];
+    const uint32_t head = q[0];
+    ++q;
+    if (!(head & 0x80000000u)) {
+        for (int r = (int)head - 1; r >= 0; --r) *o++ = q[r];
+        return;
+    }
+    const int n_moves = (int)(head & 0x7FFFFFFFu);
+    int cur = -1, len = 0;
+    for (int t = n_moves - 1; t >= 0; --t) {
+        const int code = (q[t >> 4] >> (2 * (t & 15))) & 3;
+        const int op = code == DIR_DIAG ? 0 : code == DIR_UP ? 1 : 2;
+        if (op == cur) {
+            ++len;
+        } else {
+            if (len) *o++ = ((uint32_t)len << 4) | (uint32_t)cur;
+            cur = op;
+            len = 1;
+        }
+    }
+    if (len) *o++ = ((uint32_t)len << 4) | (uint32_t)cur;
+}
+
 }  // namespace
+
+size_t cigar_compact_scratch_bytes(int n) {
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, n + 1);
+    return bytes + 256;
+}
+
+int launch_cigar_compact(int n, int queue_words, const uint32_t *moves, const uint32_t *run_count, uint32_t *run_offs,
+                         uint32_t *cigar_out, size_t out_cap_words, void *scratch, size_t scratch_bytes, cudaStream_t stream) {
+    if (n <= 0) return 0;
+    cub::DeviceScan::ExclusiveSum(scratch, scratch_bytes, run_count, run_offs, n + 1, stream);
+    cigar_compact_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, queue_words, moves, run_offs, cigar_out, out_cap_words);
+    return 1;  // our kernel; the scan is the library's
+}
 
 size_t traceback_queue_words(int read_length, int ref_length) { return (size_t)(read_length + ref_length + 15) / 16 + 1; }
 
 // The per-thread move queues live in dynamic shared memory while they fit beside the kernel's static arrays
 // (48 KB per block without opt-in); beyond that the caller provides slots * queue_words words of global memory.
 bool traceback_needs_global_queue(int read_length, int ref_length) {
-    return traceback_queue_words(read_length, ref_length) * TB_THREADS * sizeof(uint32_t) + 4 * TB_THREADS * sizeof(int) > 48 * 1024;
+    return traceback_queue_words(read_length, ref_length) * TB_THREADS * sizeof(uint32_t) + 8 * TB_THREADS * sizeof(int) > 48 * 1024;
 }
 
 int launch_traceback(const ChunkGeom &g, const ChunkBuffers &b, int mode, const Scoring &sc, uint32_t *global_queue,

@@ -158,3 +158,44 @@ def cigar_from_strings(aln_read: np.ndarray, aln_ref: np.ndarray, start: np.ndar
             off[i + 1] = off[i]
     cigar = np.concatenate(runs) if runs else np.zeros(0, np.uint32)
     return coords, off, cigar
+
+
+def mixed_batch_torch(n: int, min_len: int, max_len: int, p_sub: float, seed: int, device, slice_pairs: int = 1 << 20):
+    """Config C3 at full size, generated on the GPU (the numpy generator above needs minutes for 10 M pairs):
+    same recipe -- ref uniform ACGT, read = ref with per-base substitutions, read length ~U{min..max}, ref length
+    ~U{read..max}, '\\0' padding to max_len.  Returns device tensors (reads[n,max_len], refs[n,max_len] uint8,
+    read_lens[n], ref_lens[n] int32).  Bench input only: parity tests use the numpy generators."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    acgt = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
+    reads = torch.empty((n, max_len), dtype=torch.uint8, device=device)
+    refs = torch.empty((n, max_len), dtype=torch.uint8, device=device)
+    rl = torch.randint(min_len, max_len + 1, (n,), generator=g, device=device, dtype=torch.int32)
+    fl = (rl + (torch.rand((n,), generator=g, device=device) * (max_len + 1 - rl).float()).int()).clamp_(max=max_len)
+    col = torch.arange(max_len, device=device, dtype=torch.int32)[None, :]
+    for lo in range(0, n, slice_pairs):
+        hi = min(n, lo + slice_pairs)
+        code = torch.randint(0, 4, (hi - lo, max_len), generator=g, device=device, dtype=torch.uint8)
+        sub = torch.rand((hi - lo, max_len), generator=g, device=device) < p_sub
+        shift = torch.randint(1, 4, (hi - lo, max_len), generator=g, device=device, dtype=torch.uint8)
+        rcode = torch.where(sub, (code + shift) % 4, code)
+        refs[lo:hi] = torch.where(col < fl[lo:hi, None], acgt[code.long()], torch.zeros((), dtype=torch.uint8, device=device))
+        reads[lo:hi] = torch.where(col < rl[lo:hi, None], acgt[rcode.long()], torch.zeros((), dtype=torch.uint8, device=device))
+        del code, sub, shift, rcode
+    return reads, refs, rl, fl
+
+
+def pack_batch_torch(seqs, lens, slice_pairs: int = 1 << 20):
+    """Device (n, L) padded rows + lengths -> page-locked host arrays (flat uint8, int64 offsets[n+1]) as numpy views."""
+    import torch
+    n, L = seqs.shape
+    off = torch.zeros(n + 1, dtype=torch.int64)
+    off[1:] = torch.cumsum(lens.to(torch.int64).cpu(), 0)
+    flat = torch.empty(int(off[-1]), dtype=torch.uint8).pin_memory()
+    col = torch.arange(L, device=seqs.device, dtype=torch.int32)[None, :]
+    for lo in range(0, n, slice_pairs):
+        hi = min(n, lo + slice_pairs)
+        part = seqs[lo:hi][col < lens[lo:hi, None]]
+        flat[int(off[lo]):int(off[hi])].copy_(part)
+    return flat.numpy(), off.pin_memory().numpy()
