@@ -345,10 +345,11 @@ def test_nw_align_end_aligned_duos(ctx):
     short_refs[:, 80:] = 0  # padded refs: the pad-column rule reads the last true column at shifted rows
     for f in (refs, short_refs):
         for sc in PARAM_SETS[:3]:
-            a, b, start, end = ctx.align_flat(ora.NW, 0, reads, f, sc)
-            oa, ob, ostart, oend = ora.align(ora.NW, 0, reads, f, sc)
-            assert np.array_equal(start, ostart) and np.array_equal(end, oend), sc
-            assert used_region_equal(a, b, start, oa, ob, ostart).size == 0, sc
+            for pol in (0, 1):  # both pointer policies run on the packed kernel (second plane: UP >= LEFT / LEFT >= UP)
+                a, b, start, end = ctx.align_flat(ora.NW, pol, reads, f, sc)
+                oa, ob, ostart, oend = ora.align(ora.NW, pol, reads, f, sc)
+                assert np.array_equal(start, ostart) and np.array_equal(end, oend), (sc, pol)
+                assert used_region_equal(a, b, start, oa, ob, ostart).size == 0, (sc, pol)
 
 
 def test_c2_workload_sample_at_scale(ctx):

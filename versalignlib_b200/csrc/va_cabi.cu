@@ -475,6 +475,7 @@ void fill_geom(ChunkGeom &g, const Shape &sh, int n) {
     g.duos = g.slots / 2;
     g.fast_tw = 0;
     g.solo = 0;
+    g.policy = 0;
 }
 
 // Where one chunk's device work reads and writes.
@@ -499,6 +500,7 @@ int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int
     } while (0)
     ChunkGeom g;
     fill_geom(g, sh, n);
+    g.policy = sh.align ? policy : 0;
     // VERSALIGN_CUDA_GENERAL_ONLY=1 keeps every pair on the 32-bit kernel (parity tests use it to
     // cover that kernel on inputs the packed kernels would otherwise take)
     static const bool general_only = [] { const char *v = getenv("VERSALIGN_CUDA_GENERAL_ONLY"); return v && atoi(v) != 0; }();

@@ -389,7 +389,9 @@ bool fits8(int v) { return v >= -128 && v <= 127; }
 // cell can leave the int16 range; otherwise the call stays on the general 32-bit kernel.
 bool fast_scoring_ok(int mode, int policy, const Scoring &sc, int read_length, int ref_length) {
     const bool align = mode == MODE_NW_ALIGN || mode == MODE_SW_ALIGN;
-    if (align && policy != 0) return false;  // SSE/AVX pointer rule: general kernel
+    // SSE/AVX pointer rule: packed for NW align (the second plane records LEFT >= UP, va_nw.cu); SW align under
+    // that rule walks through zero cells and needs a third plane -- general kernel
+    if (align && policy != 0 && mode != MODE_NW_ALIGN) return false;
     int mx = 1;
     for (int v : {sc.match, sc.mismatch, sc.gap_read, sc.gap_ref}) mx = max(mx, v < 0 ? -v : v);
     // the most one diagonal step can add: a "mismatch" score above the match score counts too

@@ -53,6 +53,7 @@ struct ChunkGeom {
     int fast_tw;       // column-strip width of the packed 16-bit kernels for this call, 0 = not eligible
     int duos;          // slots / 2: stride of the arrays the packed kernels index by pair-of-pairs
     int solo;          // 1: the packed inter-task kernels also take single slots whose duo is not fast (va_fast.cuh)
+    int policy;        // traceback pointer policy of the call (0 Default/OpenCL, 1 SSE/AVX); align modes only
 };
 
 // Constants of the packed (two pairs per thread, s16x2) kernels, built on the host per call.

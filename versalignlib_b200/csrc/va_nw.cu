@@ -64,7 +64,11 @@ __device__ __forceinline__ void cp_async_wait() {
 // SOLO: the instantiation for single slots whose duo is not fast (va_fast.cuh): same sweep, the owner's
 // halves of the shared words stored with 16-bit stores.  Kept apart so the duo kernel's stores stay
 // unconditional (its schedule sits right at the register budget).
-template <bool ALIGN, int TW, bool SOLO>
+// POLICY (align only): which comparison the second direction plane records -- 0: UP >= LEFT (Default / OpenCL,
+// DefaultKernel.cpp:338-346: DIAG > UP > LEFT), 1: LEFT >= UP (SSE / AVX, SSEKernel.cpp:646-659: DIAG > LEFT > UP).
+// The packed path only takes pairs whose swept rows and columns are all ACGT (va_fast.cuh, va_prep.cu), so the
+// SSE/AVX rule's "DIAG only between two valid bases" never masks anything here and START cannot occur below row 0.
+template <bool ALIGN, int TW, bool SOLO, int POLICY>
 __global__ void __maxnreg__((Block<ALIGN, TW, SOLO>::MAXREG)) fill_nw_kernel(ChunkGeom g, ChunkBuffers b, FastConsts fc) {
     constexpr int NG = (TW + 15) / 16;
     constexpr int NT = Block<ALIGN, TW, SOLO>::NT;
@@ -155,7 +159,8 @@ __global__ void __maxnreg__((Block<ALIGN, TW, SOLO>::MAXREG)) fill_nw_kernel(Chu
                         uint32_t h;
                         if (ALIGN) {
                             bool dl, dh, ul, uh;
-                            const uint32_t t = __vibmax_s16x2(up, left, &uh, &ul);  // up >= left : UP before LEFT
+                            // policy 0: up >= left -> UP before LEFT; policy 1: left >= up -> LEFT before UP
+                            const uint32_t t = POLICY == 0 ? __vibmax_s16x2(up, left, &uh, &ul) : __vibmax_s16x2(left, up, &uh, &ul);
                             const uint32_t d = add2(diag, sub);
                             h = __vibmax_s16x2(d, t, &dh, &dl);                     // diag >= max(up,left) : DIAG first
                             const float bit = (float)(1u << (k & 15));
@@ -296,18 +301,18 @@ __global__ void __maxnreg__((Block<ALIGN, TW, SOLO>::MAXREG)) fill_nw_kernel(Chu
     if ((threadIdx.x & 31) == 0 && cells) atomicAdd(b.cell_count, cells);
 }
 
-template <bool ALIGN, int TW>
+template <bool ALIGN, int TW, int POLICY>
 void launch_one(const ChunkGeom &g, const ChunkBuffers &b, const FastConsts &fc, cudaStream_t stream) {
     const int duos = (g.n + 1) / 2;
     if (g.n >= 2) {
         const int threads = Block<ALIGN, TW, false>::NT;
-        fill_nw_kernel<ALIGN, TW, false><<<(duos + threads - 1) / threads, threads, 0, stream>>>(g, b, fc);
+        fill_nw_kernel<ALIGN, TW, false, POLICY><<<(duos + threads - 1) / threads, threads, 0, stream>>>(g, b, fc);
     }
     // leftovers of the bucketing: a fixed grid strides over the list the prep kernel compiled (empty on a
     // uniform batch: the blocks read the count and leave)
     if (g.solo) {
         const int threads = Block<ALIGN, TW, true>::NT;
-        fill_nw_kernel<ALIGN, TW, true><<<std::min(2 * ((duos + threads - 1) / threads), 148 * 4), threads, 0, stream>>>(g, b, fc);
+        fill_nw_kernel<ALIGN, TW, true, POLICY><<<std::min(2 * ((duos + threads - 1) / threads), 148 * 4), threads, 0, stream>>>(g, b, fc);
     }
 }
 
@@ -315,12 +320,15 @@ void launch_one(const ChunkGeom &g, const ChunkBuffers &b, const FastConsts &fc,
 
 int launch_fill_nw(const ChunkGeom &g, const ChunkBuffers &b, int mode, const FastConsts &fc, cudaStream_t stream) {
     const bool align = mode == MODE_NW_ALIGN;
+    const bool simd = align && g.policy == 1;
     if (g.fast_tw == 30) {
-        if (align) launch_one<true, 30>(g, b, fc, stream);
-        else launch_one<false, 30>(g, b, fc, stream);
+        if (simd) launch_one<true, 30, 1>(g, b, fc, stream);
+        else if (align) launch_one<true, 30, 0>(g, b, fc, stream);
+        else launch_one<false, 30, 0>(g, b, fc, stream);
     } else {
-        if (align) launch_one<true, 32>(g, b, fc, stream);
-        else launch_one<false, 32>(g, b, fc, stream);
+        if (simd) launch_one<true, 32, 1>(g, b, fc, stream);
+        else if (align) launch_one<true, 32, 0>(g, b, fc, stream);
+        else launch_one<false, 32, 0>(g, b, fc, stream);
     }
     return (g.n >= 2 ? 1 : 0) + (g.solo ? 1 : 0);
 }

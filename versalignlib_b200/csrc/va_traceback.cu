@@ -174,11 +174,13 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
                 // START (DefaultKernel.cpp:240-241).  The value is known along the path: it starts at the best
                 // score and every move gives back what it added.
                 int hval = NW ? 1 : (int)b.scores[pair];
+                const uint32_t pol = (uint32_t)g.policy & 1u;
                 ByteWindow wread(seq_ptr(b.raw_reads, b.read_off, pair, g.read_length), seq_end(b.raw_reads, b.read_off, g.n, g.read_length));
                 ByteWindow wref(seq_ptr(b.raw_refs, b.ref_off, pair, g.ref_length), seq_end(b.raw_refs, b.ref_off, g.n, g.ref_length));
                 while (true) {
                     const uint32_t dbit = (w.x >> bit) & 1u, ubit = (w.y >> bit) & 1u;
-                    const int code = dbit ? DIR_DIAG : (ubit ? DIR_UP : DIR_LEFT);
+                    // second plane: UP >= LEFT (policy 0) or LEFT >= UP (policy 1, SSE/AVX tie order)
+                    const int code = dbit ? DIR_DIAG : ((ubit ^ pol) ? DIR_UP : DIR_LEFT);
                     sink(code, n_moves);
                     ++n_moves;
                     if (!NW) {
