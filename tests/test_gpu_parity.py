@@ -332,6 +332,47 @@ def test_long_pairs_warp_per_pair_general_kernel(ctx):
                     assert used_region_equal(a, b, start, oa, ob, ostart).size == 0, (name, sc, opt, policy)
 
 
+def test_long_pairs_intra_task_align(ctx):
+    """Few, long pairs: the packed intra-task kernels (a CTA per pair-of-pairs, va_intra.cu) fill every mode and
+    the warp-per-pair traceback walks their [duo][strip][row] direction words.  All four functions, both NW pointer
+    policies, equal and unequal gap scores, several 512-column passes with a partial last one, duos whose reads and
+    refs differ in length, a dirty ref (that pair falls to the general kernel inside the same chunk), an odd pair
+    count -- through the flat (fixed-stride strings), scattered (compact strings) and packed (CIGAR) entry points."""
+    decks = []
+    r, f = synth.uniform_batch(12, 1000, 1200, p_sub=0.10, q_indel=0.03, seed=51)
+    decks.append(("1000x1200", r, f))
+    r, f = synth.uniform_batch(5, 2600, 3100, p_sub=0.12, q_indel=0.03, seed=52)
+    decks.append(("2600x3100_odd", r, f))
+    r, f, _, _ = synth.mixed_batch(14, 600, 1500, p_sub=0.1, q_indel=0.02, seed=53)
+    decks.append(("mixed600-1500", r, f))
+    r, f = synth.uniform_batch(8, 300, 1024, independent=True, seed=54)  # unrelated sequences: short local alignments
+    decks.append(("random300x1024", r, f))
+    r, f = synth.uniform_batch(6, 1100, 1300, p_sub=0.10, q_indel=0.03, seed=55)
+    f = f.copy()
+    f[2, 400] = ord("N")
+    decks.append(("one_dirty_ref", r, f))
+    for name, r, f in decks:
+        for sc in [(2, -1, -3, -3), (3, -2, -1, -4), (1, -1, -2, -2)]:
+            for opt in (ora.SW, ora.NW):
+                assert np.array_equal(ctx.score_flat(opt, r, f, sc), ora.score(opt, r, f, sc)), (name, sc, opt)
+                for policy in (0, 1):
+                    oa, ob, ostart, oend = ora.align(opt, policy, r, f, sc)
+                    a, b, start, end = ctx.align_flat(opt, policy, r, f, sc)
+                    assert np.array_equal(start, ostart) and np.array_equal(end, oend), (name, sc, opt, policy)
+                    assert used_region_equal(a, b, start, oa, ob, ostart).size == 0, (name, sc, opt, policy)
+    # the other two result containers on one deck
+    name, r, f = decks[0]
+    for opt in (ora.SW, ora.NW):
+        oa, ob, ostart, oend = ora.align(opt, 0, r, f)
+        a, b, start, end = ctx.align_ptrs(opt, 0, r, f)
+        assert np.array_equal(start, ostart) and used_region_equal(a, b, start, oa, ob, ostart).size == 0, opt
+        pr, ro = synth.pack_batch(r)
+        pf, fo = synth.pack_batch(f)
+        scores, coords, coff, cigar = ctx.align_packed(opt, 0, pr, ro, pf, fo)
+        wc, woff, wcig = synth.cigar_from_strings(oa, ob, ostart, oend)
+        assert np.array_equal(coords, wc) and np.array_equal(coff, woff) and np.array_equal(cigar, wcig), opt
+
+
 def test_nw_align_end_aligned_duos(ctx):
     """Packed NW align takes duos whose reads differ in length by starting the shorter lane late (CODE_PRE
     rows): refs of one length, reads of every length from 1 up, odd and even offsets, trimmed and full refs."""

@@ -316,9 +316,9 @@ struct Shape {
     size_t per_pair_workspace() const {
         size_t b = (size_t)(read_chunks + ref_chunks) * 32 + (size_t)read_chunks * 8 + 2 * sizeof(PairMeta) + 40 + (size_t)rows_alloc * 6;
         if (align) {
-            b += dir_row_bytes() * (rows_alloc + 1) + (size_t)ref_length * 2 + 8;
+            b += dir_row_bytes() * (rows_alloc + 4) + (size_t)ref_length * 2 + 8;
             const size_t qw = traceback_queue_words(read_length, ref_length);
-            if (traceback_needs_global_queue(read_length, ref_length)) b += qw * 4;
+            if (traceback_wants_global_queue(read_length, ref_length)) b += qw * 4;
         }
         return b;
     }
@@ -415,11 +415,11 @@ int reserve_slot(ChunkSlot &s, const Shape &sh, int cap_pairs, SlotKind kind) {
     if ((rc = s.scores.reserve(slots * 2))) return rc;
     if ((rc = s.end_cell.reserve(slots * 4))) return rc;
     if (sh.align) {
-        if ((rc = s.dirs.reserve(slots * sh.dir_row_bytes() * (sh.rows_alloc + 1) + 512))) return rc;
+        if ((rc = s.dirs.reserve(slots * sh.dir_row_bytes() * (sh.rows_alloc + 4) + 512))) return rc;  // (+4: the intra-task layout pads rows to a multiple of 4)
         if ((rc = s.hrow.reserve(slots / 2 * (size_t)round_up((size_t)std::max(sh.ref_length, 1), 4) * 4 + 64))) return rc;
         // traceback move queue: shared memory unless the sequences are long
         const size_t qw = traceback_queue_words(sh.read_length, sh.ref_length);
-        if (traceback_needs_global_queue(sh.read_length, sh.ref_length) && (rc = s.queue.reserve(slots * qw * 4 + 64))) return rc;
+        if (traceback_wants_global_queue(sh.read_length, sh.ref_length) && (rc = s.queue.reserve(slots * qw * 4 + 64))) return rc;
         if (pinned) {
             if ((rc = s.start.reserve(slots * 2))) return rc;
             if (sh.moves) {
@@ -476,6 +476,7 @@ void fill_geom(ChunkGeom &g, const Shape &sh, int n) {
     g.fast_tw = 0;
     g.solo = 0;
     g.policy = 0;
+    g.intra = 0;
 }
 
 // Where one chunk's device work reads and writes.
@@ -504,7 +505,19 @@ int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int
     // VERSALIGN_CUDA_GENERAL_ONLY=1 keeps every pair on the 32-bit kernel (parity tests use it to
     // cover that kernel on inputs the packed kernels would otherwise take)
     static const bool general_only = [] { const char *v = getenv("VERSALIGN_CUDA_GENERAL_ONLY"); return v && atoi(v) != 0; }();
-    if (!general_only && fast_scoring_ok(mode, policy, sc, sh.read_length, sh.ref_length)) g.fast_tw = fast_pick_tw(mode, sh.ref_length);
+    // few, long pairs: the intra-task kernels (a CTA per pair-of-pairs, va_intra.cu); decided before prep: every
+    // kernel of the chunk reads it
+    static const bool no_intra = [] { const char *v = getenv("VERSALIGN_CUDA_NO_INTRA"); return v && atoi(v) != 0; }();
+    if (!general_only) {
+        if (!no_intra && intra_preferred(mode, n, sh.read_length, sh.ref_length, e.sm_count) &&
+            fast_scoring_ok(mode, policy, sc, sh.read_length, sh.ref_length, true)) {
+            g.fast_tw = 16;
+            g.intra = 1;
+        } else if (fast_scoring_ok(mode, policy, sc, sh.read_length, sh.ref_length)) {
+            g.fast_tw = fast_pick_tw(mode, sh.ref_length);
+        }
+    }
+    const bool intra = g.intra != 0;
     ChunkBuffers b{};
     b.raw_reads = io.raw_reads;
     b.raw_refs = io.raw_refs;
@@ -552,8 +565,6 @@ int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int
         e.prof_used += 4;
         ENQ_TRY(cudaEventRecord(pe[0], stream));
     }
-    static const bool no_intra = [] { const char *v = getenv("VERSALIGN_CUDA_NO_INTRA"); return v && atoi(v) != 0; }();
-    const bool intra = g.fast_tw && !no_intra && intra_preferred(mode, n, sh.read_length, sh.ref_length, e.sm_count);
     // the inter-task kernels also take single slots (odd leftovers of the bucketing); the intra-task kernel
     // leaves those to the general kernel.  Decided before prep: every kernel of the chunk reads it.
     static const bool no_solo = [] { const char *v = getenv("VERSALIGN_CUDA_NO_SOLO"); return v && atoi(v) != 0; }();
@@ -572,7 +583,8 @@ int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int
     launches += launch_fill_general(g, b, mode, policy, sc, ws.side);
     ENQ_TRY(cudaEventRecord(ws.ev_join, ws.side));
     if (intra)
-        launches += launch_fill_intra(g, b, mode, make_fast_consts(mode, sc), stream);
+        // (all four modes run in the Smith-Waterman form there: the SW tables and constants)
+        launches += launch_fill_intra(g, b, mode, make_fast_consts(sh.align ? MODE_SW_ALIGN : MODE_SW_SCORE, sc), stream);
     else
         launches += launch_fill_fast(g, b, mode, sc, stream);
     ENQ_TRY(cudaStreamWaitEvent(stream, ws.ev_join, 0));
@@ -1040,8 +1052,10 @@ void run_shard(va_cuda_ctx *ctx, Engine &e, const HostCall &c, int64_t lo, int64
 
 int pick_chunk_pairs(const Engine &e, const Shape &sh, int64_t shard_pairs) {
     // device workspace budget per ring slot: a quarter of a third of the card, at most 6 GiB
-    const size_t budget = std::min<size_t>(e.total_mem / 12, (size_t)6 << 30);
+    // (long pairs: tens of MB of directions per pair and next to nothing to copy -- fewer, larger chunks keep the
+    // intra-task kernels' CTAs-per-duo grid full)
     const size_t per_pair = sh.per_pair_workspace() + sh.per_pair_io();
+    const size_t budget = per_pair > ((size_t)4 << 20) ? std::min<size_t>(e.total_mem / 6, (size_t)24 << 30) : std::min<size_t>(e.total_mem / 12, (size_t)6 << 30);
     int64_t cap = (int64_t)std::max<size_t>(64, budget / std::max<size_t>(per_pair, 1));
     // pinned staging per slot at most ~512 MiB
     cap = std::min<int64_t>(cap, std::max<int64_t>(64, ((int64_t)512 << 20) / (int64_t)std::max<size_t>(sh.per_pair_io(), 1)));
@@ -1440,7 +1454,9 @@ int va_cuda_max_resident_pairs(va_cuda_ctx *ctx, int align, int read_length, int
     const Shape sh = make_shape(read_length, ref_length, align != 0);
     const Engine &e = ctx->engines[0];
     // (an align sub-chunk's direction region stays below 2^32 eight-byte words: the traceback walk's offsets are 32-bit)
-    const size_t budget = std::min<size_t>(e.total_mem / 2, align ? (size_t)30 << 30 : (size_t)80 << 30);
+    // (long pairs go through the intra-task layout and the warp-per-pair traceback, which index with 64 bits)
+    const bool long_pairs = read_length >= 256 && ref_length >= 1024;
+    const size_t budget = std::min<size_t>(e.total_mem / 2, align && !long_pairs ? (size_t)30 << 30 : (size_t)80 << 30);
     *max_n = (int64_t)(budget / std::max<size_t>(sh.per_pair_workspace(), 1));
     return VA_OK;
 }

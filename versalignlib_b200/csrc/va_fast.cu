@@ -387,7 +387,7 @@ bool fits8(int v) { return v >= -128 && v <= 127; }
 
 // The packed kernels are exact only while (a) every table entry fits a signed byte and (b) no
 // cell can leave the int16 range; otherwise the call stays on the general 32-bit kernel.
-bool fast_scoring_ok(int mode, int policy, const Scoring &sc, int read_length, int ref_length) {
+bool fast_scoring_ok(int mode, int policy, const Scoring &sc, int read_length, int ref_length, bool intra) {
     const bool align = mode == MODE_NW_ALIGN || mode == MODE_SW_ALIGN;
     // SSE/AVX pointer rule: packed for NW align (the second plane records LEFT >= UP, va_nw.cu); SW align under
     // that rule walks through zero cells and needs a third plane -- general kernel
@@ -397,6 +397,19 @@ bool fast_scoring_ok(int mode, int policy, const Scoring &sc, int read_length, i
     // the most one diagonal step can add: a "mismatch" score above the match score counts too
     const long long gain = max(max(sc.match, sc.mismatch), 0);
     const long long min_len = read_length < ref_length ? read_length : ref_length;
+    if (intra) {
+        // va_intra.cu: every mode in the Smith-Waterman form (tables s or s - gap_ref, values carried as "H + gap"), so
+        // the range is the matrix's own.  Above: gain * min(len).  Below: SW cells are floored at 0; an NW score cell is
+        // at least max(i*gap_ref, j*gap_read) (straight down / right from the zero borders), an NW align cell at least
+        // i*gap_ref (straight down from row 0).
+        if (sc.gap_read > 0 || sc.gap_ref > 0) return false;
+        const int off = align ? sc.gap_ref : 0;
+        if (!fits8(sc.match - off) || !fits8(sc.mismatch - off) || !fits8(-off)) return false;
+        long long low = 0;
+        if (mode == MODE_NW_SCORE) low = (long long)mx * (min_len + 2);
+        if (mode == MODE_NW_ALIGN) low = -(long long)sc.gap_ref * (read_length + 2);
+        return gain * min_len + 2 * mx <= 32000 && low + 2 * mx <= 32000 && mx <= 8000;
+    }
     if (mode == MODE_NW_SCORE || mode == MODE_NW_ALIGN) {
         // shifted recurrence (va_nw.cu): gap scores <= 0, table entries s - gap_ref - gap_read, and
         // 0 <= V <= gain*min(rows,cols) + |gap_ref|*rows + |gap_read|*cols

@@ -22,6 +22,7 @@ __device__ __forceinline__ bool duo_is_fast(const ChunkGeom &g, int mode, int sl
     if (a.cols != a.true_cols || b.cols != b.true_cols) return false;  // no padded / N tail inside the sweep
     // NW align's end-cell rule reads each lane's last valid row from the registers after the sweep: lanes
     // of different read lengths are end-aligned (nw_row_offset), so both need at least one row
+    // (the intra-task kernel starts both lanes at row 0 and captures each lane's own last row)
     if (mode == MODE_NW_ALIGN) return a.rows > 0 && b.rows > 0;
     return max(a.rows, b.rows) > 0;
 }
@@ -123,6 +124,12 @@ __device__ __forceinline__ void store_half(uint4 *p, int half, uint2 v, const Fa
 
 __device__ __forceinline__ int fast_groups(int tw) { return (tw + 15) >> 4; }
 
+// Intra-task kernels (va_intra.cu): a lane's strip is 16 columns; direction words are uint2 (DIAG plane, second
+// plane; low 16 bits lane A) at [duo][strip][row], rows padded to a multiple of 4 so that four rows are one
+// aligned 32-byte sector.
+constexpr int INTRA_TW = 16;
+__host__ __device__ __forceinline__ int intra_dir_rows(const ChunkGeom &g) { return (g.rows_alloc + 3) & ~3; }
+
 // Direction words of the packed kernel: one uint4 per (strip, ROW PAIR, group of 16 columns, duo)
 //   .x/.y = DIAG plane / UP plane of the even row, .z/.w = the same for the odd row;
 //   in each 32-bit plane the low half belongs to lane A (slot 2u), the high half to lane B.
@@ -132,6 +139,7 @@ __device__ __forceinline__ int fast_row_pairs(const ChunkGeom &g) { return (g.ro
 
 // Packed NW align, duo lanes of different read lengths: sweep row of a lane's matrix row r is r + this
 __device__ __forceinline__ int nw_row_offset(const PairMeta &me, const PairMeta &other) { return max((int)me.rows, (int)other.rows) - (int)me.rows; }
+__device__ __forceinline__ int nw_row_offset(const ChunkGeom &g, const PairMeta &me, const PairMeta &other) { return g.intra ? 0 : nw_row_offset(me, other); }
 
 // index (in uint4 units) of the word holding `row`
 __device__ __forceinline__ size_t fast_dir_index(const ChunkGeom &g, int strip, int row, int group, int duo) {

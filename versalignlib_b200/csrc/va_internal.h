@@ -54,6 +54,8 @@ struct ChunkGeom {
     int duos;          // slots / 2: stride of the arrays the packed kernels index by pair-of-pairs
     int solo;          // 1: the packed inter-task kernels also take single slots whose duo is not fast (va_fast.cuh)
     int policy;        // traceback pointer policy of the call (0 Default/OpenCL, 1 SSE/AVX); align modes only
+    int intra;         // 1: the chunk's packed duos are computed by the intra-task kernels (va_intra.cu): 16-column strips,
+                       // directions at [duo][strip][row], boundary at [duo][row], no end-aligned NW duos
 };
 
 // Constants of the packed (two pairs per thread, s16x2) kernels, built on the host per call.
@@ -118,7 +120,8 @@ int launch_prep(const ChunkGeom &g, const ChunkBuffers &b, int mode, int policy,
 int launch_fill_general(const ChunkGeom &g, const ChunkBuffers &b, int mode, int policy, const Scoring &sc,
                         cudaStream_t stream);
 // packed kernels (va_fast.cu)
-bool fast_scoring_ok(int mode, int policy, const Scoring &sc, int read_length, int ref_length);
+// intra: the intra-task kernels' domain (SW align without the 16-bit best-cell key, NW modes un-shifted)
+bool fast_scoring_ok(int mode, int policy, const Scoring &sc, int read_length, int ref_length, bool intra = false);
 int fast_pick_tw(int mode, int ref_length);
 size_t fast_dirs_bytes_per_row_per_slot(int ref_length);
 FastConsts make_fast_consts(int mode, const Scoring &sc);
@@ -130,6 +133,7 @@ bool intra_preferred(int mode, int n_pairs, int read_length, int ref_length, int
 int launch_fill_intra(const ChunkGeom &g, const ChunkBuffers &b, int mode, const FastConsts &fc, cudaStream_t stream);
 size_t traceback_queue_words(int read_length, int ref_length);
 bool traceback_needs_global_queue(int read_length, int ref_length);
+bool traceback_wants_global_queue(int read_length, int ref_length);
 int launch_traceback(const ChunkGeom &g, const ChunkBuffers &b, int mode, const Scoring &sc, uint32_t *global_queue,
                      cudaStream_t stream);
 // packed entry points: per-pair CIGAR runs (walk order, fixed slots) -> one forward-order block (va_traceback.cu).

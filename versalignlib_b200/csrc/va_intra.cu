@@ -1,20 +1,35 @@
-// va_intra.cu -- intra-task Smith-Waterman score kernel for long pairs: ONE WARP computes one
-// pair-of-pairs (two pairs in the two s16 lanes of every register), walking the matrix as a
-// skewed wavefront.  The reference has nothing like it -- all of its kernels walk one matrix
-// row-major with a loop-carried dependency through memory -- so parity is defined
-// by the recurrence alone (DefaultKernel.cpp:83-138): the cell arithmetic is the packed kernel's
-// (va_fast.cu), only the order of evaluation changes.
+// va_intra.cu -- intra-task kernels for long pairs: a CTA computes ONE pair-of-pairs (two pairs in the two
+// s16 lanes of every register); each of its warps walks a 512-column pass of the matrix as a skewed
+// wavefront and the warps pipeline consecutive passes.  The reference has nothing like it -- all of its
+// kernels walk one matrix row-major with a loop-carried dependency through memory -- so parity
+// is defined by the recurrences alone (score: DefaultKernel.cpp:83-202; fill with pointers:
+// DefaultKernel.cpp:204-389, SSEKernel.cpp:646-659 for the SSE/AVX tie order): the cell arithmetic is the
+// packed kernels' (va_fast.cu), only the order of evaluation changes.
 //
-//   * lane l owns TW consecutive ref columns of the current pass (32*TW columns per pass);
+//   * lane l owns 16 consecutive ref columns of the current pass (512 columns per pass);
 //   * at step t lane l computes row t-l of its columns, so its left neighbour's right edge
-//     (computed one step earlier) arrives by __shfl_up_sync together with that row's two
-//     substitution tables; lane 0 takes its inputs from a per-32-steps batch that all lanes
-//     load coalesced (read codes -> tables, previous pass's boundary column);
+//     (computed one step earlier) arrives by __shfl_up_sync together with that row's table index; lane 0
+//     takes its inputs from a per-32-steps batch that all lanes load coalesced (row index, previous
+//     pass's boundary column);
 //   * lane 31's right edge is collected over 32 steps and stored coalesced as the next pass's
 //     boundary column;
-//   * the passes of one duo are spread over the warps of a CTA and run as a pipeline (see the kernel).
+//   * the passes of one duo are spread over the warps of the CTA and run as a pipeline (see the kernel);
+//   * align modes: the two comparisons of the pointer rule leave the max instructions as predicates and are
+//     banked into bit planes by predicated FADDs exactly like the inter-task kernels; a row's planes of a
+//     lane's 16 columns are one 8-byte word, stored at [duo][16-column strip][row] -- consecutive rows are
+//     consecutive words, which is what the warp-cooperative traceback of long pairs reads 32 rows at a time
+//     (va_traceback.cu);
+//   * all four modes share the Smith-Waterman form of the recurrence (values carried as "H + gap"); the
+//     Needleman-Wunsch modes drop the zero floor and differ at the borders.  (The shifted NW recurrence of
+//     va_nw.cu would leave the 16-bit range on long pairs: its values grow with rows + columns.)
+//   * SW align's best cell (first strictly greater in row-major order, DefaultKernel.cpp:252-256) cannot use
+//     the inter-task kernel's 16-bit (value, column) key -- long pairs score far above 1023 -- so each lane
+//     tracks the greatest row maximum of its strips and, whenever one of its halves sets a new one, parks the
+//     row's 16 registers in shared memory; the column is read from that snapshot at the end.
 // Used when a batch has too few pairs to fill the GPU with one thread per pair-of-pairs and
-// the pairs are long (launch_fill_intra decides).
+// the pairs are long (intra_preferred decides).
+#include <algorithm>
+
 #include "va_fast.cuh"
 
 namespace va {
@@ -23,20 +38,34 @@ namespace {
 
 constexpr uint32_t NEG2 = 0x80008000u;
 __device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b) { return __viaddmax_s16x2(a, b, NEG2); }
+__device__ __forceinline__ uint32_t pk(int v) { return ((uint32_t)v & 0xFFFFu) * 0x00010001u; }
+__device__ __forceinline__ uint32_t pk2(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
+__device__ __forceinline__ int lo16(uint32_t v) { return (int)(int16_t)(v & 0xFFFFu); }
+__device__ __forceinline__ int hi16(uint32_t v) { return (int)(int16_t)(v >> 16); }
 
 constexpr int MAX_PASSES = 64;  // 32 000 columns / (32 lanes x 16 columns)
+constexpr int TW = INTRA_TW;
+constexpr int MAX_WARPS = 16;
 
 // One CTA = one duo; its W warps take the column passes round-robin (warp w: passes w, w+W, ...) and run
 // them as a pipeline: pass p+1 follows pass p a few dozen rows behind, reading the boundary column pass p
 // leaves in global memory (32 rows per coalesced store) as soon as a shared-memory progress counter says
 // those rows are there.  A batch of a few long pairs then fills the GPU with W times as many warps.
-template <int TW>
-__global__ void __launch_bounds__(128) fill_intra_sw_score_kernel(ChunkGeom g, ChunkBuffers b, FastConsts fc) {
+//
+// MODE: one of the four functions.  POLICY (NW align): which comparison the second plane records (0: UP >= LEFT,
+// 1: LEFT >= UP).  SYM (align): gap_read == gap_ref, so "H + gR" and "H + gF" are one register.
+template <int MODE, int POLICY, bool SYM>
+__global__ void __launch_bounds__(32 * MAX_WARPS, 1) fill_intra_kernel(ChunkGeom g, ChunkBuffers b, FastConsts fc) {
     constexpr unsigned FULL = 0xffffffffu;
-    __shared__ uint32_t T[8];
+    constexpr bool ALIGN = MODE == MODE_SW_ALIGN || MODE == MODE_NW_ALIGN;
+    constexpr bool SW = MODE == MODE_SW_SCORE || MODE == MODE_SW_ALIGN;
+    constexpr bool SWA = MODE == MODE_SW_ALIGN, NWA = MODE == MODE_NW_ALIGN, SWS = MODE == MODE_SW_SCORE, NWS = MODE == MODE_NW_SCORE;
+    __shared__ uint2 s_T2[64];            // [7*code_a + code_b] -> the two lanes' 4-entry score tables (49 used)
     __shared__ int prog[MAX_PASSES];      // rows of pass p whose right edge is in global memory
-    __shared__ uint32_t warp_best[4];
-    if (threadIdx.x < 8) T[threadIdx.x] = fc.tab[threadIdx.x];
+    __shared__ uint32_t warp_best[MAX_WARPS];
+    __shared__ int warp_cell[MAX_WARPS][2][3];  // SW align: per warp and half: value, row, column of its best cell
+    extern __shared__ uint32_t s_snap[];  // SW align: [warp][slot 0/1][register][lane] row snapshots
+    if (threadIdx.x < 64) s_T2[threadIdx.x] = threadIdx.x < 49 ? make_uint2(fc.tab[threadIdx.x / 7], fc.tab[threadIdx.x % 7]) : make_uint2(0u, 0u);
     for (int t = threadIdx.x; t < MAX_PASSES; t += blockDim.x) prog[t] = 0;
     __syncthreads();
 
@@ -45,41 +74,58 @@ __global__ void __launch_bounds__(128) fill_intra_sw_score_kernel(ChunkGeom g, C
     const int slot_a = 2 * duo, slot_b = slot_a + 1;
     if (slot_b >= g.n) return;  // CTA-uniform
     const PairMeta ma = b.meta[slot_a], mb = b.meta[slot_b];
-    if (!duo_is_fast(g, MODE_SW_SCORE, slot_a, ma, mb)) return;
+    if (!duo_is_fast(g, MODE, slot_a, ma, mb)) return;
     const int m = max((int)ma.rows, (int)mb.rows), n = ma.cols;
-    const uint32_t gF2 = fc.gF2, gR2 = fc.gR2, ngR2 = fc.dFR2;  // dFR2 = -gap_read in the score modes
-    const uint8_t *cread = reinterpret_cast<const uint8_t *>(b.code_reads) + (size_t)slot_a * 16;
+    const int gF = fc.gF, gR = fc.gR;
+    const uint32_t gF2 = fc.gF2, gR2 = fc.gR2, dFR2 = fc.dFR2;  // dFR2: boundary ("H + gR") -> diagonal form
+    const uint8_t *ridx = reinterpret_cast<const uint8_t *>(b.row_idx) + (size_t)duo * 16;
     const uint8_t *cref = reinterpret_cast<const uint8_t *>(b.code_refs);
     const uint32_t chunk_stride = (uint32_t)g.slots * 16u;
+    const uint32_t ridx_stride = (uint32_t)g.duos * 16u;
     uint32_t *bnd = b.fboundary + (size_t)duo * g.rows_alloc;  // this duo's boundary column (rewritten pass after pass)
     volatile int *vprog = prog;
+    const int ns = g.ref_chunks;
+    const size_t rows2 = (size_t)intra_dir_rows(g);
+    uint2 *dirs2 = reinterpret_cast<uint2 *>(b.fdirs) + (size_t)duo * ns * rows2;
 
-    uint32_t best = 0;
+    uint32_t best = 0;  // score modes: running maximum (SW) / max(0, last column, last row) (NW)
+    // SW align: greatest row maximum so far per half, in the registers' form (value + gF); row, strip and
+    // snapshot slot it came from
+    uint32_t gbest2 = gF2;
+    int gi_a = 0, gi_b = 0, gs_a = -1, gs_b = -1, src_a = 0, src_b = 0;
+    uint32_t *snap = s_snap + (size_t)warp * 2 * TW * 32 + lane;  // [slot][register] at stride 32
+
     const int pass_cols = 32 * TW;
     const int npasses = (n + pass_cols - 1) / pass_cols;
     const int steps = m + 31;
+    const int last_lane = ((n - 1) >> 4) & 31;
+    const int ra_last = (int)ma.rows - 1, rb_last = (int)mb.rows - 1;
     for (int pass = warp; pass < npasses; pass += W) {
         const int c_base = pass * pass_cols;
         const bool first_pass = pass == 0, last_pass = pass == npasses - 1;
         const int c0 = c_base + lane * TW;
         const int kv = min(TW, max(0, n - c0));  // my valid columns in this pass
+        const int strip = c0 >> 4;
         uint32_t sel[TW], H[TW];
 #pragma unroll
         for (int k = 0; k < TW; ++k) {
             const int col = min(c0 + k, n - 1);
             const size_t off = (size_t)(col >> 4) * chunk_stride + (col & 15);
             const uint32_t fa = cref[off + (size_t)slot_a * 16], fb = cref[off + (size_t)slot_b * 16];
-            sel[k] = fa | ((fa | 8u) << 4) | ((fb | 4u) << 8) | ((fb | 12u) << 12);
-            H[k] = 0u;
+            // columns past n: a selector that yields s <= 0 for both lanes (the sign byte of a table entry)
+            sel[k] = k < kv ? (fa | ((fa | 8u) << 4) | ((fb | 4u) << 8) | ((fb | 12u) << 12)) : 0xCC88u;
+            H[k] = ALIGN ? gF2 : 0u;  // matrix row 0 is 0 (align keeps H + gF)
         }
-        uint32_t diag_next = 0u;                        // H[row][c0] of the previous row, 0 for matrix row 0
-        uint32_t cur_ta = 0, cur_tb = 0, edge = gR2;    // what this lane used / produced at its last step
-        uint32_t out_keep = 0;                          // lane 31's right edges, one per lane, for the coalesced store
+        uint32_t diag_next = ALIGN ? gF2 : 0u;            // H[row][c0] of the previous row, 0 for matrix row 0
+        uint32_t cur_idx = 0, edge = gR2;                 // what this lane used / produced at its last step
+        uint32_t out_keep = 0;                            // lane 31's right edges, one per lane, for the coalesced store
+        uint2 *dp = dirs2 + (size_t)strip * rows2;
 
         for (int t0 = 0; t0 < steps; t0 += 32) {
             // batch inputs of lane 0 for steps t0..t0+31: row r = t0 + lane
             const int r = t0 + lane;
-            uint32_t bat_a = 0, bat_b = 0, bat_left = gR2;  // matrix column 0 is 0: "left + gR" = gR
+            // matrix column 0 as "H + gR": 0 everywhere but NW align, where H(I,0) = I*gap_ref (DefaultKernel.cpp:304)
+            uint32_t bat_idx = 0, bat_left = NWA ? pk((r + 1) * gF + gR) : gR2;
             if (!first_pass && t0 < m) {
                 // the previous pass (another warp of this CTA when W > 1) must have left these rows
                 const int need = min(t0 + 32, m);
@@ -88,9 +134,7 @@ __global__ void __launch_bounds__(128) fill_intra_sw_score_kernel(ChunkGeom g, C
                 __threadfence_block();
             }
             if (r < m) {
-                const uint32_t roff = (uint32_t)(r >> 4) * chunk_stride + (uint32_t)(r & 15);
-                bat_a = T[cread[roff]];
-                bat_b = T[cread[roff + 16]];
+                bat_idx = ridx[(size_t)(r >> 4) * ridx_stride + (r & 15)];
                 if (!first_pass) bat_left = __ldcg(bnd + r);  // written by another warp: read it where it was written (L2)
             }
             __syncwarp();  // every lane has read its row before this warp overwrites the column below
@@ -98,27 +142,44 @@ __global__ void __launch_bounds__(128) fill_intra_sw_score_kernel(ChunkGeom g, C
             for (int s = 0; s < s_end; ++s) {
                 const int t = t0 + s;
                 // lane 0 reads the batch, every other lane takes what its left neighbour used last step
-                const uint32_t a0 = __shfl_sync(FULL, bat_a, s), b0 = __shfl_sync(FULL, bat_b, s), l0 = __shfl_sync(FULL, bat_left, s);
-                const uint32_t pa = __shfl_up_sync(FULL, cur_ta, 1), pb = __shfl_up_sync(FULL, cur_tb, 1), pl = __shfl_up_sync(FULL, edge, 1);
-                const uint32_t ta = lane == 0 ? a0 : pa, tb = lane == 0 ? b0 : pb;
+                const uint32_t i0 = __shfl_sync(FULL, bat_idx, s), l0 = __shfl_sync(FULL, bat_left, s);
+                const uint32_t pi = __shfl_up_sync(FULL, cur_idx, 1), pl = __shfl_up_sync(FULL, edge, 1);
+                const uint32_t idx = lane == 0 ? i0 : pi;
                 uint32_t left = lane == 0 ? l0 : pl;
                 const int row = t - lane;
                 if (row >= 0 && row < m) {
-                    cur_ta = ta;
-                    cur_tb = tb;
+                    cur_idx = idx;
+                    const uint2 tt2 = s_T2[idx];
+                    const uint32_t ta = tt2.x, tb = tt2.y;
                     uint32_t diag = diag_next;
-                    diag_next = add2(left, ngR2);
-                    if (kv == TW) {
+                    diag_next = add2(left, dFR2);  // "H + gR" -> the diagonal's form (H in the score modes, H + gF in the align modes)
+                    if (ALIGN) {
+                        float p1l = 8388608.0f, p1h = 8388608.0f, p2l = 8388608.0f, p2h = 8388608.0f;
 #pragma unroll
                         for (int k = 0; k < TW; ++k) {
-                            const uint32_t sub = prmt(ta, tb, sel[k]);
+                            const uint32_t sub = prmt(ta, tb, sel[k]);  // table holds s - gF
                             const uint32_t up = H[k];
-                            const uint32_t tt = __viaddmax_s16x2(up, gF2, left);
-                            const uint32_t h = __viaddmax_s16x2_relu(diag, sub, tt);
-                            left = add2(h, gR2);
-                            H[k] = h;
-                            if (k & 1) best = __vimax3_s16x2(best, h, H[k - 1]);
+                            bool dl, dh, ul, uh;
+                            // up+gF vs left+gR; policy 0: UP before LEFT, policy 1: LEFT before UP
+                            const uint32_t tmax = POLICY == 0 ? __vibmax_s16x2(up, left, &uh, &ul) : __vibmax_s16x2(left, up, &uh, &ul);
+                            const uint32_t d = add2(diag, sub);
+                            const uint32_t h = __vibmax_s16x2(d, tmax, &dh, &dl);  // diag+s >= max(up,left): DIAG first
+                            const float bit = (float)(1u << k);
+                            if (dl) p1l += bit;
+                            if (dh) p1h += bit;
+                            if (ul) p2l += bit;
+                            if (uh) p2h += bit;
+                            // SW: the pointer of a positive cell is this rule; a zero cell is START, which the traceback
+                            // recognises by tracking the score (DefaultKernel.cpp:238-248)
+                            left = SW ? __viaddmax_s16x2(h, gR2, gR2) : add2(h, gR2);                  // max(h, 0) + gR
+                            H[k] = SYM ? left : (SW ? __viaddmax_s16x2(h, gF2, gF2) : add2(h, gF2));  // max(h, 0) + gF
                             diag = up;
+                        }
+                        if (kv > 0) {
+                            uint2 w;
+                            w.x = __byte_perm(__float_as_uint(p1l), __float_as_uint(p1h), 0x5410);
+                            w.y = __byte_perm(__float_as_uint(p2l), __float_as_uint(p2h), 0x5410);
+                            dp[row] = w;
                         }
                     } else {
 #pragma unroll
@@ -126,14 +187,95 @@ __global__ void __launch_bounds__(128) fill_intra_sw_score_kernel(ChunkGeom g, C
                             const uint32_t sub = prmt(ta, tb, sel[k]);
                             const uint32_t up = H[k];
                             const uint32_t tt = __viaddmax_s16x2(up, gF2, left);
-                            const uint32_t h = __viaddmax_s16x2_relu(diag, sub, tt);
+                            const uint32_t h = SW ? __viaddmax_s16x2_relu(diag, sub, tt) : __viaddmax_s16x2(diag, sub, tt);
                             left = add2(h, gR2);
                             H[k] = h;
-                            if (k < kv) best = __vmaxs2(best, h);  // columns past n stay out of the maximum
                             diag = up;
                         }
                     }
                     edge = left;
+                    if (SWS) {
+                        if (kv == TW) {
+#pragma unroll
+                            for (int k = 1; k < TW; k += 2) best = __vimax3_s16x2(best, H[k], H[k - 1]);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < TW; ++k)
+                                if (k < kv) best = __vmaxs2(best, H[k]);  // columns past n stay out of the maximum
+                        }
+                    }
+                    if (SWA && kv > 0) {
+                        // the row's maximum over my (valid) columns, both halves at once
+                        uint32_t rm = NEG2;
+                        if (kv == TW) {
+#pragma unroll
+                            for (int k = 1; k < TW; k += 2) rm = __vimax3_s16x2(rm, H[k], H[k - 1]);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < TW; ++k)
+                                if (k < kv) rm = __vmaxs2(rm, H[k]);
+                        }
+                        bool ge_b, ge_a;
+                        (void)__vibmax_s16x2(rm, gbest2, &ge_b, &ge_a);  // row maximum >= best so far?
+                        if (ge_a || ge_b) {
+                            const int ra = lo16(rm), rb = hi16(rm), ba = lo16(gbest2), bb = hi16(gbest2);
+                            // strictly greater, or equal in an earlier row (a later pass revisits earlier rows)
+                            const bool new_a = ra > ba || (ra == ba && gs_a >= 0 && row < gi_a);
+                            const bool new_b = rb > bb || (rb == bb && gs_b >= 0 && row < gi_b);
+                            if (new_a || new_b) {
+                                // park the row in the slot the other half's snapshot does not live in
+                                const int slot = (new_a && new_b) ? 0 : (new_a ? (src_b ^ 1) : (src_a ^ 1));
+                                uint32_t *sp = snap + slot * (TW * 32);
+#pragma unroll
+                                for (int k = 0; k < TW; ++k) sp[k * 32] = H[k];
+                                if (new_a) {
+                                    gbest2 = (gbest2 & 0xFFFF0000u) | (rm & 0x0000FFFFu);
+                                    gi_a = row;
+                                    gs_a = strip;
+                                    src_a = slot;
+                                }
+                                if (new_b) {
+                                    gbest2 = (gbest2 & 0x0000FFFFu) | (rm & 0xFFFF0000u);
+                                    gi_b = row;
+                                    gs_b = strip;
+                                    src_b = slot;
+                                }
+                            }
+                        }
+                    }
+                    if (!SW && last_pass && lane == last_lane) {
+                        // the last true column of this row: register kv-1 of this lane
+                        uint32_t lc = H[TW - 1];
+#pragma unroll
+                        for (int k = 0; k < TW - 1; ++k)
+                            if (kv == k + 1) lc = H[k];
+                        if (NWS) best = __vmaxs2(best, lc);                          // SSEKernel.cpp:1285-1291
+                        else bnd[row] = add2(lc, pk(-gF));                           // true H: the traceback's pad-column rule reads it
+                    }
+                    if (NWS && row == m - 1 && kv > 0) {  // whole last row (SSEKernel.cpp:1302-1310)
+#pragma unroll
+                        for (int k = 0; k < TW; ++k)
+                            if (k < kv) best = __vmaxs2(best, H[k]);
+                    }
+                    if (NWA && kv > 0 && (row == ra_last || row == rb_last)) {
+                        // the row the end-cell rule scans (DefaultKernel.cpp:352-355,381-387): per strip the best of its
+                        // columns as one key per lane, (H << 16) | (0xFFFF - column); the
+                        // traceback kernel reduces the strip keys of a pair (va_nw.cu's format, un-shifted values)
+                        int key_a = (int)0x80000000, key_b = (int)0x80000000;
+                        const uint32_t un = pk(-gF);  // registers hold H + gF; the keys carry the true H (long pairs: H - gap_ref*rows would leave 16 bits)
+#pragma unroll
+                        for (int k = 0; k < TW; ++k) {
+                            if (k < kv) {
+                                const uint32_t cand = add2(H[k], un);
+                                const uint32_t low = 0xFFFFu - (uint32_t)(c0 + k);
+                                key_a = max(key_a, (int)((cand << 16) | low));
+                                key_b = max(key_b, (int)((cand & 0xFFFF0000u) | low));
+                            }
+                        }
+                        uint32_t *hk = b.hrow + ((size_t)strip * g.duos + duo) * 2;
+                        if (row == ra_last) hk[0] = (uint32_t)key_a;
+                        if (row == rb_last) hk[1] = (uint32_t)key_b;
+                    }
                 }
                 // lane 31 finished row t-31: park its right edge in lane (t-31)&31 until 32 are there
                 if (!last_pass) {
@@ -153,34 +295,115 @@ __global__ void __launch_bounds__(128) fill_intra_sw_score_kernel(ChunkGeom g, C
             }
         }
     }
+    const unsigned long long cells = ((unsigned long long)ma.rows + (unsigned long long)mb.rows) * (unsigned long long)n;
+    if (!ALIGN) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) best = __vmaxs2(best, __shfl_xor_sync(FULL, best, o));
-    if (lane == 0) warp_best[warp] = best;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < W; ++w) best = __vmaxs2(best, warp_best[w]);
-        b.scores[b.pair_of[slot_a]] = (int16_t)(best & 0xFFFF);
-        b.scores[b.pair_of[slot_b]] = (int16_t)(best >> 16);
-        atomicAdd(b.cell_count, ((unsigned long long)ma.rows + (unsigned long long)mb.rows) * (unsigned long long)n);
+        for (int o = 16; o > 0; o >>= 1) best = __vmaxs2(best, __shfl_xor_sync(FULL, best, o));
+        if (lane == 0) warp_best[warp] = best;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < W; ++w) best = __vmaxs2(best, warp_best[w]);
+            b.scores[b.pair_of[slot_a]] = (int16_t)(best & 0xFFFF);
+            b.scores[b.pair_of[slot_b]] = (int16_t)(best >> 16);
+            atomicAdd(b.cell_count, cells);
+        }
+    } else if (SWA) {
+        // each lane: column of its best cell = first register of the snapshot that holds the value
+        int va = lo16(gbest2) - gF, vb = hi16(gbest2) - gF, ja = 0, jb = 0;
+        if (gs_a >= 0) {
+            const uint32_t *sp = snap + src_a * (TW * 32);
+            int k = 0;
+            while (k < TW - 1 && lo16(sp[k * 32]) != lo16(gbest2)) ++k;
+            ja = gs_a * 16 + k;
+        } else {
+            va = 0;
+        }
+        if (gs_b >= 0) {
+            const uint32_t *sp = snap + src_b * (TW * 32);
+            int k = 0;
+            while (k < TW - 1 && hi16(sp[k * 32]) != hi16(gbest2)) ++k;
+            jb = gs_b * 16 + k;
+        } else {
+            vb = 0;
+        }
+        // greatest value, then smallest row, then smallest column = first strictly greater cell in row-major order
+        auto better = [](int v, int i, int j, int ov, int oi, int oj) { return ov > v || (ov == v && (oi < i || (oi == i && oj < j))); };
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const int ova = __shfl_xor_sync(FULL, va, o), oia = __shfl_xor_sync(FULL, gi_a, o), oja = __shfl_xor_sync(FULL, ja, o);
+            const int ovb = __shfl_xor_sync(FULL, vb, o), oib = __shfl_xor_sync(FULL, gi_b, o), ojb = __shfl_xor_sync(FULL, jb, o);
+            if (better(va, gi_a, ja, ova, oia, oja)) { va = ova; gi_a = oia; ja = oja; }
+            if (better(vb, gi_b, jb, ovb, oib, ojb)) { vb = ovb; gi_b = oib; jb = ojb; }
+        }
+        if (lane == 0) {
+            warp_cell[warp][0][0] = va; warp_cell[warp][0][1] = gi_a; warp_cell[warp][0][2] = ja;
+            warp_cell[warp][1][0] = vb; warp_cell[warp][1][1] = gi_b; warp_cell[warp][1][2] = jb;
+        }
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            const int hf = threadIdx.x;
+            int v = warp_cell[0][hf][0], i = warp_cell[0][hf][1], j = warp_cell[0][hf][2];
+            for (int w = 1; w < W; ++w)
+                if (better(v, i, j, warp_cell[w][hf][0], warp_cell[w][hf][1], warp_cell[w][hf][2])) {
+                    v = warp_cell[w][hf][0]; i = warp_cell[w][hf][1]; j = warp_cell[w][hf][2];
+                }
+            if (v <= 0) v = i = j = 0;  // score 0: the traceback starts (and stops) at cell (0,0) (DefaultKernel.cpp:207-208)
+            const int p = b.pair_of[hf ? slot_b : slot_a];
+            b.scores[p] = (int16_t)v;
+            b.end_cell[2 * p] = (int16_t)i;
+            b.end_cell[2 * p + 1] = (int16_t)j;
+            if (hf == 0) atomicAdd(b.cell_count, cells);
+        }
+    } else {
+        if (threadIdx.x == 0) atomicAdd(b.cell_count, cells);
     }
+}
+
+template <int MODE, int POLICY, bool SYM>
+void launch_intra_inst(const ChunkGeom &g, const ChunkBuffers &b, const FastConsts &fc, int duos, int warps, cudaStream_t stream) {
+    const size_t smem = MODE == MODE_SW_ALIGN ? (size_t)warps * 2 * TW * 32 * sizeof(uint32_t) : 0;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(fill_intra_kernel<MODE, POLICY, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    fill_intra_kernel<MODE, POLICY, SYM><<<duos, 32 * warps, smem, stream>>>(g, b, fc);
 }
 
 }  // namespace
 
-// The intra-task kernel pays when one-thread-per-duo cannot fill the machine: few, long pairs.
+// The intra-task kernels pay when one-thread-per-duo cannot fill the machine: few, long pairs.
 bool intra_preferred(int mode, int n_pairs, int read_length, int ref_length, int sm_count) {
-    if (mode != MODE_SW_SCORE) return false;
+    (void)mode;
     const long long duos = n_pairs / 2;
     return ref_length >= 1024 && read_length >= 256 && duos < (long long)sm_count * 512;
 }
 
 int launch_fill_intra(const ChunkGeom &g, const ChunkBuffers &b, int mode, const FastConsts &fc, cudaStream_t stream) {
-    if (mode != MODE_SW_SCORE || g.n < 2) return 0;
+    if (g.n < 2) return 0;
     const int duos = g.n / 2;
-    // warps per duo: as many as there are column passes to pipeline, at most 4 (8 measured no better)
-    const int passes = (g.ref_length + 32 * 16 - 1) / (32 * 16);
-    const int warps = passes >= 4 ? 4 : passes >= 2 ? 2 : 1;
-    fill_intra_sw_score_kernel<16><<<duos, 32 * warps, 0, stream>>>(g, b, fc);
+    // warps per duo: as many as there are column passes to pipeline; at least 4 when the passes allow it (8 measured
+    // no better when duos are plentiful), more when the batch has too few duos to fill the device's warp slots
+    const int passes = (g.ref_length + 32 * TW - 1) / (32 * TW);
+    const int want = (148 * 16 + duos - 1) / duos;
+    int warps = std::max(4, std::min(want, MAX_WARPS));
+    warps = std::min(warps, passes);
+    if (warps >= 3 && warps != 4 && warps != 8 && warps != 16) warps = warps > 8 ? 8 : 4;  // 1, 2, 4, 8 or 16 warps per CTA
+    warps = std::max(warps, 1);
+    const bool sym = fc.gF == fc.gR;
+    switch (mode) {
+        case MODE_SW_SCORE: launch_intra_inst<MODE_SW_SCORE, 0, false>(g, b, fc, duos, warps, stream); break;
+        case MODE_NW_SCORE: launch_intra_inst<MODE_NW_SCORE, 0, false>(g, b, fc, duos, warps, stream); break;
+        case MODE_SW_ALIGN:
+            if (sym) launch_intra_inst<MODE_SW_ALIGN, 0, true>(g, b, fc, duos, warps, stream);
+            else launch_intra_inst<MODE_SW_ALIGN, 0, false>(g, b, fc, duos, warps, stream);
+            break;
+        default:
+            if (g.policy == 1) {
+                if (sym) launch_intra_inst<MODE_NW_ALIGN, 1, true>(g, b, fc, duos, warps, stream);
+                else launch_intra_inst<MODE_NW_ALIGN, 1, false>(g, b, fc, duos, warps, stream);
+            } else {
+                if (sym) launch_intra_inst<MODE_NW_ALIGN, 0, true>(g, b, fc, duos, warps, stream);
+                else launch_intra_inst<MODE_NW_ALIGN, 0, false>(g, b, fc, duos, warps, stream);
+            }
+            break;
+    }
     return 1;
 }
 

@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(256) encode_kernel(ChunkGeom g, ChunkBuffers b
                 const int pair_b = has_b ? (int)order[slot + 1] : 0;
                 if (has_b) cb = codes_pair_reads[(size_t)c * g.slots + pair_b];
                 // (equal sort keys = equal extents: nothing to shift, and no need to look at the meta records)
-                if (mode == MODE_NW_ALIGN && has_b && sorted_keys[slot] != sorted_keys[slot + 1]) {
+                if (mode == MODE_NW_ALIGN && !g.intra && has_b && sorted_keys[slot] != sorted_keys[slot + 1]) {
                     // packed NW align end-aligns a duo's lanes: the lane with fewer rows starts late, behind
                     // CODE_PRE rows (va_internal.h); only duos the packed kernel takes are ever read back
                     // (slots that end up solo sweep from their own row 0: no shift for them)

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
     const int owner = slot_owner(g, mode, slot, (slot & 1) ? meta_other : meta, (slot & 1) ? meta : meta_other);
     const bool packed = owner != OWN_NONE;
     // packed NW align end-aligns the lanes of a duo: this lane's matrix row r is sweep row r + row_off
-    const int row_off = (NW && owner == OWN_DUO) ? nw_row_offset(meta, meta_other) : 0;
+    const int row_off = (NW && owner == OWN_DUO) ? nw_row_offset(g, meta, meta_other) : 0;
     const int duo = slot >> 1, lane_shift = (slot & 1) * 16;
     const int pair = b.pair_of[slot];  // raw bytes and results are indexed in the caller's pair order
 
@@ -394,6 +394,260 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Long pairs (the chunk was filled by the intra-task kernels, va_intra.cu): ONE WARP per pair.
+//   walk  the direction words of a duo lie at [duo][16-column strip][row], consecutive rows = consecutive 8-byte
+//         words.  The warp keeps a window of 32 rows x 2 strips in registers (lane l: the words of row wr0 + l of
+//         strips ws and ws-1, two coalesced 256-byte loads) and follows the path through it with shuffles -- all
+//         lanes carry the same walk state -- so HBM latency is paid once per ~24 moves instead of once per move;
+//         a one-thread walk of a 10 kbp x 12 kbp pair is ~22 000 dependent loads.
+//   emit  the same warp replays the move queue (global memory) 32 moves per step, like traceback_kernel.
+// Pairs the general kernel computed (dirty refs, SSE/AVX policy in SW) walk its [segment][row][slot] half-words,
+// one broadcast load per move.
+// ------------------------------------------------------------------------------------------------------------
+template <bool NW>
+__global__ void __launch_bounds__(TB_THREADS) traceback_long_kernel(ChunkGeom g, ChunkBuffers b, Scoring sc, uint32_t *gq, int queue_words) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int slot = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    if (slot >= g.n) return;  // warp-uniform
+    const bool moves_only = b.moves_out != nullptr;
+    const bool compact = b.aln_compact != nullptr;
+    const int L = g.read_length + g.ref_length;
+    const int gap_ref = sc.gap_ref;
+    const PairMeta meta = b.meta[slot];
+    const int rows = meta.rows, cols = meta.cols;
+    const int mode = NW ? MODE_NW_ALIGN : MODE_SW_ALIGN;
+    const PairMeta meta_other = b.meta[slot ^ 1];
+    const bool packed = slot_owner(g, mode, slot, (slot & 1) ? meta_other : meta, (slot & 1) ? meta : meta_other) == OWN_DUO;
+    const int duo = slot >> 1, lane_shift = (slot & 1) * 16;
+    const int pair = b.pair_of[slot];
+    const int ns = g.ref_chunks;
+    const size_t rows2 = (size_t)intra_dir_rows(g);
+
+    // ---- end cell ----------------------------------------------------------------------
+    int i, j;
+    if (packed && NW) {
+        // arg-max of matrix row `rows` (first strictly greater column, column 0 = rows*gap_ref first): the fill kernel left
+        // one key per 16-column strip and lane, (H << 16) | (0xFFFF - column)
+        int key = (int)(((uint32_t)(rows * gap_ref) << 16) | 0xFFFFu);
+        const int nstrips = (cols + INTRA_TW - 1) / INTRA_TW;
+        const uint32_t *hk = b.hrow + (size_t)duo * 2 + (slot & 1);
+        for (int st = lane; st < nstrips; st += 32) key = max(key, (int)hk[(size_t)st * g.duos * 2]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) key = max(key, __shfl_xor_sync(FULL, key, o));
+        const int best = key >> 16, idx = 0xFFFF - (key & 0xFFFF);
+        i = rows - 1;
+        // pad columns (never filled) take part in the reference's arg-max: see traceback_kernel
+        const int pad_cols = g.ref_length - cols, reach = min(pad_cols, rows);
+        int col_max = (reach == rows && rows > 0) ? 0 : INT_MIN;  // matrix row 0
+        if (reach > 0) {
+            const uint32_t *bl = b.fboundary + (size_t)duo * g.rows_alloc;  // last true column, true H
+            for (int r = rows - 2 - lane; r >= rows - 1 - reach && r >= 0; r -= 32) col_max = max(col_max, (int)(int16_t)(bl[r] >> lane_shift));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) col_max = max(col_max, __shfl_xor_sync(FULL, col_max, o));
+        }
+        j = (pad_cols > 0 && col_max > best) ? (int)meta.max_ref_pos : min((int)meta.max_ref_pos, idx);
+        if (lane == 0) {
+            b.scores[pair] = (int16_t)best;
+            b.end_cell[2 * pair] = (int16_t)i;
+            b.end_cell[2 * pair + 1] = (int16_t)j;
+        }
+    } else {
+        i = b.end_cell[2 * pair];
+        j = b.end_cell[2 * pair + 1];
+    }
+    const int end_i = i, end_j = j;
+    const int score = (int)b.scores[pair];
+
+    // ---- walk (every lane carries the same state) ----------------------------------------
+    int final_i = end_i, final_j = end_j;
+    auto walk = [&](auto &&sink) -> int {
+        int i = end_i, j = end_j;
+        int n_moves = 0;
+        if (packed) {
+            const bool in_range = i >= 0 && i < rows && j < cols;
+            if (in_range && j >= 0 && (NW || score > 0)) {
+                const uint2 *base = reinterpret_cast<const uint2 *>(b.fdirs) + (size_t)duo * ns * rows2;
+                const uint32_t pol = (uint32_t)g.policy & 1u;
+                int strip = j >> 4, k = j & 15;
+                int ws = -2, wr0 = 0;  // window: rows [wr0, wr0 + 31] of strips ws and ws - 1
+                uint2 wa = make_uint2(0u, 0u), wb = make_uint2(0u, 0u);
+                int hval = NW ? 1 : score;
+                ByteWindow wread(seq_ptr(b.raw_reads, b.read_off, pair, g.read_length), seq_end(b.raw_reads, b.read_off, g.n, g.read_length));
+                ByteWindow wref(seq_ptr(b.raw_refs, b.ref_off, pair, g.ref_length), seq_end(b.raw_refs, b.ref_off, g.n, g.ref_length));
+                while (true) {
+                    if ((strip != ws && strip != ws - 1) || i < wr0) {
+                        ws = strip;
+                        wr0 = i - 31;
+                        const int row = wr0 + lane;
+                        if (row >= 0) {
+                            wa = __ldg(base + (size_t)ws * rows2 + row);
+                            if (ws > 0) wb = __ldg(base + (size_t)(ws - 1) * rows2 + row);
+                        }
+                    }
+                    const uint2 mine = strip == ws ? wa : wb;
+                    const int src = i - wr0;
+                    const uint32_t wx = __shfl_sync(FULL, mine.x, src), wy = __shfl_sync(FULL, mine.y, src);
+                    const int bit = lane_shift + k;
+                    const uint32_t dbit = (wx >> bit) & 1u, ubit = (wy >> bit) & 1u;
+                    const int code = dbit ? DIR_DIAG : ((ubit ^ pol) ? DIR_UP : DIR_LEFT);
+                    sink(code, n_moves);
+                    ++n_moves;
+                    if (!NW) {  // SW: a zero cell is START (DefaultKernel.cpp:240-241); the value is known along the path
+                        if (code == DIR_UP) hval -= sc.gap_ref;
+                        else if (code == DIR_LEFT) hval -= sc.gap_read;
+                        else {
+                            const unsigned ca = wread.get(i) & 0xDFu, cb = wref.get(j) & 0xDFu;
+                            const bool va = ca == 'A' || ca == 'C' || ca == 'G' || ca == 'T', vb = cb == 'A' || cb == 'C' || cb == 'G' || cb == 'T';
+                            hval -= (va && vb) ? (ca == cb ? sc.match : sc.mismatch) : 0;
+                        }
+                    }
+                    if (code != DIR_LEFT) --i;
+                    if (code != DIR_UP) {
+                        --j;
+                        if (k == 0) {
+                            --strip;
+                            k = 15;
+                        } else {
+                            --k;
+                        }
+                    }
+                    if ((i | j) < 0 || (!NW && hval <= 0)) break;
+                }
+            }
+            // matrix column 0 (DefaultKernel.cpp:304): NW walks up to row 0, SW stops
+            if (NW && i >= 0 && i < rows && j < 0) {
+                for (; i >= 0; --i) {
+                    sink(DIR_UP, n_moves);
+                    ++n_moves;
+                }
+            }
+        } else {
+            while (true) {
+                int code;
+                if (i < 0 || i >= rows || j >= cols) code = DIR_START;
+                else if (j < 0) code = NW ? DIR_UP : DIR_START;
+                else code = (b.dirs[((size_t)(j >> 3) * g.rows_alloc + i) * g.slots + slot] >> (2 * (j & 7))) & 3;
+                if (code == DIR_START) break;
+                sink(code, n_moves);
+                ++n_moves;
+                if (code != DIR_LEFT) --i;
+                if (code != DIR_UP) --j;
+            }
+        }
+        final_i = i;
+        final_j = j;
+        return n_moves;
+    };
+    // 2-bit queue sink: 16 moves per word, written by lane 0
+    uint32_t acc = 0;
+    uint32_t *qbase = gq + slot;
+    size_t qstride = (size_t)g.slots;
+    uint32_t *qcur = qbase;
+    auto queue_sink = [&](int code, int t) {
+        acc |= (uint32_t)code << (2 * (t & 15));
+        if ((t & 15) == 15) {
+            if (lane == 0) *qcur = acc;
+            qcur += qstride;
+            acc = 0;
+        }
+    };
+    int n_moves;
+    if (moves_only) {
+        // see traceback_kernel: CIGAR runs in walk order, or the raw queue when there are more runs than slots
+        uint32_t *out = b.moves_out + (size_t)pair * (queue_words + 1);
+        int cur = -1, len = 0, nruns = 0;
+        auto rle_sink = [&](int code, int) {
+            const int op = code == DIR_DIAG ? 0 : code == DIR_UP ? 1 : 2;
+            if (op == cur) {
+                ++len;
+            } else {
+                if (len) {
+                    if (nruns < queue_words && lane == 0) out[1 + nruns] = ((uint32_t)len << 4) | (uint32_t)cur;
+                    ++nruns;
+                }
+                cur = op;
+                len = 1;
+            }
+        };
+        n_moves = walk(rle_sink);
+        if (len) {
+            if (nruns < queue_words && lane == 0) out[1 + nruns] = ((uint32_t)len << 4) | (uint32_t)cur;
+            ++nruns;
+        }
+        if (nruns <= queue_words) {
+            if (lane == 0) out[0] = (uint32_t)nruns;
+        } else {
+            qbase = qcur = out + 1;
+            qstride = 1;
+            n_moves = walk(queue_sink);
+            if ((n_moves & 15) && lane == 0) *qcur = acc;
+            if (lane == 0) out[0] = 0x80000000u | (uint32_t)n_moves;
+        }
+        if (lane == 0) {
+            if (b.coords) {
+                int32_t *co = b.coords + 4 * (size_t)pair;
+                co[0] = final_i + 1;
+                co[1] = end_i + 1;
+                co[2] = final_j + 1;
+                co[3] = end_j + 1;
+            }
+            if (b.run_count) b.run_count[pair] = (uint32_t)nruns;
+            b.start[pair] = (int16_t)(L - 1 - n_moves);
+        }
+        return;
+    }
+    n_moves = walk(queue_sink);
+    if ((n_moves & 15) && lane == 0) *qcur = acc;
+    __syncwarp();
+    __threadfence_block();
+
+    // ---- emit (see traceback_kernel) -------------------------------------------------------
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const uint8_t *rd = seq_ptr(b.raw_reads, b.read_off, pair, g.read_length) + end_i;
+    const uint8_t *rf = seq_ptr(b.raw_refs, b.ref_off, pair, g.ref_length) + end_j;
+    uint8_t *oa, *ob;
+    if (compact) {
+        unsigned long long base = 0;
+        if (lane == 0) {
+            base = atomicAdd(b.compact_cursor, 2ull * (unsigned long long)(n_moves + 1));
+            b.compact_off[pair] = (uint32_t)base;
+        }
+        base = __shfl_sync(FULL, base, 0);
+        oa = b.aln_compact + (size_t)base + n_moves;
+        ob = oa + n_moves + 1;
+    } else {
+        oa = b.aln_read + (size_t)pair * L + (L - 1);
+        ob = b.aln_ref + (size_t)pair * L + (L - 1);
+    }
+    for (int t0 = 0; t0 < n_moves; t0 += 32) {
+        const int t = t0 + lane;
+        const bool valid = t < n_moves;
+        const uint32_t word = valid ? qbase[(size_t)(t >> 4) * qstride] : 0u;
+        const int code = (word >> (2 * (t & 15))) & 3;
+        const bool takes_r = valid && code != DIR_LEFT, takes_f = valid && code != DIR_UP;
+        const unsigned mr = __ballot_sync(FULL, takes_r), mf = __ballot_sync(FULL, takes_f);
+        uint8_t a = '-', c = '-';
+        if (takes_r) a = *(rd - __popc(mr & lt_mask));
+        if (takes_f) c = *(rf - __popc(mf & lt_mask));
+        if (valid && (compact || t <= L - 2)) {
+            oa[-1 - t] = a;
+            ob[-1 - t] = c;
+        }
+        rd -= __popc(mr);
+        rf -= __popc(mf);
+    }
+    if (lane == 0) {
+        b.start[pair] = (int16_t)(L - 1 - n_moves);
+        if (compact || L >= 1) {
+            *oa = 0;
+            *ob = 0;
+        }
+    }
+}
+
 // Packed entry points: pair i's runs leave the traceback in walk order in its fixed slot (or as the raw 2-bit
 // queue when there were more runs than slots); here they become the forward-order BAM CIGAR at run_offs[i].
 __global__ void __launch_bounds__(256) cigar_compact_kernel(int n, int queue_words, const uint32_t *__restrict__ moves,
@@ -451,11 +705,22 @@ bool traceback_needs_global_queue(int read_length, int ref_length) {
     return traceback_queue_words(read_length, ref_length) * TB_THREADS * sizeof(uint32_t) + 8 * TB_THREADS * sizeof(int) > 48 * 1024;
 }
 
+// long shapes may run the warp-per-pair traceback (chunks filled by the intra-task kernels), whose queues are always global
+bool traceback_wants_global_queue(int read_length, int ref_length) {
+    return traceback_needs_global_queue(read_length, ref_length) || (read_length >= 256 && ref_length >= 1024);
+}
+
 int launch_traceback(const ChunkGeom &g, const ChunkBuffers &b, int mode, const Scoring &sc, uint32_t *global_queue,
                      cudaStream_t stream) {
     if (g.n <= 0) return 0;
-    const int blocks = (g.n + TB_THREADS - 1) / TB_THREADS;
     const int qw = (int)traceback_queue_words(g.read_length, g.ref_length);
+    if (g.intra) {  // long pairs: one warp per pair, queues in global memory
+        const int blocks = (int)(((long long)g.n * 32 + TB_THREADS - 1) / TB_THREADS);
+        if (mode == MODE_NW_ALIGN) traceback_long_kernel<true><<<blocks, TB_THREADS, 0, stream>>>(g, b, sc, global_queue, qw);
+        else traceback_long_kernel<false><<<blocks, TB_THREADS, 0, stream>>>(g, b, sc, global_queue, qw);
+        return 1;
+    }
+    const int blocks = (g.n + TB_THREADS - 1) / TB_THREADS;
     const size_t smem = (size_t)qw * TB_THREADS * sizeof(uint32_t);
     const bool use_shared = !traceback_needs_global_queue(g.read_length, g.ref_length) && !b.moves_out;
     uint32_t *gq = use_shared ? nullptr : global_queue;
