@@ -349,7 +349,7 @@ def config_c4(torch, ctx, dev, roof_gcups, max_over_ranks, barrier, quick: bool)
     out["score_e2e_gcups"] = cells / sec / 1e9
     out["score_e2e_agrees_with_resident"] = bool(np.array_equal(sc, d_s.cpu().numpy()))
     # compute_alignments on a declared subset: the first n_aln pairs of every rank
-    n_aln = min(n, 16 if quick else 128)
+    n_aln = min(n, 64 if quick else 1184)  # 1184 pairs = 592 pair-of-pairs = one CTA wave of the intra-task kernel at 4 warps per CTA
     L = 22_000
     sub_r, sub_f = d_r[:n_aln].contiguous(), d_f[:n_aln].contiguous()
     d_a = torch.empty((n_aln, L), dtype=torch.uint8, device=dev)

@@ -1050,6 +1050,22 @@ void run_shard(va_cuda_ctx *ctx, Engine &e, const HostCall &c, int64_t lo, int64
 #undef SHARD_TRY
 }
 
+// Long-pair align chunks (intra-task kernels, va_intra.cu): a CTA per pair-of-pairs with 4, 8 or 16 warps, 16 warps per
+// SM -- so the device holds 4, 2 or 1 x sm_count duos at a time and a chunk should be exactly one such wave.  And the
+// direction words one launch touches should stay below ~24 GB: at 35 GB (1184 pairs of 10 kbp x 12 kbp) the fill ran 20 %
+// and the traceback 3x slower than at 18 GB -- the accesses are spread over more pages than the TLBs reach.
+int64_t intra_align_chunk_pairs(const Engine &e, const Shape &sh) {
+    const size_t per_duo = (size_t)sh.ref_chunks * 8 * (((size_t)sh.rows_alloc + 3) & ~(size_t)3);
+    const size_t limit = (size_t)24 << 30;
+    for (int waves : {4, 2, 1}) {
+        const int64_t duos = (int64_t)e.sm_count * waves;
+        if ((size_t)duos * per_duo <= limit || waves == 1) return 2 * duos;
+    }
+    return 2 * (int64_t)e.sm_count;
+}
+
+bool long_pair_shape(int read_length, int ref_length) { return read_length >= 256 && ref_length >= 1024; }
+
 int pick_chunk_pairs(const Engine &e, const Shape &sh, int64_t shard_pairs) {
     // device workspace budget per ring slot: a quarter of a third of the card, at most 6 GiB
     // (long pairs: tens of MB of directions per pair and next to nothing to copy -- fewer, larger chunks keep the
@@ -1064,6 +1080,10 @@ int pick_chunk_pairs(const Engine &e, const Shape &sh, int64_t shard_pairs) {
     static const int64_t min_chunk = [] { const char *v = getenv("VERSALIGN_CUDA_MIN_CHUNK"); return v && atoll(v) > 0 ? atoll(v) : 65536LL; }();
     int64_t want = std::max<int64_t>((shard_pairs + 7) / 8, min_chunk);
     want = std::min<int64_t>(want, cap);
+    // (only when a chunk of the usual size would go to the intra-task kernels anyway)
+    if (sh.align && long_pair_shape(sh.read_length, sh.ref_length) &&
+        intra_preferred(MODE_SW_ALIGN, (int)std::min<int64_t>(want, shard_pairs), sh.read_length, sh.ref_length, e.sm_count))
+        want = std::min<int64_t>(cap, intra_align_chunk_pairs(e, sh));
     want = std::min<int64_t>(want, std::max<int64_t>(shard_pairs, 1));
     want = (int64_t)round_up((size_t)want, 64);
     return (int)std::min<int64_t>(want, (int64_t)1 << 30);
@@ -1455,7 +1475,7 @@ int va_cuda_max_resident_pairs(va_cuda_ctx *ctx, int align, int read_length, int
     const Engine &e = ctx->engines[0];
     // (an align sub-chunk's direction region stays below 2^32 eight-byte words: the traceback walk's offsets are 32-bit)
     // (long pairs go through the intra-task layout and the warp-per-pair traceback, which index with 64 bits)
-    const bool long_pairs = read_length >= 256 && ref_length >= 1024;
+    const bool long_pairs = long_pair_shape(read_length, ref_length);
     const size_t budget = std::min<size_t>(e.total_mem / 2, align && !long_pairs ? (size_t)30 << 30 : (size_t)80 << 30);
     *max_n = (int64_t)(budget / std::max<size_t>(sh.per_pair_workspace(), 1));
     return VA_OK;
@@ -1476,7 +1496,10 @@ static int resident_call(va_cuda_ctx *ctx, int opt, bool align, int policy, cons
     CUDA_TRY(cudaSetDevice(e.device));
     int64_t max_n = 0;
     va_cuda_max_resident_pairs(ctx, align, read_length, ref_length, &max_n);
-    const int sub = (int)std::min<int64_t>(n, std::max<int64_t>(64, max_n / 64 * 64));
+    int64_t sub64 = std::max<int64_t>(64, max_n / 64 * 64);
+    if (align && long_pair_shape(read_length, ref_length) && intra_preferred(c.mode, (int)std::min<int64_t>(n, sub64), read_length, ref_length, e.sm_count))
+        sub64 = std::min<int64_t>(sub64, intra_align_chunk_pairs(e, c.sh));
+    const int sub = (int)std::min<int64_t>(n, sub64);
     rc = reserve_slot(e.resident, c.sh, sub, SLOT_RESIDENT);
     if (rc) return rc;
     ChunkSlot &ws = e.resident;

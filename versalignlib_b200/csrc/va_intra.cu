@@ -8,8 +8,8 @@
 //
 //   * lane l owns 16 consecutive ref columns of the current pass (512 columns per pass);
 //   * at step t lane l computes row t-l of its columns, so its left neighbour's right edge
-//     (computed one step earlier) arrives by __shfl_up_sync together with that row's table index; lane 0
-//     takes its inputs from a per-32-steps batch that all lanes load coalesced (row index, previous
+//     (computed one step earlier) arrives by __shfl_up_sync together with that row's two score tables; lane 0
+//     takes its inputs from a per-32-steps batch that all lanes load coalesced (row index -> tables, previous
 //     pass's boundary column);
 //   * lane 31's right edge is collected over 32 steps and stored coalesced as the next pass's
 //     boundary column;
@@ -29,6 +29,7 @@
 // Used when a batch has too few pairs to fill the GPU with one thread per pair-of-pairs and
 // the pairs are long (intra_preferred decides).
 #include <algorithm>
+#include <type_traits>
 
 #include "va_fast.cuh"
 
@@ -46,6 +47,10 @@ __device__ __forceinline__ int hi16(uint32_t v) { return (int)(int16_t)(v >> 16)
 constexpr int MAX_PASSES = 64;  // 32 000 columns / (32 lanes x 16 columns)
 constexpr int TW = INTRA_TW;
 constexpr int MAX_WARPS = 16;
+// register cap: 128 = 16 warps per SM (four per scheduler); the launcher sizes CTAs from it
+#ifndef VA_INTRA_MAXREG
+#define VA_INTRA_MAXREG 128
+#endif
 
 // One CTA = one duo; its W warps take the column passes round-robin (warp w: passes w, w+W, ...) and run
 // them as a pipeline: pass p+1 follows pass p a few dozen rows behind, reading the boundary column pass p
@@ -55,7 +60,7 @@ constexpr int MAX_WARPS = 16;
 // MODE: one of the four functions.  POLICY (NW align): which comparison the second plane records (0: UP >= LEFT,
 // 1: LEFT >= UP).  SYM (align): gap_read == gap_ref, so "H + gR" and "H + gF" are one register.
 template <int MODE, int POLICY, bool SYM>
-__global__ void __launch_bounds__(32 * MAX_WARPS, 1) fill_intra_kernel(ChunkGeom g, ChunkBuffers b, FastConsts fc) {
+__global__ void __maxnreg__(VA_INTRA_MAXREG) fill_intra_kernel(ChunkGeom g, ChunkBuffers b, FastConsts fc) {
     constexpr unsigned FULL = 0xffffffffu;
     constexpr bool ALIGN = MODE == MODE_SW_ALIGN || MODE == MODE_NW_ALIGN;
     constexpr bool SW = MODE == MODE_SW_SCORE || MODE == MODE_SW_ALIGN;
@@ -63,6 +68,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, 1) fill_intra_kernel(ChunkGeom
     __shared__ uint2 s_T2[64];            // [7*code_a + code_b] -> the two lanes' 4-entry score tables (49 used)
     __shared__ int prog[MAX_PASSES];      // rows of pass p whose right edge is in global memory
     __shared__ uint32_t warp_best[MAX_WARPS];
+    __shared__ uint32_t s_edge[MAX_WARPS][32];  // lane 31's right edges of the last (up to) 32 rows, per warp
     __shared__ int warp_cell[MAX_WARPS][2][3];  // SW align: per warp and half: value, row, column of its best cell
     extern __shared__ uint32_t s_snap[];  // SW align: [warp][slot 0/1][register][lane] row snapshots
     if (threadIdx.x < 64) s_T2[threadIdx.x] = threadIdx.x < 49 ? make_uint2(fc.tab[threadIdx.x / 7], fc.tab[threadIdx.x % 7]) : make_uint2(0u, 0u);
@@ -106,7 +112,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, 1) fill_intra_kernel(ChunkGeom
         const int c0 = c_base + lane * TW;
         const int kv = min(TW, max(0, n - c0));  // my valid columns in this pass
         const int strip = c0 >> 4;
-        uint32_t sel[TW], H[TW];
+        uint32_t sel[TW], H[TW], H2[TW];
 #pragma unroll
         for (int k = 0; k < TW; ++k) {
             const int col = min(c0 + k, n - 1);
@@ -117,15 +123,15 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, 1) fill_intra_kernel(ChunkGeom
             H[k] = ALIGN ? gF2 : 0u;  // matrix row 0 is 0 (align keeps H + gF)
         }
         uint32_t diag_next = ALIGN ? gF2 : 0u;            // H[row][c0] of the previous row, 0 for matrix row 0
-        uint32_t cur_idx = 0, edge = gR2;                 // what this lane used / produced at its last step
-        uint32_t out_keep = 0;                            // lane 31's right edges, one per lane, for the coalesced store
+        uint32_t cur_ta = 0, cur_tb = 0, edge = gR2;      // what this lane used / produced at its last step
         uint2 *dp = dirs2 + (size_t)strip * rows2;
+        uint2 w_even = make_uint2(0u, 0u);  // direction word of the even row before this one
 
         for (int t0 = 0; t0 < steps; t0 += 32) {
             // batch inputs of lane 0 for steps t0..t0+31: row r = t0 + lane
             const int r = t0 + lane;
             // matrix column 0 as "H + gR": 0 everywhere but NW align, where H(I,0) = I*gap_ref (DefaultKernel.cpp:304)
-            uint32_t bat_idx = 0, bat_left = NWA ? pk((r + 1) * gF + gR) : gR2;
+            uint32_t bat_a = 0, bat_b = 0, bat_left = NWA ? pk((r + 1) * gF + gR) : gR2;
             if (!first_pass && t0 < m) {
                 // the previous pass (another warp of this CTA when W > 1) must have left these rows
                 const int need = min(t0 + 32, m);
@@ -134,23 +140,26 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, 1) fill_intra_kernel(ChunkGeom
                 __threadfence_block();
             }
             if (r < m) {
-                bat_idx = ridx[(size_t)(r >> 4) * ridx_stride + (r & 15)];
+                const uint2 tt2 = s_T2[ridx[(size_t)(r >> 4) * ridx_stride + (r & 15)]];
+                bat_a = tt2.x;
+                bat_b = tt2.y;
                 if (!first_pass) bat_left = __ldcg(bnd + r);  // written by another warp: read it where it was written (L2)
             }
             __syncwarp();  // every lane has read its row before this warp overwrites the column below
             const int s_end = min(32, steps - t0);
-            for (int s = 0; s < s_end; ++s) {
+            // Two steps per loop iteration over two register sets (H -> H2 -> H): a row's new H[k] cannot overwrite the
+            // old one while the next cell still needs it as its diagonal, so one set costs a register move per cell.
+            auto do_step = [&](auto all_rows_valid, const int s, const uint32_t(&Hi)[TW], uint32_t(&H)[TW]) {
                 const int t = t0 + s;
                 // lane 0 reads the batch, every other lane takes what its left neighbour used last step
-                const uint32_t i0 = __shfl_sync(FULL, bat_idx, s), l0 = __shfl_sync(FULL, bat_left, s);
-                const uint32_t pi = __shfl_up_sync(FULL, cur_idx, 1), pl = __shfl_up_sync(FULL, edge, 1);
-                const uint32_t idx = lane == 0 ? i0 : pi;
+                const uint32_t a0 = __shfl_sync(FULL, bat_a, s), b0 = __shfl_sync(FULL, bat_b, s), l0 = __shfl_sync(FULL, bat_left, s);
+                const uint32_t pa = __shfl_up_sync(FULL, cur_ta, 1), pb = __shfl_up_sync(FULL, cur_tb, 1), pl = __shfl_up_sync(FULL, edge, 1);
+                const uint32_t ta = lane == 0 ? a0 : pa, tb = lane == 0 ? b0 : pb;
                 uint32_t left = lane == 0 ? l0 : pl;
                 const int row = t - lane;
-                if (row >= 0 && row < m) {
-                    cur_idx = idx;
-                    const uint2 tt2 = s_T2[idx];
-                    const uint32_t ta = tt2.x, tb = tt2.y;
+                if (decltype(all_rows_valid)::value || (row >= 0 && row < m)) {
+                    cur_ta = ta;
+                    cur_tb = tb;
                     uint32_t diag = diag_next;
                     diag_next = add2(left, dFR2);  // "H + gR" -> the diagonal's form (H in the score modes, H + gF in the align modes)
                     if (ALIGN) {
@@ -158,7 +167,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, 1) fill_intra_kernel(ChunkGeom
 #pragma unroll
                         for (int k = 0; k < TW; ++k) {
                             const uint32_t sub = prmt(ta, tb, sel[k]);  // table holds s - gF
-                            const uint32_t up = H[k];
+                            const uint32_t up = Hi[k];
                             bool dl, dh, ul, uh;
                             // up+gF vs left+gR; policy 0: UP before LEFT, policy 1: LEFT before UP
                             const uint32_t tmax = POLICY == 0 ? __vibmax_s16x2(up, left, &uh, &ul) : __vibmax_s16x2(left, up, &uh, &ul);
@@ -175,17 +184,24 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, 1) fill_intra_kernel(ChunkGeom
                             H[k] = SYM ? left : (SW ? __viaddmax_s16x2(h, gF2, gF2) : add2(h, gF2));  // max(h, 0) + gF
                             diag = up;
                         }
-                        if (kv > 0) {
+                        {
+                            // an even row keeps its word; the odd row after it stores both as one aligned 16-byte word (8-byte
+                            // stores of single rows cost the L2 twice the partial-sector writes: 2.2 -> 3.1 TCUPS; one 256-bit
+                            // store per four rows measured no better than this).  The last row of an odd-sized matrix goes out alone.
                             uint2 w;
                             w.x = __byte_perm(__float_as_uint(p1l), __float_as_uint(p1h), 0x5410);
                             w.y = __byte_perm(__float_as_uint(p2l), __float_as_uint(p2h), 0x5410);
-                            dp[row] = w;
+                            if (kv > 0) {
+                                if (row & 1) *reinterpret_cast<uint4 *>(dp + row - 1) = make_uint4(w_even.x, w_even.y, w.x, w.y);
+                                else if (row == m - 1) dp[row] = w;
+                            }
+                            w_even = w;
                         }
                     } else {
 #pragma unroll
                         for (int k = 0; k < TW; ++k) {
                             const uint32_t sub = prmt(ta, tb, sel[k]);
-                            const uint32_t up = H[k];
+                            const uint32_t up = Hi[k];
                             const uint32_t tt = __viaddmax_s16x2(up, gF2, left);
                             const uint32_t h = SW ? __viaddmax_s16x2_relu(diag, sub, tt) : __viaddmax_s16x2(diag, sub, tt);
                             left = add2(h, gR2);
@@ -215,9 +231,17 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, 1) fill_intra_kernel(ChunkGeom
                             for (int k = 0; k < TW; ++k)
                                 if (k < kv) rm = __vmaxs2(rm, H[k]);
                         }
-                        bool ge_b, ge_a;
-                        (void)__vibmax_s16x2(rm, gbest2, &ge_b, &ge_a);  // row maximum >= best so far?
-                        if (ge_a || ge_b) {
+                        // a new best: strictly greater than the best so far -- or equal to it in an EARLIER row, which only a
+                        // later pass can meet (rows above the row of the best so far)
+                        bool keep_b, keep_a;
+                        (void)__vibmax_s16x2(gbest2, rm, &keep_b, &keep_a);  // best so far >= row maximum?
+                        bool cand = !(keep_a && keep_b);
+                        if (row < max(gi_a, gi_b)) {
+                            bool ge_b, ge_a;
+                            (void)__vibmax_s16x2(rm, gbest2, &ge_b, &ge_a);
+                            cand = cand || ge_a || ge_b;
+                        }
+                        if (cand) {
                             const int ra = lo16(rm), rb = hi16(rm), ba = lo16(gbest2), bb = hi16(gbest2);
                             // strictly greater, or equal in an earlier row (a later pass revisits earlier rows)
                             const bool new_a = ra > ba || (ra == ba && gs_a >= 0 && row < gi_a);
@@ -276,21 +300,44 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, 1) fill_intra_kernel(ChunkGeom
                         if (row == ra_last) hk[0] = (uint32_t)key_a;
                         if (row == rb_last) hk[1] = (uint32_t)key_b;
                     }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < TW; ++k) H[k] = Hi[k];
                 }
-                // lane 31 finished row t-31: park its right edge in lane (t-31)&31 until 32 are there
+                // lane 31 finished row t-31: it parks its right edge in shared memory; every 32 rows the warp stores them coalesced
                 if (!last_pass) {
-                    const uint32_t v = __shfl_sync(FULL, edge, 31);
                     const int orow = t - 31;
                     if (orow >= 0) {
-                        if (lane == (orow & 31)) out_keep = v;
+                        if (lane == 31) s_edge[warp][orow & 31] = edge;
                         if ((orow & 31) == 31 || orow == m - 1) {
+                            __syncwarp();
                             const int row0 = orow & ~31;
-                            if (row0 + lane <= orow) bnd[row0 + lane] = out_keep;
+                            if (row0 + lane <= orow) bnd[row0 + lane] = s_edge[warp][lane];
                             __threadfence_block();
                             __syncwarp();
                             if (lane == 0) vprog[pass] = orow + 1;  // rows [0, orow] of this pass are out
                         }
                     }
+                }
+            };
+            // Batches in which every lane has a row (all but the first and the last one or two of a pass) run a copy of
+            // the step without the row test: with the test, the skipped path pins H to its input registers and the
+            // computed path pays a register move per cell to get there.
+            if (t0 >= 32 && t0 + 32 <= m) {
+                for (int s = 0; s < 32; s += 2) {
+                    do_step(std::true_type{}, s, H, H2);
+                    do_step(std::true_type{}, s + 1, H2, H);
+                }
+            } else {
+                int s = 0;
+                for (; s + 1 < s_end; s += 2) {
+                    do_step(std::false_type{}, s, H, H2);
+                    do_step(std::false_type{}, s + 1, H2, H);
+                }
+                if (s < s_end) {  // odd tail of the last batch
+                    do_step(std::false_type{}, s, H, H2);
+#pragma unroll
+                    for (int k = 0; k < TW; ++k) H[k] = H2[k];
                 }
             }
         }
