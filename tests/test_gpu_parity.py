@@ -474,3 +474,46 @@ def test_packed_inputs_in_pinned_memory(ctx):
     assert np.array_equal(coords[idx], wc)
     for k, i in enumerate(idx[:500]):
         assert np.array_equal(cigar[coff[i]:coff[i + 1]], wcig[woff[k]:woff[k + 1]]), i
+
+
+def test_c2_full_million_pairs_against_oracle(ctx):
+    """The whole C2 bench workload, not a sample: 1 M x (150 vs 150) NW compute_alignments, every start index, end
+    cell and byte of both gapped strings against the OpenMP oracle (about 15 s of host time on the GPU box)."""
+    n = 1_000_000
+    reads, refs = synth.uniform_batch(n, 150, 150, p_sub=0.08, q_indel=0.02, seed=synth.BASE_SEED + 2)
+    a, b, start, end = ctx.align_flat(ora.NW, 0, reads, refs)
+    bad = 0
+    for lo in range(0, n, 250_000):  # slices bound the oracle's output arrays
+        hi = lo + 250_000
+        oa, ob, ostart, oend = ora.align(ora.NW, 0, reads[lo:hi], refs[lo:hi])
+        assert np.array_equal(start[lo:hi], ostart) and np.array_equal(end[lo:hi], oend), lo
+        bad += used_region_equal(a[lo:hi], b[lo:hi], start[lo:hi], oa, ob, ostart).size
+    assert bad == 0
+
+
+def test_in_process_multi_device_shard():
+    """One context over every visible device: the pair range is sharded inside the C ABI (one host thread per device,
+    no exchange), results against the oracle -- flat, scattered and packed entry points.  Needs >= 2 GPUs."""
+    nd = capi.device_count()
+    if nd < 2:
+        pytest.skip("needs at least 2 CUDA devices")
+    reads, refs, rl, fl = synth.mixed_batch(150_001, 20, 120, p_sub=0.1, q_indel=0.02, seed=9)
+    with capi.CudaContext(devices=list(range(nd))) as mctx:
+        for opt in (ora.SW, ora.NW):
+            assert np.array_equal(mctx.score_flat(opt, reads, refs), ora.score(opt, reads, refs)), ("score", opt)
+            a, b, start, end = mctx.align_flat(opt, 0, reads, refs)
+            oa, ob, ostart, oend = ora.align(opt, 0, reads, refs)
+            assert np.array_equal(start, ostart) and np.array_equal(end, oend), ("align", opt)
+            assert used_region_equal(a, b, start, oa, ob, ostart).size == 0, ("strings", opt)
+        assert mctx.timings()["devices"] == nd
+        pr, ro = synth.pack_batch(reads, rl)
+        pf, fo = synth.pack_batch(refs, fl)
+        tr, tf = np.ascontiguousarray(reads[:, :int(rl.max())]), np.ascontiguousarray(refs[:, :int(fl.max())])
+        assert np.array_equal(mctx.score_packed(ora.SW, pr, ro, pf, fo), ora.score(ora.SW, tr, tf))
+        scores, coords, coff, cigar = mctx.align_packed(ora.NW, 0, pr, ro, pf, fo)
+        idx = np.arange(0, reads.shape[0], 37)
+        want = synth.cigar_from_strings(*ora.align(ora.NW, 0, np.ascontiguousarray(tr[idx]), np.ascontiguousarray(tf[idx])))
+        assert np.array_equal(coords[idx], want[0])
+        got_runs = [cigar[coff[i]:coff[i + 1]].tolist() for i in idx]
+        want_runs = [want[2][want[1][k]:want[1][k + 1]].tolist() for k in range(len(idx))]
+        assert got_runs == want_runs

@@ -215,7 +215,7 @@ struct PinBuf {
 
 // Device workspace of one chunk in flight.
 struct ChunkSlot {
-    DevBuf raw_reads, raw_refs, read_off, ref_off, code_reads, code_refs, row_idx, solo_list, meta, pair_of, prep_scratch, boundary, dirs, hrow, queue,
+    DevBuf raw_reads, raw_refs, read_off, ref_off, code_reads, code_refs, row_idx, solo_list, meta, pair_of, prep_scratch, boundary, dirs, zdirs, hrow, queue,
         scores, end_cell, start, moves, compact, compact_off, cursor, coords, run_count, run_offs, cigar, scan_tmp;
     PinBuf h_reads, h_refs, h_read_off, h_ref_off, h_scores, h_end_cell, h_start, h_compact, h_compact_off, h_cursor, h_coords, h_run_offs,
         h_cigar, h_moves;
@@ -232,7 +232,7 @@ struct ChunkSlot {
 
     void release() {
         DevBuf *d[] = {&raw_reads, &raw_refs, &read_off, &ref_off, &code_reads, &code_refs, &row_idx, &solo_list, &meta, &pair_of, &prep_scratch,
-                       &boundary, &dirs, &hrow, &queue, &scores, &end_cell, &start, &moves, &compact, &compact_off, &cursor, &coords,
+                       &boundary, &dirs, &zdirs, &hrow, &queue, &scores, &end_cell, &start, &moves, &compact, &compact_off, &cursor, &coords,
                        &run_count, &run_offs, &cigar, &scan_tmp};
         for (auto *b : d) b->release();
         PinBuf *h[] = {&h_reads, &h_refs, &h_read_off, &h_ref_off, &h_scores, &h_end_cell, &h_start, &h_compact, &h_compact_off, &h_cursor,
@@ -306,6 +306,7 @@ struct Shape {
     int read_chunks, ref_chunks, segs, rows_alloc;
     bool align;
     bool moves = false;    // align results leave the device as CIGAR runs (packed entry points), not as strings
+    bool zplane = false;   // SW align under the SSE/AVX pointer policy: the packed kernel stores a third plane
     bool offsets = false;  // inputs are offset-addressed (packed entry points): per-pair lengths, no padding
     bool stage_reads = true, stage_refs = true, stage_offs = true;  // false: that input is page-locked, no staging copy
     size_t queue_words() const { return traceback_queue_words(read_length, ref_length); }
@@ -317,6 +318,7 @@ struct Shape {
         size_t b = (size_t)(read_chunks + ref_chunks) * 32 + (size_t)read_chunks * 8 + 2 * sizeof(PairMeta) + 40 + (size_t)rows_alloc * 6;
         if (align) {
             b += dir_row_bytes() * (rows_alloc + 4) + (size_t)ref_length * 2 + 8;
+            if (zplane) b += fast_dirs_bytes_per_row_per_slot(ref_length) / 2 * (rows_alloc + 4);
             const size_t qw = traceback_queue_words(read_length, ref_length);
             if (traceback_wants_global_queue(read_length, ref_length)) b += qw * 4;
         }
@@ -416,6 +418,7 @@ int reserve_slot(ChunkSlot &s, const Shape &sh, int cap_pairs, SlotKind kind) {
     if ((rc = s.end_cell.reserve(slots * 4))) return rc;
     if (sh.align) {
         if ((rc = s.dirs.reserve(slots * sh.dir_row_bytes() * (sh.rows_alloc + 4) + 512))) return rc;  // (+4: the intra-task layout pads rows to a multiple of 4)
+        if (sh.zplane && (rc = s.zdirs.reserve(slots * (fast_dirs_bytes_per_row_per_slot(sh.ref_length) / 2) * (sh.rows_alloc + 4) + 512))) return rc;
         if ((rc = s.hrow.reserve(slots / 2 * (size_t)round_up((size_t)std::max(sh.ref_length, 1), 4) * 4 + 64))) return rc;
         // traceback move queue: shared memory unless the sequences are long
         const size_t qw = traceback_queue_words(sh.read_length, sh.ref_length);
@@ -514,7 +517,7 @@ int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int
             g.fast_tw = 16;
             g.intra = 1;
         } else if (fast_scoring_ok(mode, policy, sc, sh.read_length, sh.ref_length)) {
-            g.fast_tw = fast_pick_tw(mode, sh.ref_length);
+            g.fast_tw = fast_pick_tw(mode, sh.ref_length, g.policy);
         }
     }
     const bool intra = g.intra != 0;
@@ -535,6 +538,7 @@ int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int
     b.fboundary = (uint32_t *)((char *)ws.boundary.p + round_up((size_t)g.slots * sh.rows_alloc * 4, 256));
     b.dirs = (uint16_t *)ws.dirs.p;
     b.fdirs = (uint4 *)((char *)ws.dirs.p + round_up((size_t)g.slots * sh.gen_dir_row_bytes() * sh.rows_alloc, 256));
+    b.fdirs_z = sh.zplane ? (uint2 *)ws.zdirs.p : nullptr;
     b.scores = io.scores;
     b.end_cell = io.end_cell;
     b.aln_read = io.aln_read;
@@ -1172,6 +1176,7 @@ int prepare_call(va_cuda_ctx *ctx, HostCall &c, int opt, bool align, int policy,
     c.policy = policy;
     c.sc = Scoring{sc->match, sc->mismatch, sc->gap_read, sc->gap_ref};
     c.sh = make_shape(read_length, ref_length, align);
+    c.sh.zplane = align && policy == VA_POLICY_SIMD && c.mode == MODE_SW_ALIGN;
     c.n = n;
     return VA_OK;
 }

@@ -51,15 +51,15 @@ __device__ __forceinline__ void cp_async_wait() {
 // 5 x 96 leave 136): see va_nw.cu -- the pairs whose row loops ptxas compiles without parking predicates
 // (tools/check_sass.py).
 #ifndef VA_FAST_FORCE_NT
-template <int MODE, int TW, bool SYM, bool SOLO>
+template <int MODE, int TW, bool SYM, bool SOLO, int POLICY = 0>
 struct FastBlock {  // SW align duo kernel with equal gaps: 4 x 128 threads, 128 registers; everything else 5 x 96, 136
                     // (score: measured 1-3 % faster; SW align's solo / asymmetric-gap loops: clean only there)
-    static constexpr bool WIDE = MODE == MODE_SW_SCORE || (MODE == MODE_SW_ALIGN && (SOLO || !SYM));
+    static constexpr bool WIDE = MODE == MODE_SW_SCORE || (MODE == MODE_SW_ALIGN && (SOLO || !SYM || POLICY == 1));
     static constexpr int NT = WIDE ? 96 : 128;
     static constexpr int MAXREG = WIDE ? 136 : 128;
 };
 #else
-template <int MODE, int TW, bool SYM, bool SOLO>
+template <int MODE, int TW, bool SYM, bool SOLO, int POLICY = 0>
 struct FastBlock {
     static constexpr int NT = VA_FAST_FORCE_NT;
     static constexpr int MAXREG = VA_FAST_FORCE_NT == 96 ? 136 : 128;
@@ -71,14 +71,19 @@ struct FastBlock {
 // cell below needs) are the same register: one add less per cell in SW align.
 // SOLO: the instantiation for single slots whose duo is not fast (va_fast.cuh): same sweep, the owner's
 // halves of the shared words stored with 16-bit stores.
-template <int MODE, int TW, bool SYM, bool SOLO>
-__global__ void __maxnreg__((FastBlock<MODE, TW, SYM, SOLO>::MAXREG)) fill_fast_kernel(ChunkGeom g, ChunkBuffers b, FastConsts fc) {
+// POLICY (SW align): 0 = Default / OpenCL pointers (DIAG > UP > LEFT; a zero cell is START, recognised by the traceback
+// from the score along the path).  1 = SSE / AVX (SSEKernel.cpp:366-379: DIAG > LEFT > UP, no zero rule -- a cell is
+// START only when its value 0 beats all three candidates, so the walk runs on through zero cells): the second plane
+// records LEFT >= UP and a THIRD plane records "h >= 0" (not START), one more max with predicate outputs per cell.
+template <int MODE, int TW, bool SYM, bool SOLO, int POLICY = 0>
+__global__ void __maxnreg__((FastBlock<MODE, TW, SYM, SOLO, POLICY>::MAXREG)) fill_fast_kernel(ChunkGeom g, ChunkBuffers b, FastConsts fc) {
     constexpr bool SWA = MODE == MODE_SW_ALIGN;
     constexpr int NG = (TW + 15) / 16;
     static_assert(MODE == MODE_SW_ALIGN || MODE == MODE_SW_SCORE, "SW modes only");
 
     __shared__ uint2 s_T2[256];              // [7*code_a + code_b] -> the two lanes' 4-entry score tables (49 used)
-    constexpr int NT = FastBlock<MODE, TW, SYM, SOLO>::NT;
+    constexpr int NT = FastBlock<MODE, TW, SYM, SOLO, POLICY>::NT;
+    constexpr bool ZPLANE = SWA && POLICY == 1;
     __shared__ uint4 s_idx[3][NT];           // staged row indices: 16 rows per thread and buffer
     __shared__ uint32_t s_bnd[3][16][NT];    // staged right edge of the previous strip, [row][thread]
     for (int t = threadIdx.x; t < 256; t += NT) s_T2[t] = t < 49 ? make_uint2(fc.tab[t / 7], fc.tab[t % 7]) : make_uint2(0u, 0u);
@@ -96,6 +101,7 @@ __global__ void __maxnreg__((FastBlock<MODE, TW, SYM, SOLO>::MAXREG)) fill_fast_
         const uint8_t *cref = reinterpret_cast<const uint8_t *>(b.code_refs);
         uint32_t *bnd = b.fboundary;
         uint4 *dirs = b.fdirs;
+        uint2 *zdirs = b.fdirs_z;
 
         uint32_t best = 0;  // SW score: running max
         // SW align: best cell so far, per lane (first strictly greater in row-major order)
@@ -139,6 +145,7 @@ __global__ void __maxnreg__((FastBlock<MODE, TW, SYM, SOLO>::MAXREG)) fill_fast_
             {
                 uint32_t *bp = bnd + duo;
                 uint4 *dp = dirs + fast_dir_index(g, s, 0, 0, duo);
+                uint2 *zp = ZPLANE ? zdirs + fast_dir_index(g, s, 0, 0, duo) : nullptr;
                 const int nchunks = (m + 15) >> 4;
                 auto stage = [&](int c, int buf) {
                     cp_async16(&s_idx[buf][threadIdx.x], b.row_idx + (size_t)c * g.duos + duo);
@@ -150,7 +157,17 @@ __global__ void __maxnreg__((FastBlock<MODE, TW, SYM, SOLO>::MAXREG)) fill_fast_
                     }
                     cp_async_commit();
                 };
-                // one matrix row of this strip; SW align returns the row's two direction planes per group
+                // the third plane of one row (32 bits per group: 16 columns x both lanes) into its half of the row pair's word
+                auto store_z = [&](int half, const uint32_t(&z)[NG]) {
+#pragma unroll
+                    for (int q = 0; q < NG; ++q) {
+                        uint32_t *zw = reinterpret_cast<uint32_t *>(zp + (size_t)q * g.duos);
+                        if (!SOLO) zw[half] = z[q];
+                        else reinterpret_cast<uint16_t *>(zw)[2 * half + fw.lane] = (uint16_t)(z[q] >> (16 * fw.lane));
+                    }
+                };
+                // one matrix row of this strip; SW align returns the row's two direction planes per group (+ the third in wz)
+                uint32_t wz[NG];
                 auto do_row = [&](int i, const uint2 tt, uint32_t left_in, uint2(&w)[NG]) {
                     const uint32_t ta = tt.x, tb = tt.y;
                     // A solo thread shares its boundary words with another thread: the half that is not its own
@@ -161,17 +178,18 @@ __global__ void __maxnreg__((FastBlock<MODE, TW, SYM, SOLO>::MAXREG)) fill_fast_
                     uint32_t rowkey = 0;
                     uint32_t diag = diag_next;
                     diag_next = add2(left, dFR2);
-                    float p1l[NG], p1h[NG], p2l[NG], p2h[NG];
+                    float p1l[NG], p1h[NG], p2l[NG], p2h[NG], p3l[NG], p3h[NG];
                     uint32_t prev_key = 0;
 #pragma unroll
-                    for (int q = 0; q < NG; ++q) p1l[q] = p1h[q] = p2l[q] = p2h[q] = 8388608.0f;
+                    for (int q = 0; q < NG; ++q) p1l[q] = p1h[q] = p2l[q] = p2h[q] = p3l[q] = p3h[q] = 8388608.0f;
 #pragma unroll
                     for (int k = 0; k < TW; ++k) {
                         const uint32_t sub = prmt(ta, tb, sel[k]);
                         const uint32_t up = H[k];
                         if (SWA) {
                             bool dl, dh, ul, uh;
-                            const uint32_t t = __vibmax_s16x2(up, left, &uh, &ul);  // up+gF >= left+gR : UP before LEFT
+                            // policy 0: up+gF >= left+gR -> UP before LEFT; policy 1: the other way round
+                            const uint32_t t = POLICY == 0 ? __vibmax_s16x2(up, left, &uh, &ul) : __vibmax_s16x2(left, up, &uh, &ul);
                             const uint32_t d = add2(diag, sub);                     // diag + s (table holds s - gF)
                             uint32_t h = __vibmax_s16x2(d, t, &dh, &dl);            // diag+s >= max(up,left) : DIAG first
                             const float bit = (float)(1u << (k & 15));
@@ -181,8 +199,17 @@ __global__ void __maxnreg__((FastBlock<MODE, TW, SYM, SOLO>::MAXREG)) fill_fast_
                             if (uh) p2h[k >> 4] += bit;
                             // the pointer of a positive cell is the NW rule; a zero cell is START, which the
                             // traceback recognises by tracking the score (DefaultKernel.cpp:238-248)
-                            left = __viaddmax_s16x2(h, gR2, fc.swa_l0);           // max(h, 0) + gR   (biased)
-                            H[k] = SYM ? left : __viaddmax_s16x2(h, gF2, fc.swa_g0);
+                            if (ZPLANE) {
+                                bool zh, zl;
+                                h = __vibmax_s16x2(h, fc.swa_zero, &zh, &zl);      // h >= 0: the cell has a pointer (not START)
+                                if (zl) p3l[k >> 4] += bit;
+                                if (zh) p3h[k >> 4] += bit;
+                                left = add2(h, gR2);
+                                H[k] = SYM ? left : add2(h, gF2);
+                            } else {
+                                left = __viaddmax_s16x2(h, gR2, fc.swa_l0);       // max(h, 0) + gR   (biased)
+                                H[k] = SYM ? left : __viaddmax_s16x2(h, gF2, fc.swa_g0);
+                            }
                             const uint32_t key = left * k32 + (uint32_t)(31 - k) * 0x00010001u;  // k32 = 32, opaque: stays an IMAD (FMA pipe)
                             if (k & 1) {
                                 rowkey = __vimax3_s16x2(rowkey, key, prev_key);
@@ -220,6 +247,7 @@ __global__ void __maxnreg__((FastBlock<MODE, TW, SYM, SOLO>::MAXREG)) fill_fast_
                         for (int q = 0; q < NG; ++q) {
                             w[q].x = __byte_perm(__float_as_uint(p1l[q]), __float_as_uint(p1h[q]), 0x5410);
                             w[q].y = __byte_perm(__float_as_uint(p2l[q]), __float_as_uint(p2h[q]), 0x5410);
+                            if (ZPLANE) wz[q] = __byte_perm(__float_as_uint(p3l[q]), __float_as_uint(p3h[q]), 0x5410);
                         }
                     }
                 };
@@ -247,7 +275,7 @@ __global__ void __maxnreg__((FastBlock<MODE, TW, SYM, SOLO>::MAXREG)) fill_fast_
                     const int r0 = c * 16, rend = min(16, m - r0);
                     // two rows per iteration: their direction words leave as one 16-byte store per group
                     int r = 0;
-                    for (; r + 1 < rend; r += 2, dp += (size_t)NG * g.duos) {
+                    for (; r + 1 < rend; r += 2, dp += (size_t)NG * g.duos, zp += ZPLANE ? (size_t)NG * g.duos : 0) {
                         const uint2 t0 = nt0, t1 = nt1;
                         const uint32_t l0 = nl0, l1 = nl1;
                         {  // rows r+2, r+3 (the first two rows of the next chunk after rows 14, 15)
@@ -267,11 +295,13 @@ __global__ void __maxnreg__((FastBlock<MODE, TW, SYM, SOLO>::MAXREG)) fill_fast_
                         if (SWA) {
 #pragma unroll
                             for (int q = 0; q < NG; ++q) store_half<SOLO>(dp + (size_t)q * g.duos, 0, w0[q], fw);
+                            if (ZPLANE) store_z(0, wz);
                         }
                         do_row(r0 + r + 1, t1, l1, w0);
                         if (SWA) {
 #pragma unroll
                             for (int q = 0; q < NG; ++q) store_half<SOLO>(dp + (size_t)q * g.duos, 1, w0[q], fw);
+                            if (ZPLANE) store_z(1, wz);
                         }
                     }
                     if (r < rend) {  // odd row count (last chunk only): the last word holds one row
@@ -280,6 +310,7 @@ __global__ void __maxnreg__((FastBlock<MODE, TW, SYM, SOLO>::MAXREG)) fill_fast_
                         if (SWA) {
 #pragma unroll
                             for (int q = 0; q < NG; ++q) store_half<SOLO>(dp + (size_t)q * g.duos, 0, w0[q], fw);
+                            if (ZPLANE) store_z(0, wz);
                         }
                     }
                     buf = buf1;
@@ -335,14 +366,14 @@ __global__ void __maxnreg__((FastBlock<MODE, TW, SYM, SOLO>::MAXREG)) fill_fast_
     if ((threadIdx.x & 31) == 0 && cells) atomicAdd(b.cell_count, cells);
 }
 
-template <int MODE, int TW, bool SYM, bool SOLO>
+template <int MODE, int TW, bool SYM, bool SOLO, int POLICY = 0>
 void launch_inst(const ChunkGeom &g, const ChunkBuffers &b, const FastConsts &fc, cudaStream_t stream) {
-    const int threads = FastBlock<MODE, TW, SYM, SOLO>::NT;
+    const int threads = FastBlock<MODE, TW, SYM, SOLO, POLICY>::NT;
     const int duos = (g.n + 1) / 2;
     const int blocks = (duos + threads - 1) / threads;
     // duo grid: one thread per duo.  solo grid: a fixed grid strides over the list the prep kernel compiled
     // (va_fast.cuh); empty on a uniform batch, where the blocks read the count and leave.
-    fill_fast_kernel<MODE, TW, SYM, SOLO><<<SOLO ? std::min(2 * blocks, 148 * 4) : blocks, threads, 0, stream>>>(g, b, fc);
+    fill_fast_kernel<MODE, TW, SYM, SOLO, POLICY><<<SOLO ? std::min(2 * blocks, 148 * 4) : blocks, threads, 0, stream>>>(g, b, fc);
 }
 
 template <int MODE, int TW>
@@ -360,6 +391,16 @@ void launch_one(const ChunkGeom &g, const ChunkBuffers &b, const FastConsts &fc,
 template <int MODE>
 void launch_tw(const ChunkGeom &g, const ChunkBuffers &b, const FastConsts &fc, cudaStream_t stream) {
     if constexpr (MODE == MODE_SW_ALIGN) {  // more live state per cell: narrower strips keep it in registers
+        if (g.policy == 1) {  // SSE/AVX pointers: 16-column strips only (fast_pick_tw)
+            if (fc.gF == fc.gR) {
+                if (g.n >= 2) launch_inst<MODE, 16, true, false, 1>(g, b, fc, stream);
+                if (g.solo) launch_inst<MODE, 16, true, true, 1>(g, b, fc, stream);
+            } else {
+                if (g.n >= 2) launch_inst<MODE, 16, false, false, 1>(g, b, fc, stream);
+                if (g.solo) launch_inst<MODE, 16, false, true, 1>(g, b, fc, stream);
+            }
+            return;
+        }
         switch (g.fast_tw) {
             case 16: launch_one<MODE, 16>(g, b, fc, stream); break;
             default: launch_one<MODE, 20>(g, b, fc, stream); break;
@@ -389,9 +430,9 @@ bool fits8(int v) { return v >= -128 && v <= 127; }
 // cell can leave the int16 range; otherwise the call stays on the general 32-bit kernel.
 bool fast_scoring_ok(int mode, int policy, const Scoring &sc, int read_length, int ref_length, bool intra) {
     const bool align = mode == MODE_NW_ALIGN || mode == MODE_SW_ALIGN;
-    // SSE/AVX pointer rule: packed for NW align (the second plane records LEFT >= UP, va_nw.cu); SW align under
-    // that rule walks through zero cells and needs a third plane -- general kernel
-    if (align && policy != 0 && mode != MODE_NW_ALIGN) return false;
+    // SSE/AVX pointer rule: the second plane records LEFT >= UP (va_nw.cu, va_fast.cu); SW align under that rule walks
+    // through zero cells and stores a third plane -- inter-task kernel only (the intra-task one has no room for it yet)
+    if (align && policy != 0 && mode == MODE_SW_ALIGN && intra) return false;
     int mx = 1;
     for (int v : {sc.match, sc.mismatch, sc.gap_read, sc.gap_ref}) mx = max(mx, v < 0 ? -v : v);
     // the most one diagonal step can add: a "mismatch" score above the match score counts too
@@ -429,7 +470,8 @@ bool fast_scoring_ok(int mode, int policy, const Scoring &sc, int read_length, i
     return top + mx <= 32000 && mx <= 8000;
 }
 
-int fast_pick_tw(int mode, int ref_length) {
+int fast_pick_tw(int mode, int ref_length, int policy) {
+    if (mode == MODE_SW_ALIGN && policy == 1) return 16;  // three planes: one group of 16 columns
     if (mode == MODE_SW_ALIGN) {
         if (const char *v = getenv("VERSALIGN_CUDA_SWA_TW")) {
             const int t = atoi(v);
@@ -483,6 +525,7 @@ FastConsts make_fast_consts(int mode, const Scoring &sc) {
         fc.swa_g0 = pk(sc.gap_ref + B);    // matrix row 0 / zero floor, as "H + gF"
         fc.swa_off = sc.gap_read + B;      // key>>5 minus this is the cell value
         fc.swa_k32 = 32;
+        fc.swa_zero = pk(B);
     }
     return fc;
 }

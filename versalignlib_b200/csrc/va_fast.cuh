@@ -20,6 +20,10 @@ __device__ __forceinline__ bool duo_is_fast(const ChunkGeom &g, int mode, int sl
     if ((a.flags & 2) || (b.flags & 2)) return false;
     if (a.cols != b.cols || a.cols <= 0) return false;
     if (a.cols != a.true_cols || b.cols != b.true_cols) return false;  // no padded / N tail inside the sweep
+    // SSE/AVX policy, SW: DIAG only between two ACGT bases (SSEKernel.cpp:366-379) -- the planes cannot say "masked",
+    // so no non-ACGT byte inside the swept read rows either (NW rows end at the first one anyway)
+    // (a row past the read's last base -- the one row an empty read is given -- counts as one too)
+    if (mode == MODE_SW_ALIGN && g.policy == 1 && (((a.flags | b.flags) & 1) || a.rows > a.true_rows || b.rows > b.true_rows)) return false;
     // NW align's end-cell rule reads each lane's last valid row from the registers after the sweep: lanes
     // of different read lengths are end-aligned (nw_row_offset), so both need at least one row
     // (the intra-task kernel starts both lanes at row 0 and captures each lane's own last row)
@@ -35,6 +39,7 @@ __device__ __forceinline__ bool duo_is_fast(const ChunkGeom &g, int mode, int sl
 __device__ __forceinline__ bool solo_ok(const ChunkGeom &g, int slot, const PairMeta &m) {
     if (g.fast_tw == 0 || !g.solo || slot >= g.n) return false;
     if (m.flags & 2) return false;
+    if (g.policy == 1 && ((m.flags & 1) || m.rows > m.true_rows)) return false;  // (see duo_is_fast; g.policy is 0 in the score modes)
     return m.cols > 0 && m.cols == m.true_cols && m.rows > 0;
 }
 

@@ -66,6 +66,7 @@ struct FastConsts {
     int gF, gR;
     // SW align only (see va_fast.cu): biased initial values and key constants
     uint32_t swa_l0, swa_g0, swa_k32;
+    uint32_t swa_zero;  // the biased value of a zero cell (SSE/AVX policy: "not START" is h >= 0)
     int swa_off;
 };
 
@@ -88,6 +89,8 @@ struct ChunkBuffers {
     uint16_t *dirs;            // general kernel: [segs][rows_alloc][slots] half-words, 2 bits per cell, 8 cells each
     uint4 *fdirs;              // packed kernel:  [strip][row pair][group][duos], see va_fast.cuh
                                // (separate regions: one chunk can hold pairs of both kinds)
+    uint2 *fdirs_z;            // packed SW align under the SSE/AVX policy: third plane "cell is not START" (h >= 0), same
+                               // indexing as fdirs, .x = even row / .y = odd row of the pair, low 16 bits lane A; else NULL
     int32_t *solo_list;        // [slots] slots the packed kernels take on their own (va_fast.cuh), written by the prep
     int32_t *solo_count;       // kernel in no particular order; *solo_count entries
     uint32_t *hrow;            // packed NW align: [strip][duo][2] arg-max key of the last valid matrix row per strip and lane
@@ -122,7 +125,7 @@ int launch_fill_general(const ChunkGeom &g, const ChunkBuffers &b, int mode, int
 // packed kernels (va_fast.cu)
 // intra: the intra-task kernels' domain (SW align without the 16-bit best-cell key, NW modes un-shifted)
 bool fast_scoring_ok(int mode, int policy, const Scoring &sc, int read_length, int ref_length, bool intra = false);
-int fast_pick_tw(int mode, int ref_length);
+int fast_pick_tw(int mode, int ref_length, int policy = 0);
 size_t fast_dirs_bytes_per_row_per_slot(int ref_length);
 FastConsts make_fast_consts(int mode, const Scoring &sc);
 int launch_fill_fast(const ChunkGeom &g, const ChunkBuffers &b, int mode, const Scoring &sc, cudaStream_t stream);

@@ -40,7 +40,6 @@ namespace {
 constexpr uint32_t NEG2 = 0x80008000u;
 __device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b) { return __viaddmax_s16x2(a, b, NEG2); }
 __device__ __forceinline__ uint32_t pk(int v) { return ((uint32_t)v & 0xFFFFu) * 0x00010001u; }
-__device__ __forceinline__ uint32_t pk2(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
 __device__ __forceinline__ int lo16(uint32_t v) { return (int)(int16_t)(v & 0xFFFFu); }
 __device__ __forceinline__ int hi16(uint32_t v) { return (int)(int16_t)(v >> 16); }
 
@@ -425,6 +424,8 @@ bool intra_preferred(int mode, int n_pairs, int read_length, int ref_length, int
 int launch_fill_intra(const ChunkGeom &g, const ChunkBuffers &b, int mode, const FastConsts &fc, cudaStream_t stream) {
     if (g.n < 2) return 0;
     const int duos = g.n / 2;
+    // (a nearly empty second wave is cheap -- its CTAs have the SMs to themselves -- so 625 duos run faster as 592 + 33
+    // CTAs of 4 warps than as one wave of 2-warp CTAs: measured 4.2 vs 3.2 TCUPS)
     // warps per duo: as many as there are column passes to pipeline; at least 4 when the passes allow it (8 measured
     // no better when duos are plentiful), more when the batch has too few duos to fill the device's warp slots
     const int passes = (g.ref_length + 32 * TW - 1) / (32 * TW);

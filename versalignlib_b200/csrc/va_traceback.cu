@@ -158,7 +158,10 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
                 k += kmin;
             }
             const bool in_range = i >= 0 && i < rows && j < cols;
-            if (in_range && j >= 0 && (NW || (int)b.scores[pair] > 0)) {
+            // SW under the SSE/AVX policy (g.policy 1): no zero rule -- the walk follows the pointers through zero cells until
+            // the third plane says START (h < 0 before the floor); it begins even when the score is 0
+            const bool sw_simd = !NW && g.policy == 1;
+            if (in_range && j >= 0 && (NW || sw_simd || (int)b.scores[pair] > 0)) {
                 // 32-bit offsets in uint2 units (the host keeps a chunk's direction region below 2^32 of them)
                 const uint32_t group_step2 = 2u * (uint32_t)g.duos;                      // next group
                 const uint32_t pair_step2 = (uint32_t)ng * group_step2;                  // next row pair
@@ -169,6 +172,7 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
                 const uint32_t up_even = pair_step2 - 1u;  // from an even sweep row to the odd row above it
                 const uint32_t strip_back = strip_step2 - (uint32_t)((tw - 1) >> 4) * group_step2;  // to the last group of the strip before
                 int bit = lane_shift + (k & 15);
+                const uint32_t *z32 = reinterpret_cast<const uint32_t *>(b.fdirs_z) + 2 * (size_t)duo;  // same numbering as base2
                 uint2 w = __ldg(base2 + off);
                 // SW: the packed fill stores the pointer a cell would have in NW; a cell whose value is 0 is
                 // START (DefaultKernel.cpp:240-241).  The value is known along the path: it starts at the best
@@ -178,12 +182,13 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
                 ByteWindow wread(seq_ptr(b.raw_reads, b.read_off, pair, g.read_length), seq_end(b.raw_reads, b.read_off, g.n, g.read_length));
                 ByteWindow wref(seq_ptr(b.raw_refs, b.ref_off, pair, g.ref_length), seq_end(b.raw_refs, b.ref_off, g.n, g.ref_length));
                 while (true) {
+                    if (sw_simd && !((__ldg(z32 + off) >> bit) & 1u)) break;  // START
                     const uint32_t dbit = (w.x >> bit) & 1u, ubit = (w.y >> bit) & 1u;
                     // second plane: UP >= LEFT (policy 0) or LEFT >= UP (policy 1, SSE/AVX tie order)
                     const int code = dbit ? DIR_DIAG : ((ubit ^ pol) ? DIR_UP : DIR_LEFT);
                     sink(code, n_moves);
                     ++n_moves;
-                    if (!NW) {
+                    if (!NW && !sw_simd) {
                         if (code == DIR_UP) hval -= sc.gap_ref;
                         else if (code == DIR_LEFT) hval -= sc.gap_read;
                         else {
@@ -213,7 +218,7 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
                             --bit;
                         }
                     }
-                    if ((i | j) < 0 || (!NW && hval <= 0)) break;
+                    if ((i | j) < 0 || (!NW && !sw_simd && hval <= 0)) break;
                     w = __ldg(base2 + off);
                 }
             }
