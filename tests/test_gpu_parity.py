@@ -252,6 +252,22 @@ def test_packed_entry_points(ctx, opt):
                 assert np.array_equal(scores, ora.score(opt, reads, refs)), (name, policy)
 
 
+def test_packed_entry_points_gap_rich_alignments(ctx):
+    """Cheap gaps and expensive mismatches give alignments with far more CIGAR runs than move slots: every size
+    class of the device-side compaction -- fits the estimate, needs the second copy, exceeds the pinned block,
+    exceeds the device block (moves replayed on the host) -- must return the oracle's CIGARs (regression: the pinned
+    block is rounded differently from the device block and the zone between the two failed with 'invalid argument')."""
+    for n, rl, fl, seed in [(3000, 64, 96, 21), (20_000, 40, 40, 22), (70_000, 24, 31, 23)]:
+        reads, refs = synth.uniform_batch(n, rl, fl, independent=True, seed=seed)
+        pr, ro = synth.pack_batch(reads)
+        pf, fo = synth.pack_batch(refs)
+        for sc in [(2, -30, -1, -1), (2, -1, -3, -3), (5, -4, -1, -7)]:
+            for opt in (ora.SW, ora.NW):
+                scores, coords, coff, cigar = ctx.align_packed(opt, 0, pr, ro, pf, fo, sc)
+                want_coords, want_off, want_cigar = synth.cigar_from_strings(*ora.align(opt, 0, reads, refs, sc))
+                assert np.array_equal(coff, want_off) and np.array_equal(cigar, want_cigar) and np.array_equal(coords, want_coords), (n, sc, opt)
+
+
 def test_positive_gap_scores_stay_exact(ctx):
     """Gap scores > 0 are outside the packed kernels' domain (their padding arguments need gaps <= 0):
     the general kernel must take over, results unchanged."""

@@ -770,7 +770,8 @@ int scatter_packed(va_cuda_ctx *ctx, Engine &e, const HostCall &c, ChunkSlot &s,
     CigarPart cp;
     cp.first = first;
     cp.count = count;
-    if (total > s.cigar.cap / 4) {
+    // (the pinned block may be a little smaller than the device block: the two round their sizes differently)
+    if (total > std::min(s.cigar.cap, s.h_cigar.cap) / 4) {
         // does not fit the compaction buffer (nothing was written past it): fetch the per-pair moves instead
         const size_t mv_bytes = (size_t)count * (c.sh.queue_words() + 1) * 4;
         int rc = s.h_moves.reserve(mv_bytes + 16);
@@ -1010,7 +1011,7 @@ void run_shard(va_cuda_ctx *ctx, Engine &e, const HostCall &c, int64_t lo, int64
             st.d2h += (int64_t)count * 2;
         } else if (moves) {
             // scores, coordinates, run offsets; the runs themselves for as many as the last chunk had per pair (+ margin)
-            const size_t cap_words = s.cigar.cap / 4;
+            const size_t cap_words = std::min(s.cigar.cap, s.h_cigar.cap) / 4;
             const size_t want = e.est_per_pair > 0 ? (size_t)(e.est_per_pair * 1.05 * count) + 1024 : cap_words;
             s.sent = std::min(cap_words, std::min(want, (size_t)count * (c.sh.queue_words() + 1)));
             SHARD_TRY(cudaMemcpyAsync(s.h_run_offs.p, s.run_offs.p, (size_t)(count + 1) * 4, cudaMemcpyDeviceToHost, s.stream));
