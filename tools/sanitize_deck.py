@@ -1,4 +1,6 @@
-"""Small all-modes deck for compute-sanitizer (memcheck): every kernel, both policies, ragged sizes."""
+"""Small all-modes deck for compute-sanitizer (memcheck / racecheck): every kernel -- inter-task packed, intra-task
+packed (the 700 x 1100 deck: CTA-pipelined wavefront passes, warp-per-pair traceback), general -- both pointer
+policies, ragged sizes, all result containers."""
 import os
 import sys
 
@@ -25,6 +27,11 @@ def main():
                         ctx.align_flat(opt, pol, reads, refs, sc)
                 ctx.score_ptrs(0, reads, refs, sc)
                 ctx.align_ptrs(1, 0, reads, refs, sc)
+            pr, ro = synth.pack_batch(reads)
+            pf, fo = synth.pack_batch(refs)
+            ctx.score_packed(0, pr, ro, pf, fo)
+            for opt in (0, 1):
+                ctx.align_packed(opt, 1 - opt, pr, ro, pf, fo)
     print("sanitize deck done")
 
 
