@@ -26,7 +26,7 @@ class Scoring(ctypes.Structure):
 
 def build(force: bool = False) -> None:
     """Compile the oracle (and the reference kernels when /root/reference is mounted)."""
-    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(os.path.join(HERE, "va_oracle.c")):
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(os.path.join(HERE, f)) for f in ("va_oracle.c", "va_oracle_affine.c", "va_oracle.h")):
         subprocess.run(["make", "-C", HERE, "oracle"], check=True, capture_output=True)
     if os.path.isdir("/root/reference/src/Kernels"):
         subprocess.run(["make", "-C", HERE, "ref"], check=True, capture_output=True)
@@ -47,6 +47,13 @@ def lib():
         L.va_oracle_align.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                       ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(Scoring), ctypes.c_void_p,
                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        L.va_oracle_score_affine.restype = ctypes.c_int
+        L.va_oracle_score_affine.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                             ctypes.POINTER(Scoring), ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+        L.va_oracle_align_affine.restype = ctypes.c_int
+        L.va_oracle_align_affine.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                             ctypes.POINTER(Scoring), ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         _lib = L
     return _lib
 
@@ -84,6 +91,35 @@ def align(opt: int, policy: int, reads: np.ndarray, refs: np.ndarray, scoring=(2
     if rc != 0:
         raise ValueError(f"va_oracle_align rc={rc}")
     return a, b, start, end
+
+
+def score_affine(opt: int, reads: np.ndarray, refs: np.ndarray, scoring=(2, -1, -3, -3), gap_open: int = -5, threads: int = 0) -> np.ndarray:
+    """Affine-gap variant (not in the reference; see va_oracle_affine.c)."""
+    reads, refs = _chk(reads), _chk(refs)
+    out = np.zeros(reads.shape[0], dtype=np.int16)
+    sc = Scoring(*scoring)
+    rc = lib().va_oracle_score_affine(opt, reads.shape[0], reads.ctypes.data, reads.shape[1], refs.ctypes.data, refs.shape[1],
+                                      ctypes.byref(sc), gap_open, out.ctypes.data, threads)
+    if rc != 0:
+        raise ValueError(f"va_oracle_score_affine rc={rc}")
+    return out
+
+
+def align_affine(opt: int, reads: np.ndarray, refs: np.ndarray, scoring=(2, -1, -3, -3), gap_open: int = -5, threads: int = 0):
+    """Returns (aln_read[n,L], aln_ref[n,L], start[n], end_cell[n,2], scores[n])."""
+    reads, refs = _chk(reads), _chk(refs)
+    n, L = reads.shape[0], reads.shape[1] + refs.shape[1]
+    a = np.zeros((n, L), dtype=np.uint8)
+    b = np.zeros((n, L), dtype=np.uint8)
+    start = np.zeros(n, dtype=np.int16)
+    end = np.zeros((n, 2), dtype=np.int16)
+    scores = np.zeros(n, dtype=np.int16)
+    sc = Scoring(*scoring)
+    rc = lib().va_oracle_align_affine(opt, n, reads.ctypes.data, reads.shape[1], refs.ctypes.data, refs.shape[1], ctypes.byref(sc),
+                                      gap_open, a.ctypes.data, b.ctypes.data, start.ctypes.data, end.ctypes.data, scores.ctypes.data, threads)
+    if rc != 0:
+        raise ValueError(f"va_oracle_align_affine rc={rc}")
+    return a, b, start, end, scores
 
 
 def ref_lib(name: str) -> str | None:
