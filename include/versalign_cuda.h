@@ -49,6 +49,15 @@ extern "C" {
 
 #define VA_OPT_SW 0
 #define VA_OPT_NW 1
+/* Affine-gap (Gotoh) variants -- NOT in the reference: the same modes with a gap of length L
+ * costing gap_open + L * gap_read (in the read) / gap_open + L * gap_ref (in the ref); gap_open == 0 reproduces
+ * VA_OPT_SW / VA_OPT_NW bit for bit (policy VA_POLICY_DEFAULT_OCL, the only pointer rule of the variant).  The
+ * reference dispatches on opt & 0xF only (DefaultKernel.cpp:31-40), so the gap-open score (<= 0) travels in the bits
+ * above that nibble and every entry point below takes the variant unchanged:
+ *     opt = VA_OPT_SW_AFFINE | VA_OPT_GAP_OPEN(-5)                                                              */
+#define VA_OPT_SW_AFFINE 2
+#define VA_OPT_NW_AFFINE 3
+#define VA_OPT_GAP_OPEN(g) ((int)(((unsigned)(-(g)) & 0xFFFFu) << 8))
 
 /* Traceback pointer rule.  The reference's kernels disagree:
  *   VA_POLICY_DEFAULT_OCL  DefaultKernel.cpp:238-248,338-346 and alignment_kernels.cl:106-112,334-339

@@ -13,7 +13,16 @@ import numpy as np
 from . import build as _build
 
 SW, NW = 0, 1
+SW_AFFINE, NW_AFFINE = 2, 3  # affine-gap variants (not in the reference): see affine_opt()
 POLICY_DEFAULT_OCL, POLICY_SIMD = 0, 1
+
+
+def affine_opt(opt: int, gap_open: int) -> int:
+    """VA_OPT_*_AFFINE | VA_OPT_GAP_OPEN(gap_open) of include/versalign_cuda.h: the affine-gap variant of mode `opt`
+    (SW or NW) with a gap-open score <= 0; every entry point takes the result as its `opt`."""
+    if gap_open > 0 or gap_open < -0xFFFF:
+        raise ValueError("gap_open must be in [-65535, 0]")
+    return (SW_AFFINE if (opt & 0xF) == SW else NW_AFFINE) | (((-gap_open) & 0xFFFF) << 8)
 
 # every symbol include/versalign_cuda.h declares (tests check the .so exports all of them)
 C_ABI_SYMBOLS = [

@@ -125,6 +125,8 @@ public:
         if (missing) throw "Cannot instantiate Kernel. Lacking parameters";
         policy_ = optional_param("cuda_traceback_policy", "VERSALIGN_CUDA_POLICY", VA_POLICY_DEFAULT_OCL);
         if (policy_ != VA_POLICY_DEFAULT_OCL && policy_ != VA_POLICY_SIMD) fatal("cuda_traceback_policy must be 0 (Default/OpenCL) or 1 (SSE/AVX)");
+        gap_open_ = optional_param("score_gap_open", "VERSALIGN_CUDA_GAP_OPEN", 0);
+        if (gap_open_ > 0 || gap_open_ < -32767) fatal("score_gap_open must be in [-32767, 0]");
         const int n_devices = optional_param("cuda_devices", "VERSALIGN_CUDA_DEVICES", 0);
         // one process per GPU (torchrun): rank r passes cuda_device_first = r, cuda_devices = 1
         const int first = optional_param("cuda_device_first", "VERSALIGN_CUDA_DEVICE_FIRST", 0);
@@ -138,17 +140,17 @@ public:
     void score_alignments(int const &opt, int const &aln_number, char const *const *const reads,
                           char const *const *const refs, short *const scores) override {
         const int alg = opt & 0xF;
-        if (alg != VA_OPT_SW && alg != VA_OPT_NW) return;  // unsupported mode: touch nothing
+        if (alg < VA_OPT_SW || alg > VA_OPT_NW_AFFINE) return;  // unsupported mode: touch nothing
         apply_threads();
         log_info("Running CUDAKernel score.");
-        int rc = va_cuda_score_ptrs(ctx_, opt, &scoring_, aln_number, reads, read_length_, refs, ref_length_, scores);
+        int rc = va_cuda_score_ptrs(ctx_, with_gap_open(opt), &scoring_, aln_number, reads, read_length_, refs, ref_length_, scores);
         if (rc != VA_OK) fatal(std::string("score_alignments failed: ") + va_cuda_last_error());
     }
 
     void compute_alignments(int const &opt, int const &aln_number, char const *const *const reads,
                             char const *const *const refs, Alignment *const alignments) override {
         const int alg = opt & 0xF;
-        if (alg != VA_OPT_SW && alg != VA_OPT_NW) return;
+        if (alg < VA_OPT_SW || alg > VA_OPT_NW_AFFINE) return;
         apply_threads();
         log_info("Running CUDAKernel align.");
         const int n = aln_number;
@@ -165,13 +167,17 @@ public:
                           offsetof(Alignment, refStart) == offsetof(va_cuda_alignment_record, ref_start) &&
                           offsetof(Alignment, refEnd) == offsetof(va_cuda_alignment_record, ref_end),
                       "va_cuda_alignment_record restates struct Alignment (AlignmentKernel.h:12-24)");
-        int rc = va_cuda_align_records(ctx_, opt, policy_, &scoring_, n, reads, read_length_, refs, ref_length_,
+        int rc = va_cuda_align_records(ctx_, with_gap_open(opt), alg >= VA_OPT_SW_AFFINE ? VA_POLICY_DEFAULT_OCL : policy_, &scoring_, n, reads, read_length_, refs, ref_length_,
                                        [](size_t bytes, void *) -> char * { return new (std::nothrow) char[bytes]; }, nullptr,
                                        alignments, sizeof(Alignment), nullptr);
         if (rc != VA_OK) fatal(std::string("compute_alignments failed: ") + va_cuda_last_error());
     }
 
 private:
+    // opt values 2 / 3 (beyond the reference's 0 / 1): the affine-gap variants; their gap-open score is the optional
+    // key "score_gap_open" (env VERSALIGN_CUDA_GAP_OPEN), read when the kernel is spawned
+    int with_gap_open(int opt) const { return (opt & 0xF) >= VA_OPT_SW_AFFINE ? ((opt & 0xF) | VA_OPT_GAP_OPEN(gap_open_)) : opt; }
+
     // num_threads is read on every call like the reference (DefaultKernel.cpp:45); here it sizes
     // the host staging pool.
     void apply_threads() {
@@ -187,6 +193,7 @@ private:
     va_cuda_scoring scoring_{};
     int read_length_ = 0, ref_length_ = 0;
     int policy_ = VA_POLICY_DEFAULT_OCL;
+    int gap_open_ = 0;
     va_cuda_ctx *ctx_ = nullptr;
 };
 

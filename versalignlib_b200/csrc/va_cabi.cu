@@ -215,7 +215,7 @@ struct PinBuf {
 
 // Device workspace of one chunk in flight.
 struct ChunkSlot {
-    DevBuf raw_reads, raw_refs, read_off, ref_off, code_reads, code_refs, row_idx, solo_list, meta, pair_of, prep_scratch, boundary, dirs, zdirs, hrow, queue,
+    DevBuf raw_reads, raw_refs, read_off, ref_off, code_reads, code_refs, row_idx, solo_list, meta, pair_of, prep_scratch, boundary, boundary_e, dirs, dirs4, zdirs, hrow, queue,
         scores, end_cell, start, moves, compact, compact_off, cursor, coords, run_count, run_offs, cigar, scan_tmp;
     PinBuf h_reads, h_refs, h_read_off, h_ref_off, h_scores, h_end_cell, h_start, h_compact, h_compact_off, h_cursor, h_coords, h_run_offs,
         h_cigar, h_moves;
@@ -232,7 +232,7 @@ struct ChunkSlot {
 
     void release() {
         DevBuf *d[] = {&raw_reads, &raw_refs, &read_off, &ref_off, &code_reads, &code_refs, &row_idx, &solo_list, &meta, &pair_of, &prep_scratch,
-                       &boundary, &dirs, &zdirs, &hrow, &queue, &scores, &end_cell, &start, &moves, &compact, &compact_off, &cursor, &coords,
+                       &boundary, &boundary_e, &dirs, &dirs4, &zdirs, &hrow, &queue, &scores, &end_cell, &start, &moves, &compact, &compact_off, &cursor, &coords,
                        &run_count, &run_offs, &cigar, &scan_tmp};
         for (auto *b : d) b->release();
         PinBuf *h[] = {&h_reads, &h_refs, &h_read_off, &h_ref_off, &h_scores, &h_end_cell, &h_start, &h_compact, &h_compact_off, &h_cursor,
@@ -307,6 +307,7 @@ struct Shape {
     bool align;
     bool moves = false;    // align results leave the device as CIGAR runs (packed entry points), not as strings
     bool zplane = false;   // SW align under the SSE/AVX pointer policy: the packed kernel stores a third plane
+    bool affine = false;   // affine-gap variant: general kernel only, E boundary + 4-bit directions
     bool offsets = false;  // inputs are offset-addressed (packed entry points): per-pair lengths, no padding
     bool stage_reads = true, stage_refs = true, stage_offs = true;  // false: that input is page-locked, no staging copy
     size_t queue_words() const { return traceback_queue_words(read_length, ref_length); }
@@ -319,6 +320,7 @@ struct Shape {
         if (align) {
             b += dir_row_bytes() * (rows_alloc + 4) + (size_t)ref_length * 2 + 8;
             if (zplane) b += fast_dirs_bytes_per_row_per_slot(ref_length) / 2 * (rows_alloc + 4);
+            if (affine) b += (size_t)segs * 4 * rows_alloc;
             const size_t qw = traceback_queue_words(read_length, ref_length);
             if (traceback_wants_global_queue(read_length, ref_length)) b += qw * 4;
         }
@@ -348,10 +350,12 @@ Shape make_shape(int read_length, int ref_length, bool align) {
 
 int mode_of(int opt, bool align) {
     const int alg = opt & 0xF;
-    if (alg == VA_OPT_SW) return align ? MODE_SW_ALIGN : MODE_SW_SCORE;
-    if (alg == VA_OPT_NW) return align ? MODE_NW_ALIGN : MODE_NW_SCORE;
+    if (alg == VA_OPT_SW || alg == VA_OPT_SW_AFFINE) return align ? MODE_SW_ALIGN : MODE_SW_SCORE;
+    if (alg == VA_OPT_NW || alg == VA_OPT_NW_AFFINE) return align ? MODE_NW_ALIGN : MODE_NW_SCORE;
     return -1;
 }
+bool opt_is_affine(int opt) { return (opt & 0xF) == VA_OPT_SW_AFFINE || (opt & 0xF) == VA_OPT_NW_AFFINE; }
+int opt_gap_open(int opt) { return -(int)(((unsigned)opt >> 8) & 0xFFFFu); }
 
 int check_domain(const va_cuda_scoring *sc, int read_length, int ref_length) {
     if (!sc) return set_error(VA_ERR_ARG, "scoring is null");
@@ -416,6 +420,8 @@ int reserve_slot(ChunkSlot &s, const Shape &sh, int cap_pairs, SlotKind kind) {
     if ((rc = s.boundary.reserve(slots * sh.rows_alloc * 6 + 512))) return rc;
     if ((rc = s.scores.reserve(slots * 2))) return rc;
     if ((rc = s.end_cell.reserve(slots * 4))) return rc;
+    if (sh.affine && (rc = s.boundary_e.reserve(slots * sh.rows_alloc * 4 + 512))) return rc;
+    if (sh.affine && sh.align && (rc = s.dirs4.reserve(slots * (size_t)sh.segs * 4 * sh.rows_alloc + 512))) return rc;
     if (sh.align) {
         if ((rc = s.dirs.reserve(slots * sh.dir_row_bytes() * (sh.rows_alloc + 4) + 512))) return rc;  // (+4: the intra-task layout pads rows to a multiple of 4)
         if (sh.zplane && (rc = s.zdirs.reserve(slots * (fast_dirs_bytes_per_row_per_slot(sh.ref_length) / 2) * (sh.rows_alloc + 4) + 512))) return rc;
@@ -480,6 +486,8 @@ void fill_geom(ChunkGeom &g, const Shape &sh, int n) {
     g.solo = 0;
     g.policy = 0;
     g.intra = 0;
+    g.affine = 0;
+    g.gap_open = 0;
 }
 
 // Where one chunk's device work reads and writes.
@@ -494,7 +502,7 @@ struct DeviceIO {
 };
 
 // Enqueue prep + fill (+ traceback) for n pairs.  Returns kernels launched (or < 0).
-int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int policy, const Scoring &sc, int n,
+int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int policy, const Scoring &sc, int gap_open, int n,
                         const DeviceIO &io, cudaStream_t stream, bool profile = false) {
 #define ENQ_TRY(expr)                                                                                                  \
     do {                                                                                                               \
@@ -505,13 +513,15 @@ int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int
     ChunkGeom g;
     fill_geom(g, sh, n);
     g.policy = sh.align ? policy : 0;
+    g.affine = sh.affine ? 1 : 0;
+    g.gap_open = gap_open;
     // VERSALIGN_CUDA_GENERAL_ONLY=1 keeps every pair on the 32-bit kernel (parity tests use it to
     // cover that kernel on inputs the packed kernels would otherwise take)
     static const bool general_only = [] { const char *v = getenv("VERSALIGN_CUDA_GENERAL_ONLY"); return v && atoi(v) != 0; }();
     // few, long pairs: the intra-task kernels (a CTA per pair-of-pairs, va_intra.cu); decided before prep: every
     // kernel of the chunk reads it
     static const bool no_intra = [] { const char *v = getenv("VERSALIGN_CUDA_NO_INTRA"); return v && atoi(v) != 0; }();
-    if (!general_only) {
+    if (!general_only && !sh.affine) {  // (the affine-gap variant runs on the general kernel)
         if (!no_intra && intra_preferred(mode, n, sh.read_length, sh.ref_length, e.sm_count) &&
             fast_scoring_ok(mode, policy, sc, sh.read_length, sh.ref_length, true)) {
             g.fast_tw = 16;
@@ -535,6 +545,8 @@ int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int
     b.meta = (PairMeta *)ws.meta.p;
     b.pair_of = (int32_t *)ws.pair_of.p;
     b.boundary = (int32_t *)ws.boundary.p;
+    b.boundary_e = (int32_t *)ws.boundary_e.p;
+    b.dirs4 = (uint32_t *)ws.dirs4.p;
     b.fboundary = (uint32_t *)((char *)ws.boundary.p + round_up((size_t)g.slots * sh.rows_alloc * 4, 256));
     b.dirs = (uint16_t *)ws.dirs.p;
     b.fdirs = (uint4 *)((char *)ws.dirs.p + round_up((size_t)g.slots * sh.gen_dir_row_bytes() * sh.rows_alloc, 256));
@@ -622,7 +634,7 @@ struct CigarPart {
 
 // What the host-buffer entry points have in common.
 struct HostCall {
-    int mode = 0, policy = 0;
+    int mode = 0, policy = 0, gap_open = 0;
     Scoring sc{};
     Shape sh{};
     int n = 0;
@@ -1002,7 +1014,7 @@ void run_shard(va_cuda_ctx *ctx, Engine &e, const HostCall &c, int64_t lo, int64
         io.start = (int16_t *)s.start.p;
         io.compact = strings;
         io.moves = moves;
-        int launches = enqueue_device_work(e, s, c.sh, c.mode, c.policy, c.sc, count, io, s.stream);
+        int launches = enqueue_device_work(e, s, c.sh, c.mode, c.policy, c.sc, c.gap_open, count, io, s.stream);
         if (launches < 0) return fail(launches);
         st.launches += launches;
         SHARD_TRY(cudaEventRecord(s.ev_k1, s.stream));
@@ -1177,7 +1189,10 @@ int prepare_call(va_cuda_ctx *ctx, HostCall &c, int opt, bool align, int policy,
     c.policy = policy;
     c.sc = Scoring{sc->match, sc->mismatch, sc->gap_read, sc->gap_ref};
     c.sh = make_shape(read_length, ref_length, align);
-    c.sh.zplane = align && policy == VA_POLICY_SIMD && c.mode == MODE_SW_ALIGN;
+    c.sh.affine = opt_is_affine(opt);
+    c.gap_open = c.sh.affine ? opt_gap_open(opt) : 0;
+    if (c.sh.affine && align && policy != VA_POLICY_DEFAULT_OCL) return set_error(VA_ERR_ARG, "the affine-gap variant has one pointer rule (policy 0)");
+    c.sh.zplane = align && policy == VA_POLICY_SIMD && c.mode == MODE_SW_ALIGN && !c.sh.affine;
     c.n = n;
     return VA_OK;
 }
@@ -1533,7 +1548,7 @@ static int resident_call(va_cuda_ctx *ctx, int opt, bool align, int policy, cons
             io.start = (int16_t *)d_start + first;
             io.zero_prefix = true;
         }
-        int k = enqueue_device_work(e, ws, c.sh, c.mode, c.policy, c.sc, count, io, st, e.profiling);
+        int k = enqueue_device_work(e, ws, c.sh, c.mode, c.policy, c.sc, c.gap_open, count, io, st, e.profiling);
         if (k < 0) return k;
         launches += k;
     }

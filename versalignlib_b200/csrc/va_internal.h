@@ -54,6 +54,8 @@ struct ChunkGeom {
     int duos;          // slots / 2: stride of the arrays the packed kernels index by pair-of-pairs
     int solo;          // 1: the packed inter-task kernels also take single slots whose duo is not fast (va_fast.cuh)
     int policy;        // traceback pointer policy of the call (0 Default/OpenCL, 1 SSE/AVX); align modes only
+    int affine;        // 1: affine-gap variant (general kernel only): a gap of length L costs gap_open + L * gap_{read,ref}
+    int gap_open;      // <= 0
     int intra;         // 1: the chunk's packed duos are computed by the intra-task kernels (va_intra.cu): 16-column strips,
                        // directions at [duo][strip][row], boundary at [duo][row], no end-aligned NW duos
 };
@@ -93,6 +95,8 @@ struct ChunkBuffers {
                                // indexing as fdirs, .x = even row / .y = odd row of the pair, low 16 bits lane A; else NULL
     int32_t *solo_list;        // [slots] slots the packed kernels take on their own (va_fast.cuh), written by the prep
     int32_t *solo_count;       // kernel in no particular order; *solo_count entries
+    int32_t *boundary_e;       // affine variant: [rows_alloc][slots] E (gap-in-read state) of the previous strip's right edge
+    uint32_t *dirs4;           // affine variant: [segs][rows_alloc][slots] words, 4 bits per cell (H source, E opened, F opened), 8 cells each
     uint32_t *hrow;            // packed NW align: [strip][duo][2] arg-max key of the last valid matrix row per strip and lane
     int16_t *scores;           // [n]
     int16_t *end_cell;         // [n][2]

@@ -21,7 +21,16 @@ namespace va {
 
 constexpr int GEN_TW = 16;
 
-template <int MODE, int POLICY>
+// AFFINE: the affine-gap (Gotoh) variant, SURVEY.md 8(f) rank 4 -- not in the reference; the smallest generalisation of
+// its linear modes (same borders, end-cell rules, outputs; gap_open == 0 reproduces them bit for bit):
+//     E(i,j) = max(E(i,j-1), H(i,j-1) + gap_open) + gap_read       F(i,j) = max(F(i-1,j), H(i-1,j) + gap_open) + gap_ref
+//     H(i,j) = max(H(i-1,j-1) + s, F, E [, 0])                      pointers: START > DIAG > F > E; a gap state opens on ties
+// F lives in a register per column, E runs along the row (and crosses strips beside the boundary column); 4 direction
+// bits per cell.  (oracle/va_oracle_affine.c is the checker.)
+constexpr int AFF_NEG = -(1 << 29);
+enum : int { AFF_E_OPEN = 4, AFF_F_OPEN = 8 };
+
+template <int MODE, int POLICY, bool AFFINE = false>
 __global__ void __launch_bounds__(128) fill_general_kernel(ChunkGeom g, ChunkBuffers b, Scoring sc) {
     constexpr bool SW = MODE == MODE_SW_SCORE || MODE == MODE_SW_ALIGN;
     constexpr bool ALIGN = MODE == MODE_SW_ALIGN || MODE == MODE_NW_ALIGN;
@@ -39,12 +48,12 @@ __global__ void __launch_bounds__(128) fill_general_kernel(ChunkGeom g, ChunkBuf
     if (slot < g.n && slot_owner(g, MODE, slot, b.meta[slot & ~1], b.meta[slot | 1]) == OWN_NONE) {
         const PairMeta meta = b.meta[slot];
         const int m = meta.rows, n = meta.cols;
-        const int gF = sc.gap_ref, gR = sc.gap_read;
+        const int gF = sc.gap_ref, gR = sc.gap_read, gO = AFFINE ? g.gap_open : 0;
         cells = (unsigned long long)m * (unsigned long long)n;
 
         int best = 0, best_i = 0, best_j = 0;  // SW: first strictly greater cell in row-major order
         int border = 0;                        // NW score: max(0, last column, last row)
-        int row_max = m * gF, row_idx = 0;     // NW align: arg-max of the last valid row, column 0 first
+        int row_max = m * gF + gO, row_idx = 0;  // NW align: arg-max of the last valid row, column 0 first
         // NW align on a trimmed ref (columns past n are pad columns that only score 0, not filled):
         // the end-cell rule scans them too (DefaultKernel.cpp:352-355).  While both gaps are <= 0 a pad
         // cell of the last valid row can exceed the best true cell only by carrying a value of the last
@@ -53,15 +62,19 @@ __global__ void __launch_bounds__(128) fill_general_kernel(ChunkGeom g, ChunkBuf
         const int pad_cols = MODE == MODE_NW_ALIGN ? g.ref_length - n : 0;
         const int pad_reach = min(pad_cols, m);           // matrix rows m-1 .. m-pad_reach feed the pad cells
         int col_max = (pad_reach == m && m > 0) ? 0 : INT_MIN;  // matrix row 0 is 0 when it is in reach
-        if (MODE == MODE_NW_ALIGN && n == 0 && pad_reach > 0) col_max = max(col_max, (m - pad_reach) * gF);  // column 0 is i*gF
+        if (MODE == MODE_NW_ALIGN && n == 0 && pad_reach > 0) col_max = max(col_max, (m - pad_reach) * gF + gO);  // column 0 is i*gF
         const uint32_t *rcodes = reinterpret_cast<const uint32_t *>(b.code_reads);
 
         for (int c0 = 0; c0 < n; c0 += GEN_TW) {
             const uint4 fq = b.code_refs[(size_t)(c0 >> 4) * g.slots + slot];
             const uint32_t fw[4] = {fq.x, fq.y, fq.z, fq.w};
-            int H[GEN_TW];
+            int H[GEN_TW], F[AFFINE ? GEN_TW : 1];
 #pragma unroll
             for (int k = 0; k < GEN_TW; ++k) H[k] = 0;  // row 0 of the matrix is 0 in every mode
+            if (AFFINE) {
+#pragma unroll
+                for (int k = 0; k < GEN_TW; ++k) F[k] = AFF_NEG;
+            }
             int diag_in = 0;                             // H[i][c0]: value left of the strip, previous row
             const bool last_strip = c0 + GEN_TW >= n;
             uint32_t rword = 0;
@@ -69,22 +82,42 @@ __global__ void __launch_bounds__(128) fill_general_kernel(ChunkGeom g, ChunkBuf
                 if ((i & 3) == 0) rword = rcodes[((size_t)(i >> 4) * g.slots + slot) * 4 + ((i >> 2) & 3)];
                 const int rc = (rword >> (8 * (i & 3))) & 0xFF;
                 const int *srow = sub + rc * 8;
-                int left;
-                if (c0 == 0) left = MODE == MODE_NW_ALIGN ? (i + 1) * gF : 0;  // matrix column 0
-                else left = b.boundary[(size_t)i * g.slots + slot];
+                int left, e_run = AFF_NEG;
+                if (c0 == 0) left = MODE == MODE_NW_ALIGN ? (i + 1) * gF + gO : 0;  // matrix column 0
+                else {
+                    left = b.boundary[(size_t)i * g.slots + slot];
+                    if (AFFINE) e_run = b.boundary_e[(size_t)i * g.slots + slot];
+                }
                 int diag = diag_in;
                 diag_in = left;
-                uint32_t dirbits = 0;
+                uint32_t dirbits = 0, dirbits_hi = 0;
 #pragma unroll
                 for (int k = 0; k < GEN_TW; ++k) {
                     const int fc = (fw[k >> 2] >> (8 * (k & 3))) & 0xFF;
                     const int up = H[k];
                     const int d = diag + srow[fc];
-                    const int u = up + gF;
-                    const int l = left + gR;
+                    int u, l;
+                    bool e_open = false, f_open = false;
+                    if (AFFINE) {
+                        e_open = left + gO >= e_run;
+                        f_open = up + gO >= F[k];
+                        e_run = max(e_run, left + gO) + gR;
+                        F[k] = max(F[k], up + gO) + gF;
+                        u = F[k];
+                        l = e_run;
+                    } else {
+                        u = up + gF;
+                        l = left + gR;
+                    }
                     int h = max(d, max(u, l));
                     if (SW) h = max(h, 0);
-                    if (ALIGN) {
+                    if (ALIGN && AFFINE) {
+                        int code = h == d ? DIR_DIAG : (h == u ? DIR_UP : DIR_LEFT);
+                        if (SW && h == 0) code = DIR_START;
+                        code |= (e_open ? AFF_E_OPEN : 0) | (f_open ? AFF_F_OPEN : 0);
+                        if (k < 8) dirbits |= (uint32_t)code << (4 * k);
+                        else dirbits_hi |= (uint32_t)code << (4 * (k - 8));
+                    } else if (ALIGN) {
                         int code;
                         if (POLICY == 0) {
                             // START (SW and zero) > DIAG > UP > LEFT   (DefaultKernel.cpp:238-248,338-346)
@@ -123,8 +156,15 @@ __global__ void __launch_bounds__(128) fill_general_kernel(ChunkGeom g, ChunkBuf
                     H[k] = h;
                     left = h;
                 }
-                if (!last_strip) b.boundary[(size_t)i * g.slots + slot] = left;
-                if (ALIGN) {
+                if (!last_strip) {
+                    b.boundary[(size_t)i * g.slots + slot] = left;
+                    if (AFFINE) b.boundary_e[(size_t)i * g.slots + slot] = e_run;
+                }
+                if (ALIGN && AFFINE) {
+                    const int seg = c0 >> 3;
+                    b.dirs4[((size_t)seg * g.rows_alloc + i) * g.slots + slot] = dirbits;
+                    if (seg + 1 < g.segs) b.dirs4[((size_t)(seg + 1) * g.rows_alloc + i) * g.slots + slot] = dirbits_hi;
+                } else if (ALIGN) {
                     const int seg = c0 >> 3;
                     b.dirs[((size_t)seg * g.rows_alloc + i) * g.slots + slot] = (uint16_t)(dirbits & 0xFFFF);
                     if (seg + 1 < g.segs)
@@ -361,6 +401,10 @@ __global__ void __launch_bounds__(256) int_peak_kernel(int iters, unsigned int s
 template <int MODE>
 static void launch_fill_mode(const ChunkGeom &g, const ChunkBuffers &b, int policy, const Scoring &sc, cudaStream_t stream) {
     const int threads = 128;
+    if (g.affine) {  // affine-gap variant: one thread per pair, Default/OpenCL-style pointer order only
+        fill_general_kernel<MODE, 0, true><<<(g.n + threads - 1) / threads, threads, 0, stream>>>(g, b, sc);
+        return;
+    }
     // long pairs: a warp per pair (a thread per pair would take seconds per matrix)
     if ((long long)g.read_length * g.ref_length >= (1LL << 20) && (long long)g.n * 32 <= (1LL << 30)) {
         const int blocks = (int)(((long long)g.n * 32 + threads - 1) / threads);

@@ -229,6 +229,34 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
                     ++n_moves;
                 }
             }
+        } else if (g.affine) {
+            // affine-gap variant (fill_general_kernel<.., AFFINE>): 4 bits per cell -- where H came from, and whether the E / F
+            // gap state of the cell was opened from H; the walk is the three-state machine of oracle/va_oracle_affine.c
+            int state = 0;  // 0 = H, 1 = F (a run of UP moves), 2 = E (a run of LEFT moves)
+            while (true) {
+                int code;
+                if (i < 0 || i >= rows || j >= cols) code = DIR_START;
+                else if (j < 0) code = NW ? (DIR_UP | (i == 0 ? 8 : 0)) : DIR_START;  // column 0: one leading gap, opened in row 0
+                else code = (b.dirs4[((size_t)(j >> 3) * g.rows_alloc + i) * g.slots + slot] >> (4 * (j & 7))) & 15;
+                if (state == 0) {
+                    const int hp = code & 3;
+                    if (hp == DIR_START) break;
+                    if (hp == DIR_UP) { state = 1; continue; }
+                    if (hp == DIR_LEFT) { state = 2; continue; }
+                    sink(DIR_DIAG, n_moves);
+                    --i;
+                    --j;
+                } else if (state == 1) {
+                    sink(DIR_UP, n_moves);
+                    if (code & 8) state = 0;
+                    --i;
+                } else {
+                    sink(DIR_LEFT, n_moves);
+                    if (code & 4) state = 0;
+                    --j;
+                }
+                ++n_moves;
+            }
         } else {
             while (true) {
                 int code;
