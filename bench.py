@@ -18,7 +18,8 @@ Workload (BASELINE.json configs[1], "C2"): the library's "Needleman-Wunsch" comp
                over the N GPUs that BASELINE.json's north_star describes, on N x the pairs
   roofline     the fill kernel against the measured integer-pipe peak (VIADDMNMX.S16x2 lane-ops/s
                divided by 3 ops per cell), plus its HBM view
-  modes        resident GCUPS of every function (and of the SSE/AVX pointer policy) on the same shape
+  modes        resident GCUPS of every function (both pointer policies; the 32-bit general kernel through the affine-gap
+               variant) on the same shape
   configs      the other BASELINE configs at these N GPUs: C1 through the plug-in boundary next to the
                reference's SSE / AVX / Default kernels, C3 (10 M distinct mixed-length pairs, strong-scaled over
                the ranks, cells = true rows x cols), C4 (10 k long pairs split over the ranks); each with resident
@@ -471,7 +472,11 @@ def run_ours(args):
             ("sw_align_default_ocl", lambda: ctx.align_device(SW, POLICY_DEFAULT_OCL, mr, mf, d_a, d_b, d_start, d_end, SCORING, stream=stream)),
             ("nw_align_default_ocl", lambda: ctx.align_device(NW, POLICY_DEFAULT_OCL, mr, mf, d_a, d_b, d_start, d_end, SCORING, stream=stream)),
             ("sw_align_simd", lambda: ctx.align_device(SW, POLICY_SIMD, mr, mf, d_a, d_b, d_start, d_end, SCORING, stream=stream)),
-            ("nw_align_simd", lambda: ctx.align_device(NW, POLICY_SIMD, mr, mf, d_a, d_b, d_start, d_end, SCORING, stream=stream))):
+            ("nw_align_simd", lambda: ctx.align_device(NW, POLICY_SIMD, mr, mf, d_a, d_b, d_start, d_end, SCORING, stream=stream)),
+            # the 32-bit general kernel (what leaves the packed kernels' domain falls to it), here through the affine-gap
+            # variant, which has no packed kernel yet
+            ("sw_score_affine_general_kernel", lambda: ctx.score_device(capi.affine_opt(SW, -5), mr, mf, m_s, SCORING, stream=stream)),
+            ("nw_align_affine_general_kernel", lambda: ctx.align_device(capi.affine_opt(NW, -5), POLICY_DEFAULT_OCL, mr, mf, d_a, d_b, d_start, d_end, SCORING, stream=stream))):
         ms = timed_resident(torch, fn, 3)
         modes[name] = {"resident_gcups": mcells / ms / 1e6, "ms": ms}
     modes["_note"] = f"{n_modes} pairs of the C2 shape, prep + fill (+ traceback), this rank"

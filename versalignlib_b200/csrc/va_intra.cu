@@ -67,7 +67,7 @@ __global__ void __maxnreg__(VA_INTRA_MAXREG) fill_intra_kernel(ChunkGeom g, Chun
     __shared__ uint2 s_T2[64];            // [7*code_a + code_b] -> the two lanes' 4-entry score tables (49 used)
     __shared__ int prog[MAX_PASSES];      // rows of pass p whose right edge is in global memory
     __shared__ uint32_t warp_best[MAX_WARPS];
-    __shared__ uint32_t s_edge[MAX_WARPS][32];  // lane 31's right edges of the last (up to) 32 rows, per warp
+    __shared__ uint32_t s_edge[MAX_WARPS][64];  // lane 31's right edges of the last (up to) 64 rows, per warp
     __shared__ int warp_cell[MAX_WARPS][2][3];  // SW align: per warp and half: value, row, column of its best cell
     extern __shared__ uint32_t s_snap[];  // SW align: [warp][slot 0/1][register][lane] row snapshots
     if (threadIdx.x < 64) s_T2[threadIdx.x] = threadIdx.x < 49 ? make_uint2(fc.tab[threadIdx.x / 7], fc.tab[threadIdx.x % 7]) : make_uint2(0u, 0u);
@@ -102,7 +102,7 @@ __global__ void __maxnreg__(VA_INTRA_MAXREG) fill_intra_kernel(ChunkGeom g, Chun
 
     const int pass_cols = 32 * TW;
     const int npasses = (n + pass_cols - 1) / pass_cols;
-    const int steps = m + 31;
+    const int steps = (m + 1) / 2 + 31;  // two rows per step
     const int last_lane = ((n - 1) >> 4) & 31;
     const int ra_last = (int)ma.rows - 1, rb_last = (int)mb.rows - 1;
     for (int pass = warp; pass < npasses; pass += W) {
@@ -122,43 +122,15 @@ __global__ void __maxnreg__(VA_INTRA_MAXREG) fill_intra_kernel(ChunkGeom g, Chun
             H[k] = ALIGN ? gF2 : 0u;  // matrix row 0 is 0 (align keeps H + gF)
         }
         uint32_t diag_next = ALIGN ? gF2 : 0u;            // H[row][c0] of the previous row, 0 for matrix row 0
-        uint32_t cur_ta = 0, cur_tb = 0, edge = gR2;      // what this lane used / produced at its last step
+        // what this lane used / produced for the two rows of its last step
+        uint32_t cur_ta0 = 0, cur_tb0 = 0, edge0 = gR2, cur_ta1 = 0, cur_tb1 = 0, edge1 = gR2;
         uint2 *dp = dirs2 + (size_t)strip * rows2;
-        uint2 w_even = make_uint2(0u, 0u);  // direction word of the even row before this one
+        uint2 w_even = make_uint2(0u, 0u);  // direction word of the even row of the step
 
-        for (int t0 = 0; t0 < steps; t0 += 32) {
-            // batch inputs of lane 0 for steps t0..t0+31: row r = t0 + lane
-            const int r = t0 + lane;
-            // matrix column 0 as "H + gR": 0 everywhere but NW align, where H(I,0) = I*gap_ref (DefaultKernel.cpp:304)
-            uint32_t bat_a = 0, bat_b = 0, bat_left = NWA ? pk((r + 1) * gF + gR) : gR2;
-            if (!first_pass && t0 < m) {
-                // the previous pass (another warp of this CTA when W > 1) must have left these rows
-                const int need = min(t0 + 32, m);
-                while (vprog[pass - 1] < need) {
-                }
-                __threadfence_block();
-            }
-            if (r < m) {
-                const uint2 tt2 = s_T2[ridx[(size_t)(r >> 4) * ridx_stride + (r & 15)]];
-                bat_a = tt2.x;
-                bat_b = tt2.y;
-                if (!first_pass) bat_left = __ldcg(bnd + r);  // written by another warp: read it where it was written (L2)
-            }
-            __syncwarp();  // every lane has read its row before this warp overwrites the column below
-            const int s_end = min(32, steps - t0);
-            // Two steps per loop iteration over two register sets (H -> H2 -> H): a row's new H[k] cannot overwrite the
-            // old one while the next cell still needs it as its diagonal, so one set costs a register move per cell.
-            auto do_step = [&](auto all_rows_valid, const int s, const uint32_t(&Hi)[TW], uint32_t(&H)[TW]) {
-                const int t = t0 + s;
-                // lane 0 reads the batch, every other lane takes what its left neighbour used last step
-                const uint32_t a0 = __shfl_sync(FULL, bat_a, s), b0 = __shfl_sync(FULL, bat_b, s), l0 = __shfl_sync(FULL, bat_left, s);
-                const uint32_t pa = __shfl_up_sync(FULL, cur_ta, 1), pb = __shfl_up_sync(FULL, cur_tb, 1), pl = __shfl_up_sync(FULL, edge, 1);
-                const uint32_t ta = lane == 0 ? a0 : pa, tb = lane == 0 ? b0 : pb;
-                uint32_t left = lane == 0 ? l0 : pl;
-                const int row = t - lane;
-                if (decltype(all_rows_valid)::value || (row >= 0 && row < m)) {
-                    cur_ta = ta;
-                    cur_tb = tb;
+        // One matrix row of this lane's 16 columns: Hi = the row above, H = this row (two register sets: a row's new
+        // H[k] cannot overwrite the old one while the next cell still needs it as its diagonal).
+        auto do_row = [&](const int row, const uint32_t ta, const uint32_t tb, uint32_t left, const uint32_t(&Hi)[TW], uint32_t(&H)[TW],
+                          uint32_t &edge_out) {
                     uint32_t diag = diag_next;
                     diag_next = add2(left, dFR2);  // "H + gR" -> the diagonal's form (H in the score modes, H + gF in the align modes)
                     if (ALIGN) {
@@ -184,9 +156,10 @@ __global__ void __maxnreg__(VA_INTRA_MAXREG) fill_intra_kernel(ChunkGeom g, Chun
                             diag = up;
                         }
                         {
-                            // an even row keeps its word; the odd row after it stores both as one aligned 16-byte word (8-byte
-                            // stores of single rows cost the L2 twice the partial-sector writes: 2.2 -> 3.1 TCUPS; one 256-bit
-                            // store per four rows measured no better than this).  The last row of an odd-sized matrix goes out alone.
+                            // a step computes an even row and the odd row after it: the even row keeps its word, the odd row
+                            // stores both as one aligned 16-byte word (8-byte stores of single rows cost the L2 twice the
+                            // partial-sector writes: 2.2 -> 3.1 TCUPS; one 256-bit store per four rows measured no better).
+                            // The last row of an odd-sized matrix goes out alone.
                             uint2 w;
                             w.x = __byte_perm(__float_as_uint(p1l), __float_as_uint(p1h), 0x5410);
                             w.y = __byte_perm(__float_as_uint(p2l), __float_as_uint(p2h), 0x5410);
@@ -208,7 +181,7 @@ __global__ void __maxnreg__(VA_INTRA_MAXREG) fill_intra_kernel(ChunkGeom g, Chun
                             diag = up;
                         }
                     }
-                    edge = left;
+                    edge_out = left;
                     if (SWS) {
                         if (kv == TW) {
 #pragma unroll
@@ -299,45 +272,91 @@ __global__ void __maxnreg__(VA_INTRA_MAXREG) fill_intra_kernel(ChunkGeom g, Chun
                         if (row == ra_last) hk[0] = (uint32_t)key_a;
                         if (row == rb_last) hk[1] = (uint32_t)key_b;
                     }
+        };
+
+        // A step = TWO rows per lane: at step t lane l computes rows 2(t-l) and 2(t-l)+1, so both rows' left edges and
+        // tables come from the left neighbour's previous step.  The two rows are independent enough for the scheduler to
+        // interleave them (row r+1 may start as soon as row r has its first cells), which halves the dependent chain per
+        // cell that a warp exposes between two shuffles.
+        for (int t0 = 0; t0 < steps; t0 += 32) {
+            // batch inputs of lane 0 for steps t0..t0+31: rows r0 = 2 * (t0 + lane) and r0 + 1
+            const int r0 = 2 * (t0 + lane);
+            // matrix column 0 as "H + gR": 0 everywhere but NW align, where H(I,0) = I*gap_ref (DefaultKernel.cpp:304)
+            uint32_t bat_a0 = 0, bat_b0 = 0, bat_l0 = NWA ? pk((r0 + 1) * gF + gR) : gR2;
+            uint32_t bat_a1 = 0, bat_b1 = 0, bat_l1 = NWA ? pk((r0 + 2) * gF + gR) : gR2;
+            if (!first_pass && 2 * t0 < m) {
+                // the previous pass (another warp of this CTA when W > 1) must have left these rows
+                const int need = min(2 * t0 + 64, m);
+                while (vprog[pass - 1] < need) {
+                }
+                __threadfence_block();
+            }
+            if (r0 < m) {
+                const uint2 tt2 = s_T2[ridx[(size_t)(r0 >> 4) * ridx_stride + (r0 & 15)]];
+                bat_a0 = tt2.x;
+                bat_b0 = tt2.y;
+                if (!first_pass) bat_l0 = __ldcg(bnd + r0);  // written by another warp: read it where it was written (L2)
+            }
+            if (r0 + 1 < m) {
+                const uint2 tt2 = s_T2[ridx[(size_t)((r0 + 1) >> 4) * ridx_stride + ((r0 + 1) & 15)]];
+                bat_a1 = tt2.x;
+                bat_b1 = tt2.y;
+                if (!first_pass) bat_l1 = __ldcg(bnd + r0 + 1);
+            }
+            __syncwarp();  // every lane has read its rows before this warp overwrites the column below
+            const int s_end = min(32, steps - t0);
+            auto do_step = [&](auto all_rows_valid, const int s) {
+                const int t = t0 + s;
+                // lane 0 reads the batch, every other lane takes what its left neighbour used last step
+                const uint32_t a0 = __shfl_sync(FULL, bat_a0, s), b0 = __shfl_sync(FULL, bat_b0, s), l0 = __shfl_sync(FULL, bat_l0, s);
+                const uint32_t a1 = __shfl_sync(FULL, bat_a1, s), b1 = __shfl_sync(FULL, bat_b1, s), l1 = __shfl_sync(FULL, bat_l1, s);
+                const uint32_t pa0 = __shfl_up_sync(FULL, cur_ta0, 1), pb0 = __shfl_up_sync(FULL, cur_tb0, 1), pl0 = __shfl_up_sync(FULL, edge0, 1);
+                const uint32_t pa1 = __shfl_up_sync(FULL, cur_ta1, 1), pb1 = __shfl_up_sync(FULL, cur_tb1, 1), pl1 = __shfl_up_sync(FULL, edge1, 1);
+                const int row = 2 * (t - lane);
+                if (decltype(all_rows_valid)::value || (row >= 0 && row < m)) {
+                    cur_ta0 = lane == 0 ? a0 : pa0;
+                    cur_tb0 = lane == 0 ? b0 : pb0;
+                    do_row(row, cur_ta0, cur_tb0, lane == 0 ? l0 : pl0, H, H2, edge0);
                 } else {
 #pragma unroll
-                    for (int k = 0; k < TW; ++k) H[k] = Hi[k];
+                    for (int k = 0; k < TW; ++k) H2[k] = H[k];
                 }
-                // lane 31 finished row t-31: it parks its right edge in shared memory; every 32 rows the warp stores them coalesced
+                if (decltype(all_rows_valid)::value || (row >= 0 && row + 1 < m)) {
+                    cur_ta1 = lane == 0 ? a1 : pa1;
+                    cur_tb1 = lane == 0 ? b1 : pb1;
+                    do_row(row + 1, cur_ta1, cur_tb1, lane == 0 ? l1 : pl1, H2, H, edge1);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < TW; ++k) H[k] = H2[k];
+                }
+                // lane 31 finished rows 2(t-31), 2(t-31)+1: it parks their right edges in shared memory; every 64 rows the
+                // warp stores them coalesced
                 if (!last_pass) {
-                    const int orow = t - 31;
+                    const int orow = 2 * (t - 31);
                     if (orow >= 0) {
-                        if (lane == 31) s_edge[warp][orow & 31] = edge;
-                        if ((orow & 31) == 31 || orow == m - 1) {
+                        if (lane == 31) {
+                            s_edge[warp][orow & 63] = edge0;
+                            s_edge[warp][(orow & 63) + 1] = edge1;
+                        }
+                        if ((orow & 63) == 62 || orow + 2 >= m) {
                             __syncwarp();
-                            const int row0 = orow & ~31;
-                            if (row0 + lane <= orow) bnd[row0 + lane] = s_edge[warp][lane];
+                            const int row0 = orow & ~63;
+                            if (row0 + lane < m && row0 + lane <= orow + 1) bnd[row0 + lane] = s_edge[warp][lane];
+                            if (row0 + 32 + lane < m && row0 + 32 + lane <= orow + 1) bnd[row0 + 32 + lane] = s_edge[warp][32 + lane];
                             __threadfence_block();
                             __syncwarp();
-                            if (lane == 0) vprog[pass] = orow + 1;  // rows [0, orow] of this pass are out
+                            if (lane == 0) vprog[pass] = min(orow + 2, m);  // rows [0, orow + 1] of this pass are out
                         }
                     }
                 }
             };
-            // Batches in which every lane has a row (all but the first and the last one or two of a pass) run a copy of
-            // the step without the row test: with the test, the skipped path pins H to its input registers and the
+            // Batches in which every lane has both rows (all but the first and the last one or two of a pass) run a copy of
+            // the step without the row tests: with them, the skipped path pins H to its input registers and the
             // computed path pays a register move per cell to get there.
-            if (t0 >= 32 && t0 + 32 <= m) {
-                for (int s = 0; s < 32; s += 2) {
-                    do_step(std::true_type{}, s, H, H2);
-                    do_step(std::true_type{}, s + 1, H2, H);
-                }
+            if (t0 >= 32 && 2 * (t0 + 32) <= m) {
+                for (int s = 0; s < 32; ++s) do_step(std::true_type{}, s);
             } else {
-                int s = 0;
-                for (; s + 1 < s_end; s += 2) {
-                    do_step(std::false_type{}, s, H, H2);
-                    do_step(std::false_type{}, s + 1, H2, H);
-                }
-                if (s < s_end) {  // odd tail of the last batch
-                    do_step(std::false_type{}, s, H, H2);
-#pragma unroll
-                    for (int k = 0; k < TW; ++k) H[k] = H2[k];
-                }
+                for (int s = 0; s < s_end; ++s) do_step(std::false_type{}, s);
             }
         }
     }
