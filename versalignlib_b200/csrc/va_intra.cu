@@ -96,7 +96,7 @@ __global__ void __maxnreg__(VA_INTRA_MAXREG) fill_intra_kernel(ChunkGeom g, Chun
     uint32_t best = 0;  // score modes: running maximum (SW) / max(0, last column, last row) (NW)
     // SW align: greatest row maximum so far per half, in the registers' form (value + gF); row, strip and
     // snapshot slot it came from
-    uint32_t gbest2 = gF2;
+    uint32_t gbest2 = gF2, floor2 = gF2;
     int gi_a = 0, gi_b = 0, gs_a = -1, gs_b = -1, src_a = 0, src_b = 0;
     uint32_t *snap = s_snap + (size_t)warp * 2 * TW * 32 + lane;  // [slot][register] at stride 32
 
@@ -107,9 +107,10 @@ __global__ void __maxnreg__(VA_INTRA_MAXREG) fill_intra_kernel(ChunkGeom g, Chun
     const int ra_last = (int)ma.rows - 1, rb_last = (int)mb.rows - 1;
     for (int pass = warp; pass < npasses; pass += W) {
         const int c_base = pass * pass_cols;
-        const bool first_pass = pass == 0, last_pass = pass == npasses - 1;
+        const bool first_pass = pass == 0, last_pass = pass == npasses - 1, last_pass_rt = last_pass;
         const int c0 = c_base + lane * TW;
         const int kv = min(TW, max(0, n - c0));  // my valid columns in this pass
+        const int kv_lane = kv;
         const int strip = c0 >> 4;
         uint32_t sel[TW], H[TW], H2[TW];
 #pragma unroll
@@ -129,8 +130,13 @@ __global__ void __maxnreg__(VA_INTRA_MAXREG) fill_intra_kernel(ChunkGeom g, Chun
 
         // One matrix row of this lane's 16 columns: Hi = the row above, H = this row (two register sets: a row's new
         // H[k] cannot overwrite the old one while the next cell still needs it as its diagonal).
-        auto do_row = [&](const int row, const uint32_t ta, const uint32_t tb, uint32_t left, const uint32_t(&Hi)[TW], uint32_t(&H)[TW],
-                          uint32_t &edge_out) {
+        // full_tag: compile-time "every lane of this pass has all 16 columns and the pass is not the last" -- true for the
+        // steady-state batches of all passes but the last, where it removes the partial-strip and last-pass tests.
+        auto do_row = [&](auto full_tag, const int row, const uint32_t ta, const uint32_t tb, uint32_t left, const uint32_t(&Hi)[TW],
+                          uint32_t(&H)[TW], uint32_t &edge_out) {
+            constexpr bool FULL = decltype(full_tag)::value;
+            const int kv = FULL ? TW : kv_lane;
+            const bool last_pass = FULL ? false : last_pass_rt;
                     uint32_t diag = diag_next;
                     diag_next = add2(left, dFR2);  // "H + gR" -> the diagonal's form (H in the score modes, H + gF in the align modes)
                     if (ALIGN) {
@@ -205,19 +211,23 @@ __global__ void __maxnreg__(VA_INTRA_MAXREG) fill_intra_kernel(ChunkGeom g, Chun
                         }
                         // a new best: strictly greater than the best so far -- or equal to it in an EARLIER row, which only a
                         // later pass can meet (rows above the row of the best so far)
-                        bool keep_b, keep_a;
+                        bool keep_b, keep_a, fl_b, fl_a;
                         (void)__vibmax_s16x2(gbest2, rm, &keep_b, &keep_a);  // best so far >= row maximum?
-                        bool cand = !(keep_a && keep_b);
+                        // ... and at least the warp's best as of the last batch (`floor2`): on similar sequences every lane
+                        // inside the band around the main diagonal sets a new LOCAL best in almost every row, but only
+                        // values that reach the warp-wide best can be the pair's best cell
+                        (void)__vibmax_s16x2(rm, floor2, &fl_b, &fl_a);
+                        bool cand = (!keep_a && fl_a) || (!keep_b && fl_b);
                         if (row < max(gi_a, gi_b)) {
                             bool ge_b, ge_a;
                             (void)__vibmax_s16x2(rm, gbest2, &ge_b, &ge_a);
-                            cand = cand || ge_a || ge_b;
+                            cand = cand || (ge_a && fl_a) || (ge_b && fl_b);
                         }
                         if (cand) {
                             const int ra = lo16(rm), rb = hi16(rm), ba = lo16(gbest2), bb = hi16(gbest2);
                             // strictly greater, or equal in an earlier row (a later pass revisits earlier rows)
-                            const bool new_a = ra > ba || (ra == ba && gs_a >= 0 && row < gi_a);
-                            const bool new_b = rb > bb || (rb == bb && gs_b >= 0 && row < gi_b);
+                            const bool new_a = (ra > ba || (ra == ba && gs_a >= 0 && row < gi_a)) && fl_a;
+                            const bool new_b = (rb > bb || (rb == bb && gs_b >= 0 && row < gi_b)) && fl_b;
                             if (new_a || new_b) {
                                 // park the row in the slot the other half's snapshot does not live in
                                 const int slot = (new_a && new_b) ? 0 : (new_a ? (src_b ^ 1) : (src_a ^ 1));
@@ -304,6 +314,11 @@ __global__ void __maxnreg__(VA_INTRA_MAXREG) fill_intra_kernel(ChunkGeom g, Chun
                 if (!first_pass) bat_l1 = __ldcg(bnd + r0 + 1);
             }
             __syncwarp();  // every lane has read its rows before this warp overwrites the column below
+            if (SWA) {  // the warp's best so far, per half (the snapshot filter above)
+                floor2 = gbest2;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) floor2 = __vmaxs2(floor2, __shfl_xor_sync(FULL, floor2, o));
+            }
             const int s_end = min(32, steps - t0);
             auto do_step = [&](auto all_rows_valid, const int s) {
                 const int t = t0 + s;
@@ -316,7 +331,7 @@ __global__ void __maxnreg__(VA_INTRA_MAXREG) fill_intra_kernel(ChunkGeom g, Chun
                 if (decltype(all_rows_valid)::value || (row >= 0 && row < m)) {
                     cur_ta0 = lane == 0 ? a0 : pa0;
                     cur_tb0 = lane == 0 ? b0 : pb0;
-                    do_row(row, cur_ta0, cur_tb0, lane == 0 ? l0 : pl0, H, H2, edge0);
+                    do_row(all_rows_valid, row, cur_ta0, cur_tb0, lane == 0 ? l0 : pl0, H, H2, edge0);
                 } else {
 #pragma unroll
                     for (int k = 0; k < TW; ++k) H2[k] = H[k];
@@ -324,7 +339,7 @@ __global__ void __maxnreg__(VA_INTRA_MAXREG) fill_intra_kernel(ChunkGeom g, Chun
                 if (decltype(all_rows_valid)::value || (row >= 0 && row + 1 < m)) {
                     cur_ta1 = lane == 0 ? a1 : pa1;
                     cur_tb1 = lane == 0 ? b1 : pb1;
-                    do_row(row + 1, cur_ta1, cur_tb1, lane == 0 ? l1 : pl1, H2, H, edge1);
+                    do_row(all_rows_valid, row + 1, cur_ta1, cur_tb1, lane == 0 ? l1 : pl1, H2, H, edge1);
                 } else {
 #pragma unroll
                     for (int k = 0; k < TW; ++k) H[k] = H2[k];
@@ -350,10 +365,10 @@ __global__ void __maxnreg__(VA_INTRA_MAXREG) fill_intra_kernel(ChunkGeom g, Chun
                     }
                 }
             };
-            // Batches in which every lane has both rows (all but the first and the last one or two of a pass) run a copy of
-            // the step without the row tests: with them, the skipped path pins H to its input registers and the
+            // Batches in which every lane has both rows (all but the first and the last one or two of a pass) of a pass in
+            // which every lane has all its columns (all but the last) run a copy of the step without the row / column tests: with them, the skipped path pins H to its input registers and the
             // computed path pays a register move per cell to get there.
-            if (t0 >= 32 && 2 * (t0 + 32) <= m) {
+            if (t0 >= 32 && 2 * (t0 + 32) <= m && !last_pass) {
                 for (int s = 0; s < 32; ++s) do_step(std::true_type{}, s);
             } else {
                 for (int s = 0; s < s_end; ++s) do_step(std::false_type{}, s);
