@@ -363,6 +363,9 @@ def test_long_pairs_intra_task_align(ctx):
     decks.append(("mixed600-1500", r, f))
     r, f = synth.uniform_batch(8, 300, 1024, independent=True, seed=54)  # unrelated sequences: short local alignments
     decks.append(("random300x1024", r, f))
+    r, f, rl_, fl_ = synth.mixed_batch(18, 1, 1200, p_sub=0.1, q_indel=0.02, seed=56)  # reads / refs of 1, 2, 3 ... bases next to long ones
+    r[0, 1:] = 0; r[1, 2:] = 0; r[2, 3:] = 0; f[3, 1:] = 0; r[3, 1:] = 0; f[4, 17:] = 0; r[4, 16:] = 0
+    decks.append(("mixed1-1200", r, f))
     r, f = synth.uniform_batch(6, 1100, 1300, p_sub=0.10, q_indel=0.03, seed=55)
     f = f.copy()
     f[2, 400] = ord("N")
