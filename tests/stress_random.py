@@ -26,7 +26,9 @@ def random_case(rng):
         n = int(rng.choice([1, 2, 3, 31, 64, 65, 127, 500, 2000, 9000]))
         rl, fl = int(rng.integers(1, 260)), int(rng.integers(1, 260))
     seed = int(rng.integers(1 << 30))
-    if kind in ("uniform", "long", "many"):
+    if kind == "long" and rng.random() < 0.4:  # long pairs of mixed lengths (partial last passes, duos of unequal reads)
+        reads, refs, _, _ = synth.mixed_batch(n, int(rng.integers(1, 300)), max(rl, fl, 1100), p_sub=0.1, q_indel=0.02, seed=seed)
+    elif kind in ("uniform", "long", "many"):
         reads, refs = synth.uniform_batch(n, rl, fl, p_sub=float(rng.choice([0.05, 0.3, 0.75])), q_indel=float(rng.choice([0, 0.03])), seed=seed)
     else:
         lo = max(1, min(rl, fl) // 3)
@@ -77,6 +79,17 @@ def main():
                         want = synth.cigar_from_strings(*ora.align(opt, policy, tr, tf, sc))
                         if not (np.array_equal(coords, want[0]) and np.array_equal(coff, want[1]) and np.array_equal(cigar, want[2])):
                             failures.append(("align_packed", opt, policy) + tag)
+            # the affine-gap variant (general kernel) against its own oracle; gap_open = 0 must also equal the linear result
+            if kind not in ("long", "many") and sc[2] <= 0 and sc[3] <= 0 and rng.random() < 0.3:
+                gap_open = int(rng.choice([0, -2, -9]))
+                for opt in (ora.SW, ora.NW):
+                    o = capi.affine_opt(opt, gap_open)
+                    if not np.array_equal(ctx.score_flat(o, reads, refs, sc), ora.score_affine(opt, reads, refs, sc, gap_open)):
+                        failures.append(("score_affine", opt, gap_open) + tag)
+                    a, b, start, end = ctx.align_flat(o, 0, reads, refs, sc)
+                    oa, ob, ostart, oend, _ = ora.align_affine(opt, reads, refs, sc, gap_open)
+                    if not (np.array_equal(start, ostart) and np.array_equal(end, oend) and used_region_equal(a, b, start, oa, ob, ostart).size == 0):
+                        failures.append(("align_affine", opt, gap_open) + tag)
             cases += 1
             if failures:
                 break
