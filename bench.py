@@ -91,7 +91,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
@@ -426,13 +426,20 @@ def run_ours(args):
     def step_resident():
         ctx.align_device(NW, POLICY_DEFAULT_OCL, d_reads, d_refs, d_a, d_b, d_start, d_end, SCORING, stream=stream)
 
+    # clocks: nvidia-smi is started before the warm-up (it needs a second to come up, longer on an 8-GPU box) and samples
+    # every 50 ms through the warm-up, the timed steps and the profiled pass of the same steps
+    sampler = ClockSampler(dev_index)
+    if RANK == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_resident()
     barrier()
     launches_per_step = ctx.timings()["launches"]
-    sampler = ClockSampler(dev_index)
     if RANK == 0:
-        sampler.start()
+        t_wait = time.time()
+        while not sampler.lines and time.time() - t_wait < 5.0:  # first sample in before the timed region starts
+            step_resident()
+            torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()

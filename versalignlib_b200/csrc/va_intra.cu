@@ -59,7 +59,7 @@ constexpr int MAX_WARPS = 16;
 // MODE: one of the four functions.  POLICY (NW align): which comparison the second plane records (0: UP >= LEFT,
 // 1: LEFT >= UP).  SYM (align): gap_read == gap_ref, so "H + gR" and "H + gF" are one register.
 template <int MODE, int POLICY, bool SYM>
-__global__ void __maxnreg__(VA_INTRA_MAXREG) fill_intra_kernel(ChunkGeom g, ChunkBuffers b, FastConsts fc) {
+__global__ void __maxnreg__(VA_INTRA_MAXREG) fill_intra_kernel(ChunkGeom g, ChunkBuffers b, FastConsts fc, int duo_first) {
     constexpr unsigned FULL = 0xffffffffu;
     constexpr bool ALIGN = MODE == MODE_SW_ALIGN || MODE == MODE_NW_ALIGN;
     constexpr bool SW = MODE == MODE_SW_SCORE || MODE == MODE_SW_ALIGN;
@@ -75,7 +75,7 @@ __global__ void __maxnreg__(VA_INTRA_MAXREG) fill_intra_kernel(ChunkGeom g, Chun
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
-    const int duo = blockIdx.x;
+    const int duo = duo_first + (int)blockIdx.x;
     const int slot_a = 2 * duo, slot_b = slot_a + 1;
     if (slot_b >= g.n) return;  // CTA-uniform
     const PairMeta ma = b.meta[slot_a], mb = b.meta[slot_b];
@@ -440,10 +440,10 @@ __global__ void __maxnreg__(VA_INTRA_MAXREG) fill_intra_kernel(ChunkGeom g, Chun
 }
 
 template <int MODE, int POLICY, bool SYM>
-void launch_intra_inst(const ChunkGeom &g, const ChunkBuffers &b, const FastConsts &fc, int duos, int warps, cudaStream_t stream) {
+void launch_intra_inst(const ChunkGeom &g, const ChunkBuffers &b, const FastConsts &fc, int duo_first, int duos, int warps, cudaStream_t stream) {
     const size_t smem = MODE == MODE_SW_ALIGN ? (size_t)warps * 2 * TW * 32 * sizeof(uint32_t) : 0;
     if (smem > 48 * 1024) cudaFuncSetAttribute(fill_intra_kernel<MODE, POLICY, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    fill_intra_kernel<MODE, POLICY, SYM><<<duos, 32 * warps, smem, stream>>>(g, b, fc);
+    fill_intra_kernel<MODE, POLICY, SYM><<<duos, 32 * warps, smem, stream>>>(g, b, fc, duo_first);
 }
 
 }  // namespace
@@ -455,38 +455,56 @@ bool intra_preferred(int mode, int n_pairs, int read_length, int ref_length, int
     return ref_length >= 1024 && read_length >= 256 && duos < (long long)sm_count * 512;
 }
 
-int launch_fill_intra(const ChunkGeom &g, const ChunkBuffers &b, int mode, const FastConsts &fc, cudaStream_t stream) {
-    if (g.n < 2) return 0;
-    const int duos = g.n / 2;
-    // (a nearly empty second wave is cheap -- its CTAs have the SMs to themselves -- so 625 duos run faster as 592 + 33
-    // CTAs of 4 warps than as one wave of 2-warp CTAs: measured 4.2 vs 3.2 TCUPS)
-    // warps per duo: as many as there are column passes to pipeline; at least 4 when the passes allow it (8 measured
-    // no better when duos are plentiful), more when the batch has too few duos to fill the device's warp slots
-    const int passes = (g.ref_length + 32 * TW - 1) / (32 * TW);
-    const int want = (148 * 16 + duos - 1) / duos;
+// warps per duo (= per CTA) for a launch of `duos` CTAs: as many as there are column passes to pipeline; at least 4 when the
+// passes allow it (8 measured no better when duos are plentiful), more when the launch has too few duos to fill the device's
+// warp slots (16 warps per SM at this register budget)
+static int intra_warps(int duos, int passes) {
+    const int want = (148 * 16 + duos - 1) / std::max(duos, 1);
     int warps = std::max(4, std::min(want, MAX_WARPS));
     warps = std::min(warps, passes);
     if (warps >= 3 && warps != 4 && warps != 8 && warps != 16) warps = warps > 8 ? 8 : 4;  // 1, 2, 4, 8 or 16 warps per CTA
-    warps = std::max(warps, 1);
+    return std::max(warps, 1);
+}
+
+int launch_fill_intra(const ChunkGeom &g, const ChunkBuffers &b, int mode, const FastConsts &fc, cudaStream_t stream) {
+    if (g.n < 2) return 0;
+    const int duos = g.n / 2;
+    const int passes = (g.ref_length + 32 * TW - 1) / (32 * TW);
     const bool sym = fc.gF == fc.gR;
-    switch (mode) {
-        case MODE_SW_SCORE: launch_intra_inst<MODE_SW_SCORE, 0, false>(g, b, fc, duos, warps, stream); break;
-        case MODE_NW_SCORE: launch_intra_inst<MODE_NW_SCORE, 0, false>(g, b, fc, duos, warps, stream); break;
-        case MODE_SW_ALIGN:
-            if (sym) launch_intra_inst<MODE_SW_ALIGN, 0, true>(g, b, fc, duos, warps, stream);
-            else launch_intra_inst<MODE_SW_ALIGN, 0, false>(g, b, fc, duos, warps, stream);
-            break;
-        default:
-            if (g.policy == 1) {
-                if (sym) launch_intra_inst<MODE_NW_ALIGN, 1, true>(g, b, fc, duos, warps, stream);
-                else launch_intra_inst<MODE_NW_ALIGN, 1, false>(g, b, fc, duos, warps, stream);
-            } else {
-                if (sym) launch_intra_inst<MODE_NW_ALIGN, 0, true>(g, b, fc, duos, warps, stream);
-                else launch_intra_inst<MODE_NW_ALIGN, 0, false>(g, b, fc, duos, warps, stream);
-            }
-            break;
+    auto launch = [&](int first, int count, int warps) {
+        switch (mode) {
+            case MODE_SW_SCORE: launch_intra_inst<MODE_SW_SCORE, 0, false>(g, b, fc, first, count, warps, stream); break;
+            case MODE_NW_SCORE: launch_intra_inst<MODE_NW_SCORE, 0, false>(g, b, fc, first, count, warps, stream); break;
+            case MODE_SW_ALIGN:
+                if (sym) launch_intra_inst<MODE_SW_ALIGN, 0, true>(g, b, fc, first, count, warps, stream);
+                else launch_intra_inst<MODE_SW_ALIGN, 0, false>(g, b, fc, first, count, warps, stream);
+                break;
+            default:
+                if (g.policy == 1) {
+                    if (sym) launch_intra_inst<MODE_NW_ALIGN, 1, true>(g, b, fc, first, count, warps, stream);
+                    else launch_intra_inst<MODE_NW_ALIGN, 1, false>(g, b, fc, first, count, warps, stream);
+                } else {
+                    if (sym) launch_intra_inst<MODE_NW_ALIGN, 0, true>(g, b, fc, first, count, warps, stream);
+                    else launch_intra_inst<MODE_NW_ALIGN, 0, false>(g, b, fc, first, count, warps, stream);
+                }
+                break;
+        }
+    };
+    // Whole waves of 4-warp CTAs first (the device holds 4 per SM); what is left over gets its own launch with as many
+    // warps per duo as fill the device -- as the tail of one launch those CTAs would run 4 warps each on a nearly empty
+    // device for a whole wave's time (C4 at 8 GPUs: 625 duos per rank = 592 + 33).
+    const int wave = 148 * 4;
+    const int full = passes >= 4 && duos > wave ? duos / wave * wave : 0;
+    int launches = 0;
+    if (full) {
+        launch(0, full, 4);
+        ++launches;
     }
-    return 1;
+    if (duos > full) {
+        launch(full, duos - full, intra_warps(duos - full, passes));
+        ++launches;
+    }
+    return launches;
 }
 
 }  // namespace va
