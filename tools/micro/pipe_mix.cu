@@ -39,6 +39,14 @@ __global__ void __launch_bounds__(256) k(int iters, uint32_t seed, uint32_t one,
                 if (KIND == 8) { v[c] = __viaddmax_s16x2(v[c], g, w); f[c] = fadd_imm(f[c]); f[c] = fadd_imm(f[c]); }       // ALU + 2 FADD imm
                 if (KIND == 9) { v[c] = __viaddmax_s16x2(v[c], g, w); u[c] = imad(u[c], one, w); f[c] = fadd_imm(f[c]); f[c] = fadd_imm(f[c]); }  // ALU + IMAD + 2 FADD imm
                 if (KIND == 10) { v[c] = __viaddmax_s16x2(v[c], g, w); u[c] = iadd3(u[c], w); }          // ALU + IADD3
+                if (KIND == 12) { v[c] = __viaddmax_s16x2(v[c], g, w); f[c] = ffma_reg(__uint_as_float(one), 4.0f, f[c]); }   // ALU + FFMA imm
+                if (KIND == 13) { v[c] = __viaddmax_s16x2(v[c], g, w); f[c] = ffma_reg(__uint_as_float(one), 4.0f, f[c]); f[c] = ffma_reg(__uint_as_float(one), 2.0f, f[c]); }   // ALU + 2 FFMA imm
+                if (KIND == 14) { bool ph, pl; v[c] = __vibmax_s16x2(v[c], w, &ph, &pl); if (pl) f[c] = ffma_reg(__uint_as_float(one), 4.0f, f[c]); if (ph) f[c] = ffma_reg(__uint_as_float(one), 2.0f, f[c]); }  // VIMNMX pred + 2 @p FFMA
+                if (KIND == 15) { v[c] = __viaddmax_s16x2(v[c], g, w); f[c] = ffma_reg(f[c], __uint_as_float(one), __uint_as_float(w)); f[c] = ffma_reg(f[c], __uint_as_float(one), __uint_as_float(w));}  // ALU + 2 FFMA reg
+                if (KIND == 16) { f[c] = ffma_reg(f[c], __uint_as_float(one), __uint_as_float(w)); }  // FFMA reg only
+                if (KIND == 17) { v[c] = __viaddmax_s16x2(v[c], g, w); float t; asm volatile("mul.f32 %0,%1,%2;" : "=f"(t) : "f"(f[c]), "f"(__uint_as_float(one))); f[c] = t; }  // ALU + FMUL
+                if (KIND == 18) { v[c] = __viaddmax_s16x2(v[c], g, w); float t; asm volatile("add.f32 %0,%1,%2;" : "=f"(t) : "f"(f[c]), "f"(__uint_as_float(w))); f[c] = t; }  // ALU + FADD reg
+                if (KIND == 19) { bool ph, pl; v[c] = __vibmax_s16x2(v[c], w, &ph, &pl); if (pl) f[c] = ffma_reg(__uint_as_float(one), __uint_as_float(g), f[c]); if (ph) f[c] = ffma_reg(__uint_as_float(one), __uint_as_float(w), f[c]); }  // VIMNMX pred + 2 @p FFMA reg
                 if (KIND == 11) { v[c] = __viaddmax_s16x2(v[c], g, w); u[c] = imad(u[c], 3u, w); }        // ALU + IMAD imm-multiplier
             }
             w += 0x00010001u;
@@ -85,5 +93,13 @@ int main() {
     run<10>("VIADDMNMX + IADD3", 2);
     run<7>("VIADDMNMX + FFMA reg", 2);
     run<6>("VIMNMX.pred + 2 @p FADD imm", 3);
+    run<16>("FFMA reg", 1);
+    run<12>("VIADDMNMX + FFMA imm", 2);
+    run<13>("VIADDMNMX + 2 FFMA imm", 3);
+    run<15>("VIADDMNMX + 2 FFMA reg", 3);
+    run<17>("VIADDMNMX + FMUL reg", 2);
+    run<18>("VIADDMNMX + FADD reg", 2);
+    run<14>("VIMNMX.pred + 2 @p FFMA imm", 3);
+    run<19>("VIMNMX.pred + 2 @p FFMA reg", 3);
     return 0;
 }
