@@ -536,3 +536,31 @@ def test_in_process_multi_device_shard():
         got_runs = [cigar[coff[i]:coff[i + 1]].tolist() for i in idx]
         want_runs = [want[2][want[1][k]:want[1][k + 1]].tolist() for k in range(len(idx))]
         assert got_runs == want_runs
+
+
+def test_device_resident_large_call_into_dirty_blocks(ctx):
+    """A device-resident align call of more than one wave of the packed kernels (whole wave + 20 k pairs), both
+    algorithms and pointer policies, garbage in the output blocks beforehand: the bytes before start[i] must come back
+    zero (the blocks are cleared on the side stream while the fill kernels run, va_cabi.cu) and every byte must match
+    the oracle, with and without the per-phase profiling events."""
+    import torch
+    dev = torch.device("cuda:0")
+    wave = torch.cuda.get_device_properties(0).multi_processor_count * 1024
+    n = wave + 20_000
+    reads, refs = synth.uniform_batch(n, 100, 120, p_sub=0.08, q_indel=0.02, seed=synth.BASE_SEED + 41)
+    dr, df = torch.from_numpy(reads).to(dev), torch.from_numpy(refs).to(dev)
+    L = reads.shape[1] + refs.shape[1]
+    stream = torch.cuda.current_stream().cuda_stream
+    for opt, policy in ((ora.NW, 0), (ora.SW, 0), (ora.NW, 1)):
+        oa, ob, ostart, oend = ora.align(opt, policy, reads, refs)
+        for profiled in (False, True):
+            da = torch.full((n, L), 0x55, dtype=torch.uint8, device=dev)
+            db = torch.full((n, L), 0x55, dtype=torch.uint8, device=dev)
+            dst = torch.zeros(n, dtype=torch.int16, device=dev)
+            de = torch.zeros((n, 2), dtype=torch.int16, device=dev)
+            ctx.set_profiling(profiled)
+            ctx.align_device(opt, policy, dr, df, da, db, dst, de, stream=stream)
+            torch.cuda.synchronize()
+            ctx.set_profiling(False)
+            assert np.array_equal(dst.cpu().numpy(), ostart) and np.array_equal(de.cpu().numpy(), oend), (opt, policy, profiled)
+            assert np.array_equal(da.cpu().numpy(), oa) and np.array_equal(db.cpu().numpy(), ob), (opt, policy, profiled)

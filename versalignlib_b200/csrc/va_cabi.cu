@@ -53,6 +53,17 @@ int set_error(int code, const char *fmt, ...) {
     } while (0)
 
 inline double seconds_since(Clock::time_point t0) { return std::chrono::duration<double>(Clock::now() - t0).count(); }
+
+// VERSALIGN_CUDA_TRACE=1: host-side timeline on stderr.  Call-level marks are ms since the entry point began.
+bool trace_on() {
+    static const bool on = [] { const char *v = getenv("VERSALIGN_CUDA_TRACE"); return v && atoi(v) != 0; }();
+    return on;
+}
+thread_local Clock::time_point g_call_t0;
+inline void call_begin() { if (trace_on()) g_call_t0 = Clock::now(); }
+inline void call_mark(const char *what) {
+    if (trace_on()) fprintf(stderr, "[va trace] call  %8.3f ms  %s\n", seconds_since(g_call_t0) * 1e3, what);
+}
 inline size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
 
 // ---------------------------------------------------------------------------------------
@@ -597,6 +608,12 @@ int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int
     ENQ_TRY(cudaEventRecord(ws.ev_fork, stream));
     ENQ_TRY(cudaStreamWaitEvent(ws.side, ws.ev_fork, 0));
     launches += launch_fill_general(g, b, mode, policy, sc, ws.side);
+    // bytes before start[i] are promised to be zero on the device-resident path: the copy engine clears the blocks
+    // while the fill kernels (bound by the integer pipe) run -- 0.6 GB per million 150 bp pairs
+    if (sh.align && io.zero_prefix && io.aln_read) {
+        ENQ_TRY(cudaMemsetAsync(io.aln_read, 0, (size_t)n * sh.L, ws.side));
+        ENQ_TRY(cudaMemsetAsync(io.aln_ref, 0, (size_t)n * sh.L, ws.side));
+    }
     ENQ_TRY(cudaEventRecord(ws.ev_join, ws.side));
     if (intra)
         // (all four modes run in the Smith-Waterman form there: the SW tables and constants)
@@ -606,10 +623,6 @@ int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int
     ENQ_TRY(cudaStreamWaitEvent(stream, ws.ev_join, 0));
     if (pe) ENQ_TRY(cudaEventRecord(pe[2], stream));
     if (sh.align) {
-        if (io.zero_prefix && io.aln_read) {  // bytes before start[i] are promised to be zero on this path
-            ENQ_TRY(cudaMemsetAsync(io.aln_read, 0, (size_t)n * sh.L, stream));
-            ENQ_TRY(cudaMemsetAsync(io.aln_ref, 0, (size_t)n * sh.L, stream));
-        }
         if (io.compact) ENQ_TRY(cudaMemsetAsync(ws.cursor.p, 0, 8, stream));
         if (io.moves) ENQ_TRY(cudaMemsetAsync((uint32_t *)ws.run_count.p + n, 0, 4, stream));  // the scan's sentinel entry
         launches += launch_traceback(g, b, mode, sc, (uint32_t *)ws.queue.p, stream);
@@ -629,6 +642,7 @@ struct CigarPart {
     int64_t first = 0;
     int count = 0;
     size_t words = 0;
+    bool global_offsets = false;  // cigar_off of these pairs already counts from run 0 of the batch
     std::unique_ptr<uint32_t[]> data;
 };
 
@@ -665,6 +679,7 @@ struct HostCall {
     int32_t *coords = nullptr;                        // [n][4]: read_begin, read_end, ref_begin, ref_end (0-based, half open)
     int64_t *cigar_off = nullptr;                     // [n+1]; while the call runs: chunk-relative offsets, made global at the end
     std::vector<CigarPart> *cigar_parts = nullptr;  // one per chunk, any order
+    int64_t *cigar_running = nullptr;                 // one device: chunks finish in pair order, so the runs before a chunk are known when it lands
     std::mutex *cigar_mu = nullptr;
     std::atomic<int> *cancel = nullptr;  // set by the first shard that fails: the others stop at their next chunk
 };
@@ -802,9 +817,11 @@ int scatter_packed(va_cuda_ctx *ctx, Engine &e, const HostCall &c, ChunkSlot &s,
             st.d2h += (int64_t)(total - s.sent) * 4;
         }
         e.est_per_pair = (double)total / std::max(count, 1);
+        const int64_t before = c.cigar_running ? *c.cigar_running : 0;
+        cp.global_offsets = c.cigar_running != nullptr;
         if (c.cigar_off)
-            ctx->pool->parallel_for(count, 1 << 16, [&](int64_t b, int64_t e2) {
-                for (int64_t i = b; i < e2; ++i) c.cigar_off[first + i + 1] = (int64_t)ro[i + 1];
+            ctx->pool->parallel_for(count, 1 << 14, [&](int64_t b, int64_t e2) {
+                for (int64_t i = b; i < e2; ++i) c.cigar_off[first + i + 1] = before + (int64_t)ro[i + 1];
             });
         cp.words = total;
         if (c.cigar_parts) {
@@ -814,6 +831,7 @@ int scatter_packed(va_cuda_ctx *ctx, Engine &e, const HostCall &c, ChunkSlot &s,
             ctx->pool->parallel_for((int64_t)total, 1 << 18, [&](int64_t b, int64_t e2) { memcpy(dst + b, src + b, (size_t)(e2 - b) * 4); });
         }
     }
+    if (c.cigar_running) *c.cigar_running += (int64_t)cp.words;
     if (c.cigar_parts) {
         std::lock_guard<std::mutex> lk(*c.cigar_mu);
         c.cigar_parts->push_back(std::move(cp));
@@ -910,6 +928,8 @@ int scatter_chunk(va_cuda_ctx *ctx, Engine &e, const HostCall &c, ChunkSlot &s, 
     return c.sh.moves ? scatter_packed(ctx, e, c, s, first, count, st) : scatter_strings(ctx, e, c, s, first, count, st);
 }
 
+bool long_pair_shape(int read_length, int ref_length);
+
 // One device's share [lo, hi) of the batch, chunked through the ring.
 void run_shard(va_cuda_ctx *ctx, Engine &e, const HostCall &c, int64_t lo, int64_t hi, int chunk_pairs, ShardStats &st) {
     // On any failure: remember the message (with the device), tell the sibling shards to stop, and leave nothing
@@ -952,8 +972,8 @@ void run_shard(va_cuda_ctx *ctx, Engine &e, const HostCall &c, int64_t lo, int64
         memcpy(e.est_key, key, sizeof(key));
         e.est_per_pair = 0;  // unknown: the first chunk fetches its worst case
     }
-    // VERSALIGN_CUDA_TRACE=1: host-side timeline of the shard on stderr (ms since the shard started)
-    static const bool trace = [] { const char *v = getenv("VERSALIGN_CUDA_TRACE"); return v && atoi(v) != 0; }();
+    // VERSALIGN_CUDA_TRACE=1: host-side timeline of the shard (ms since the shard started)
+    const bool trace = trace_on();
     const auto t_shard = Clock::now();
     auto mark = [&](const char *what, int64_t first) {
         if (trace) fprintf(stderr, "[va trace] dev %d %8.3f ms  %s %lld\n", e.device, seconds_since(t_shard) * 1e3, what, (long long)first);
@@ -975,13 +995,22 @@ void run_shard(va_cuda_ctx *ctx, Engine &e, const HostCall &c, int64_t lo, int64
         return rc;
     };
 
+    // Ramp: nothing leaves the device before the first chunk has been staged, copied, computed and copied back, and the
+    // host has nothing to hand out until then.  A shard of several chunks therefore starts with a quarter and a half
+    // chunk (legacy C2 call: first results after 2.3 instead of 4.3 ms of a 20 ms call).  Long pairs keep their
+    // wave-sized chunks (a chunk is a handful of pairs there and the copies are nothing).
+    static const bool ramp_allowed = [] { const char *v = getenv("VERSALIGN_CUDA_RAMP"); return !v || atoi(v) != 0; }();
+    const bool ramp = ramp_allowed && hi - lo >= 3 * (int64_t)chunk_pairs && chunk_pairs >= 4096 && !long_pair_shape(RL, FL);
     int k = 0;
-    for (int64_t first = lo; first < hi; first += chunk_pairs, ++k) {
+    int count = 0;
+    for (int64_t first = lo; first < hi; first += count, ++k) {
         if (c.cancel && c.cancel->load()) {  // another device's shard failed
             quiesce();
             return;
         }
-        const int count = (int)std::min<int64_t>(chunk_pairs, hi - first);
+        int64_t want = chunk_pairs;
+        if (ramp && k < 2) want = (int64_t)round_up((size_t)(chunk_pairs >> (2 - k)), 64);
+        count = (int)std::min<int64_t>(want, hi - first);
         ChunkSlot &s = e.ring[k % kRing];
         int rc = drain(s);  // the slot's previous chunk must be out before its pinned buffers are reused
         if (rc) return fail(rc);
@@ -1147,6 +1176,7 @@ int run_host_call(va_cuda_ctx *ctx, HostCall &c) {
                 cut[(size_t)d] = std::lower_bound(csum.begin(), csum.end(), csum.back() * d / nd) - csum.begin();
             for (int d = 1; d <= nd; ++d) cut[(size_t)d] = std::max(cut[(size_t)d], cut[(size_t)d - 1]);
         }
+        call_mark("shards start");
         for (int d = 0; d < nd; ++d) {
             const int64_t lo = cut[(size_t)d], hi = cut[(size_t)d + 1];
             if (hi <= lo) continue;
@@ -1158,6 +1188,7 @@ int run_host_call(va_cuda_ctx *ctx, HostCall &c) {
             }
         }
         for (auto &th : threads) th.join();
+        call_mark("shards done");
         c.cancel = nullptr;
         for (auto &s : stats) {
             if (s.rc != VA_OK) {
@@ -1444,9 +1475,11 @@ int va_cuda_align_packed(va_cuda_ctx *ctx, int opt, int policy, const va_cuda_sc
     if (n > 0 && (!reads || !refs || !read_off || !ref_off)) return set_error(VA_ERR_ARG, "null buffer");
     if (cigar && (!alloc || !cigar_off)) return set_error(VA_ERR_ARG, "cigar output needs alloc and cigar_off");
     if (cigar) *cigar = nullptr;
+    call_begin();
     int rl = 0, fl = 0;
     int rc = packed_lengths(ctx, n, read_off, ref_off, &rl, &fl);
     if (rc) return rc;
+    call_mark("lengths");
     HostCall c;
     bool noop;
     rc = prepare_call(ctx, c, opt, true, policy, sc, n, rl, fl, &noop);
@@ -1462,19 +1495,23 @@ int va_cuda_align_packed(va_cuda_ctx *ctx, int opt, int policy, const va_cuda_sc
     c.cigar_off = cigar_off;
     std::vector<CigarPart> parts;
     std::mutex mu;
+    int64_t running = 0;
     if (cigar || cigar_off) {
         c.cigar_parts = &parts;
         c.cigar_mu = &mu;
+        if (ctx->engines.size() == 1) c.cigar_running = &running;
     }
     if (cigar_off) cigar_off[0] = 0;
     rc = run_host_call(ctx, c);
     if (rc) return rc;
     // every chunk left its pairs' offsets relative to its own first run: line the chunks up in pair order
+    call_mark("run_host_call returned");
     std::sort(parts.begin(), parts.end(), [](const CigarPart &a, const CigarPart &b) { return a.first < b.first; });
     std::vector<int64_t> base(parts.size() + 1, 0);
     for (size_t k = 0; k < parts.size(); ++k) base[k + 1] = base[k] + (int64_t)parts[k].words;
     if (cigar_off) {
         for (size_t k = 1; k < parts.size(); ++k) {  // chunk 0 starts at run 0 already
+            if (parts[k].global_offsets) continue;
             int64_t *o = cigar_off + parts[k].first + 1;
             const int64_t add = base[k];
             ctx->pool->parallel_for(parts[k].count, 1 << 16, [&](int64_t b, int64_t e) {
@@ -1482,17 +1519,24 @@ int va_cuda_align_packed(va_cuda_ctx *ctx, int opt, int policy, const va_cuda_sc
             });
         }
     }
+    call_mark("offsets lined up");
     if (cigar) {
         const int64_t total = base[parts.size()];
         uint32_t *out = (uint32_t *)alloc((size_t)std::max<int64_t>(total, 1) * sizeof(uint32_t), user);
         if (!out) return set_error(VA_ERR_MEMORY, "the caller's allocator returned NULL");
-        for (size_t k = 0; k < parts.size(); ++k) {
-            const uint32_t *src = parts[k].data.get();
-            uint32_t *dst = out + base[k];
-            ctx->pool->parallel_for((int64_t)parts[k].words, 1 << 18, [&](int64_t b, int64_t e) { memcpy(dst + b, src + b, (size_t)(e - b) * 4); });
-        }
+        // one pass over the whole block: piece [b, e) of the output may span several parts
+        ctx->pool->parallel_for(total, 1 << 17, [&](int64_t b, int64_t e) {
+            size_t k = (size_t)(std::upper_bound(base.begin(), base.end(), b) - base.begin()) - 1;
+            while (b < e) {
+                const int64_t stop = std::min<int64_t>(e, base[k + 1]);
+                if (stop > b) memcpy(out + b, parts[k].data.get() + (b - base[k]), (size_t)(stop - b) * 4);
+                b = std::max(b, stop);
+                ++k;
+            }
+        });
         *cigar = out;
     }
+    call_mark("runs copied");
     return VA_OK;
 }
 
