@@ -10,6 +10,9 @@
 // context with one host thread per device and no inter-device exchange.
 #include "versalign_cuda.h"
 
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -693,6 +696,75 @@ struct ShardStats {
     std::string err;
 };
 
+// Sequential writer into the pinned staging block that never reads what it overwrites: the bytes are collected in a small
+// cache-resident buffer and leave as whole 64-byte lines with non-temporal stores.  A plain memcpy of 150-byte pieces
+// makes the core fetch every destination line first (read for ownership); the legacy boundary is bound by the host's
+// memory system, and that fetch was a third of the gather's traffic.
+#if defined(__SSE2__)
+class LineStreamer {
+  public:
+    explicit LineStreamer(char *dst) : dst_(dst) {}
+    void append(const char *src, size_t len) {
+        if (fill_ + len > sizeof(buf_)) flush();
+        if (len > sizeof(buf_)) {  // (not with sequences of <= 32000 bases)
+            memcpy(dst_, src, len);
+            dst_ += len;
+            return;
+        }
+        memcpy(buf_ + fill_, src, len);
+        fill_ += len;
+    }
+    void finish() {
+        flush();
+        memcpy(dst_, buf_, fill_);
+        dst_ += fill_;
+        fill_ = 0;
+        _mm_sfence();  // the copy engine reads these lines next
+    }
+
+  private:
+    void flush() {
+        size_t pos = 0;
+        const size_t head = (size_t)(-(intptr_t)reinterpret_cast<uintptr_t>(dst_)) & 63u;
+        if (head && fill_ >= head) {  // up to the first line boundary of the destination
+            memcpy(dst_, buf_, head);
+            dst_ += head;
+            pos = head;
+        } else if (head) {
+            return;
+        }
+        for (; pos + 64 <= fill_; pos += 64, dst_ += 64) {
+            const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i *>(buf_ + pos));
+            const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i *>(buf_ + pos + 16));
+            const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i *>(buf_ + pos + 32));
+            const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i *>(buf_ + pos + 48));
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst_), a);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst_ + 16), b);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst_ + 32), c);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst_ + 48), d);
+        }
+        memmove(buf_, buf_ + pos, fill_ - pos);
+        fill_ -= pos;
+    }
+    char *dst_;
+    size_t fill_ = 0;
+    alignas(64) char buf_[8192];
+};
+#else
+class LineStreamer {
+  public:
+    explicit LineStreamer(char *dst) : dst_(dst) {}
+    void append(const char *src, size_t len) {
+        memcpy(dst_, src, len);
+        dst_ += len;
+    }
+    void finish() {}
+
+  private:
+    char *dst_;
+};
+#endif
+
 // Inputs of pairs [first, first + count) -> pinned staging.  Returns false when there is nothing to stage
 // (flat inputs in page-locked memory: the H2D copies read the caller's buffers in place).
 void gather_chunk(va_cuda_ctx *ctx, const HostCall &c, ChunkSlot &s, int64_t first, int count) {
@@ -718,15 +790,31 @@ void gather_chunk(va_cuda_ctx *ctx, const HostCall &c, ChunkSlot &s, int64_t fir
         ctx->pool->parallel_for(count, 2048, [&](int64_t b, int64_t e) {
             // the blocks are scattered over the caller's heap: ask for the ones a few pairs ahead now
             constexpr int AHEAD = 8;
+            static const bool stream_stores = [] { const char *v = getenv("VERSALIGN_CUDA_STREAM_STORES"); return !v || atoi(v) != 0; }();
+            if (!stream_stores) {
+                for (int64_t i = b; i < e; ++i) {
+                    if (i + AHEAD < e) {
+                        const char *pr = c.reads_p[first + i + AHEAD], *pf = c.refs_p[first + i + AHEAD];
+                        for (int o = 0; o < RL; o += 64) __builtin_prefetch(pr + o, 0, 0);
+                        for (int o = 0; o < FL; o += 64) __builtin_prefetch(pf + o, 0, 0);
+                    }
+                    memcpy(hr + i * RL, c.reads_p[first + i], RL);
+                    memcpy(hf + i * FL, c.refs_p[first + i], FL);
+                }
+                return;
+            }
+            LineStreamer wr(hr + b * RL), wf(hf + b * FL);
             for (int64_t i = b; i < e; ++i) {
                 if (i + AHEAD < e) {
                     const char *pr = c.reads_p[first + i + AHEAD], *pf = c.refs_p[first + i + AHEAD];
                     for (int o = 0; o < RL; o += 64) __builtin_prefetch(pr + o, 0, 0);
                     for (int o = 0; o < FL; o += 64) __builtin_prefetch(pf + o, 0, 0);
                 }
-                memcpy(hr + i * RL, c.reads_p[first + i], RL);
-                memcpy(hf + i * FL, c.refs_p[first + i], FL);
+                wr.append(c.reads_p[first + i], (size_t)RL);
+                wf.append(c.refs_p[first + i], (size_t)FL);
             }
+            wr.finish();
+            wf.finish();
         });
     }
 }
