@@ -971,13 +971,35 @@ int scatter_strings(va_cuda_ctx *ctx, Engine &e, const HostCall &c, ChunkSlot &s
             }
         });
     } else if (c.alloc) {
+        // Blocks are allocated a few pairs ahead of the copy that fills them, and the lines the strings will go to are
+        // requested for writing at once: the allocator's work on pair i + AHEAD overlaps the memory latency of pair i
+        static const int ahead_env = [] { const char *v = getenv("VERSALIGN_CUDA_ALLOC_AHEAD"); return v ? atoi(v) : 6; }();
         ctx->pool->parallel_for(count, 1024, [&](int64_t b, int64_t e2) {
-            constexpr int AHEAD = 4;
+            constexpr int MAX_AHEAD = 16;
+            const int ahead = std::max(0, std::min(ahead_env, MAX_AHEAD - 1));
+            char *ring_a[MAX_AHEAD], *ring_b[MAX_AHEAD];
+            const size_t bytes = (size_t)(L > 0 ? L : 1);
+            auto obtain = [&](int64_t i) {
+                char *da = c.alloc(bytes, c.alloc_user);
+                char *db = c.alloc(bytes, c.alloc_user);
+                ring_a[i % MAX_AHEAD] = da;
+                ring_b[i % MAX_AHEAD] = db;
+                if (ahead > 0 && da && db) {
+                    const int s0 = std::max(0, (int)stt[i]);
+                    for (int o = s0; o < L; o += 64) {
+                        __builtin_prefetch(da + o, 1, 3);
+                        __builtin_prefetch(db + o, 1, 3);
+                    }
+                    __builtin_prefetch(da + L - 1, 1, 3);
+                    __builtin_prefetch(db + L - 1, 1, 3);
+                    __builtin_prefetch(hc + off[i], 0, 0);
+                }
+            };
+            int64_t next = b;
             for (int64_t i = b; i < e2; ++i) {
-                if (i + AHEAD < e2) __builtin_prefetch(hc + off[i + AHEAD], 0, 0);
+                for (; next < e2 && next <= i + ahead; ++next) obtain(next);
                 const Piece p = piece(i);
-                char *da = c.alloc((size_t)(L > 0 ? L : 1), c.alloc_user);
-                char *db = c.alloc((size_t)(L > 0 ? L : 1), c.alloc_user);
+                char *da = ring_a[i % MAX_AHEAD], *db = ring_b[i % MAX_AHEAD];
                 if (c.records) {
                     va_cuda_alignment_record *rec = reinterpret_cast<va_cuda_alignment_record *>(c.records + (size_t)(first + i) * c.record_stride);
                     rec->read = da;
