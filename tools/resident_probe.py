@@ -34,4 +34,9 @@ with capi.CudaContext(devices=[0]) as ctx:
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
-    print(f"pairs {n} ms/step {ms:.3f} GCUPS {n * 22500 / ms / 1e6:.0f} checksum {int(dst.to(torch.int64).sum())}")
+    ctx.set_profiling(True)
+    ctx.align_device(a.opt, 0, dr, df, da, db, dst, de, stream=stream)
+    ph = ctx.kernel_ms()
+    ctx.set_profiling(False)
+    print(f"pairs {n} ms/step {ms:.3f} GCUPS {n * 22500 / ms / 1e6:.0f} checksum {int(dst.to(torch.int64).sum())} "
+          f"prep/fill/traceback ms {ph[0]:.3f} {ph[1]:.3f} {ph[2]:.3f}")

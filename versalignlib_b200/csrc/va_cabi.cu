@@ -500,6 +500,7 @@ void fill_geom(ChunkGeom &g, const Shape &sh, int n) {
     g.solo = 0;
     g.policy = 0;
     g.intra = 0;
+    g.inband = 0;
     g.affine = 0;
     g.gap_open = 0;
 }
@@ -542,6 +543,7 @@ int enqueue_device_work(Engine &e, ChunkSlot &ws, const Shape &sh, int mode, int
             g.intra = 1;
         } else if (fast_scoring_ok(mode, policy, sc, sh.read_length, sh.ref_length)) {
             g.fast_tw = fast_pick_tw(mode, sh.ref_length, g.policy);
+            g.inband = fast_inband_ok(mode, policy, sc, sh.read_length, sh.ref_length) ? 1 : 0;
         }
     }
     const bool intra = g.intra != 0;

@@ -413,10 +413,12 @@ void launch_tw(const ChunkGeom &g, const ChunkBuffers &b, const FastConsts &fc, 
     }
 }
 
-uint32_t table_word(int code, int match, int mismatch, int offset) {
+// inband: the entry is 4 * s + 2 -- the value scale of the tagged NW align recurrence and its DIAG tag (va_nw.cu)
+uint32_t table_word(int code, int match, int mismatch, int offset, bool inband = false) {
     uint32_t w = 0;
     for (int f = 0; f < 4; ++f) {
-        const int s = (code < 4 ? (code == f ? match : mismatch) : 0) - offset;
+        int s = (code < 4 ? (code == f ? match : mismatch) : 0) - offset;
+        if (inband) s = 4 * s + 2;
         w |= ((uint32_t)s & 0xFFu) << (8 * f);
     }
     return w;
@@ -470,6 +472,21 @@ bool fast_scoring_ok(int mode, int policy, const Scoring &sc, int read_length, i
     return top + mx <= 32000 && mx <= 8000;
 }
 
+// The tagged form of the packed NW align kernel (va_nw.cu) carries 4V + tag in the 16-bit lanes: a quarter of the value
+// range, and table entries 4s' + 2 that still have to fit a signed byte.  Calls outside that run the plane form.
+bool fast_inband_ok(int mode, int policy, const Scoring &sc, int read_length, int ref_length) {
+    if (mode != MODE_NW_ALIGN || !fast_scoring_ok(mode, policy, sc, read_length, ref_length)) return false;
+    static const bool off_by_env = [] { const char *v = getenv("VERSALIGN_CUDA_NO_INBAND"); return v && atoi(v) != 0; }();
+    if (off_by_env) return false;
+    const int off = sc.gap_ref + sc.gap_read;
+    for (int s : {sc.match - off, sc.mismatch - off, -off})
+        if (!fits8(4 * s + 2)) return false;
+    const long long gain = max(max(sc.match, sc.mismatch), 0);
+    const long long min_len = read_length < ref_length ? read_length : ref_length;
+    const long long top = gain * min_len - (long long)sc.gap_ref * (read_length + 2) - (long long)sc.gap_read * (ref_length + 2);
+    return 4 * (top + 64) <= 32000;
+}
+
 int fast_pick_tw(int mode, int ref_length, int policy) {
     if (mode == MODE_SW_ALIGN && policy == 1) return 16;  // three planes: one group of 16 columns
     if (mode == MODE_SW_ALIGN) {
@@ -504,13 +521,15 @@ size_t fast_dirs_bytes_per_row_per_slot(int ref_length) {
     return per_duo / 2;
 }
 
-FastConsts make_fast_consts(int mode, const Scoring &sc) {
+FastConsts make_fast_consts(int mode, const Scoring &sc, bool inband) {
     FastConsts fc{};
     const bool align = mode == MODE_NW_ALIGN || mode == MODE_SW_ALIGN;
     const bool nw = mode == MODE_NW_SCORE || mode == MODE_NW_ALIGN;  // shifted recurrence, va_nw.cu
     const int off = nw ? sc.gap_ref + sc.gap_read : align ? sc.gap_ref : 0;
-    for (int c = 0; c < 8; ++c) fc.tab[c] = table_word(c, sc.match, sc.mismatch, off);
-    if (nw) fc.tab[CODE_PRE] = 0u;  // rows in front of a late-starting lane: s' = 0 hands matrix row 0 down (va_nw.cu)
+    inband = inband && mode == MODE_NW_ALIGN;
+    for (int c = 0; c < 8; ++c) fc.tab[c] = table_word(c, sc.match, sc.mismatch, off, inband);
+    // rows in front of a late-starting lane: s' = 0 hands matrix row 0 down (va_nw.cu); tagged form: 4 * 0 + 2
+    if (nw) fc.tab[CODE_PRE] = inband ? 0x02020202u : 0u;
     fc.gF = sc.gap_ref;
     fc.gR = sc.gap_read;
     fc.gF2 = ((uint32_t)sc.gap_ref & 0xFFFFu) * 0x00010001u;
@@ -532,7 +551,7 @@ FastConsts make_fast_consts(int mode, const Scoring &sc) {
 
 int launch_fill_fast(const ChunkGeom &g, const ChunkBuffers &b, int mode, const Scoring &sc, cudaStream_t stream) {
     if (g.fast_tw == 0 || (g.n < 2 && !g.solo)) return 0;
-    const FastConsts fc = make_fast_consts(mode, sc);
+    const FastConsts fc = make_fast_consts(mode, sc, g.inband != 0);
     switch (mode) {
         case MODE_SW_SCORE: launch_tw<MODE_SW_SCORE>(g, b, fc, stream); break;
         case MODE_NW_SCORE:

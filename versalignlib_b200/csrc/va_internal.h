@@ -58,6 +58,8 @@ struct ChunkGeom {
     int gap_open;      // <= 0
     int intra;         // 1: the chunk's packed duos are computed by the intra-task kernels (va_intra.cu): 16-column strips,
                        // directions at [duo][strip][row], boundary at [duo][row], no end-aligned NW duos
+    int inband;        // 1 (NW align, inter-task packed kernels): values are carried as 4V + tag and the direction words hold
+                       // 2-bit tags instead of two bit planes (va_nw.cu); the boundary column holds 4V
 };
 
 // Constants of the packed (two pairs per thread, s16x2) kernels, built on the host per call.
@@ -131,7 +133,9 @@ int launch_fill_general(const ChunkGeom &g, const ChunkBuffers &b, int mode, int
 bool fast_scoring_ok(int mode, int policy, const Scoring &sc, int read_length, int ref_length, bool intra = false);
 int fast_pick_tw(int mode, int ref_length, int policy = 0);
 size_t fast_dirs_bytes_per_row_per_slot(int ref_length);
-FastConsts make_fast_consts(int mode, const Scoring &sc);
+FastConsts make_fast_consts(int mode, const Scoring &sc, bool inband = false);
+// NW align on the packed inter-task kernels: may the values be carried as 4V + tag (va_nw.cu)?
+bool fast_inband_ok(int mode, int policy, const Scoring &sc, int read_length, int ref_length);
 int launch_fill_fast(const ChunkGeom &g, const ChunkBuffers &b, int mode, const Scoring &sc, cudaStream_t stream);
 // packed kernels of the NW modes, shifted recurrence (va_nw.cu); reached through launch_fill_fast
 int launch_fill_nw(const ChunkGeom &g, const ChunkBuffers &b, int mode, const FastConsts &fc, cudaStream_t stream);

@@ -19,6 +19,17 @@
 // row index CODE_PRE, whose table is all zero -- with s' = 0 a row reproduces the one above it (V(0,.) is
 // non-decreasing), so matrix row 0 is handed down to where that lane really starts, both lanes finish on
 // the last sweep row, and the end-cell rule reads both from the registers.
+// TAGGED form of the align kernel (INBAND, used whenever 4x the value range still fits 16 bits -- every BASELINE
+// config): the lanes carry 4V + tag, the table entries are 4s' + 2, and
+//        t = max(first + 1, second)          first = UP (policy 0) / LEFT (policy 1): wins ties, tag 1; the other: tag 0
+//        h = max(diag + (4s' + 2), t)        DIAG wins ties against both: tag 2
+//        x = h & ~3                          the clean value every later cell reads
+// so the two low bits of h ARE the traceback pointer and no comparison result has to leave an instruction as a
+// predicate: 4 integer-pipe instructions per cell-pair like the plane form, but the four predicated FADDs that bank the
+// planes become two IMADs (tag = h - x, word = word * 4 + tag) -- the plane form is bound by the issue port, this one by
+// the integer pipe alone (tools/micro/cell_mix.cu).  A row's tags fill the same 16 bytes per pair-of-pairs
+// as its two planes did: per group of 16 columns .x = columns 0..7, .y = columns 8..15, column c of a word at bits
+// 2*(7 - c) (lane A) and 16 + 2*(7 - c) (lane B); same word addressing, the traceback decodes by ChunkGeom::inband.
 // The matrix borders un-shift what they hand out: NW score's last row / last column maxima, the
 // `hrow` row and the last-true-column values the traceback kernel reads (va_traceback.cu).
 #include <algorithm>
@@ -68,9 +79,11 @@ __device__ __forceinline__ void cp_async_wait() {
 // DefaultKernel.cpp:338-346: DIAG > UP > LEFT), 1: LEFT >= UP (SSE / AVX, SSEKernel.cpp:646-659: DIAG > LEFT > UP).
 // The packed path only takes pairs whose swept rows and columns are all ACGT (va_fast.cuh, va_prep.cu), so the
 // SSE/AVX rule's "DIAG only between two valid bases" never masks anything here and START cannot occur below row 0.
-template <bool ALIGN, int TW, bool SOLO, int POLICY>
+template <bool ALIGN, int TW, bool SOLO, int POLICY, bool INBAND>
 __global__ void __maxnreg__((Block<ALIGN, TW, SOLO>::MAXREG)) fill_nw_kernel(ChunkGeom g, ChunkBuffers b, FastConsts fc) {
+    static_assert(ALIGN || !INBAND, "the tagged form is an align form");
     constexpr int NG = (TW + 15) / 16;
+    constexpr int VS = INBAND ? 4 : 1;  // value scale of the lanes
     constexpr int NT = Block<ALIGN, TW, SOLO>::NT;
     constexpr int MODE = ALIGN ? MODE_NW_ALIGN : MODE_NW_SCORE;
 
@@ -115,9 +128,9 @@ __global__ void __maxnreg__((Block<ALIGN, TW, SOLO>::MAXREG)) fill_nw_kernel(Chu
                 const uint32_t fa = cref[off + (size_t)slot_a * 16], fb = cref[off + (size_t)slot_b * 16];
                 // nibbles: lane A low byte <- table a[fa], high byte <- its sign; lane B from table b (bytes 4..7)
                 sel[k] = k >= pad ? (fa | ((fa | 8u) << 4) | ((fb | 4u) << 8) | ((fb | 12u) << 12)) : 0xCC88u;
-                H[k] = pk(ngR * (max(c0 + k - pad, c0 - 1) + 1));  // V(0,J) = -gap_read*J: matrix row 0 is 0
+                H[k] = pk(VS * ngR * (max(c0 + k - pad, c0 - 1) + 1));  // V(0,J) = -gap_read*J: matrix row 0 is 0
             }
-            uint32_t diag_next = pk(ngR * c0);  // V(0, c0)
+            uint32_t diag_next = pk(VS * ngR * c0);  // V(0, c0)
             // matrix column 0 in shifted form: H(I,0) = I*gap_ref -> 0 (align); H(I,0) = 0 -> -gap_ref*I (score)
             uint32_t col0 = ALIGN ? 0u : ngF2;
             // score mode, last strip: un-shift of the last column, gap_ref*I + gap_read*n
@@ -150,14 +163,27 @@ __global__ void __maxnreg__((Block<ALIGN, TW, SOLO>::MAXREG)) fill_nw_kernel(Chu
                     uint32_t diag = diag_next;
                     diag_next = left;  // V(I, c0) is the next row's diagonal
                     float p1l[NG], p1h[NG], p2l[NG], p2h[NG];
+                    uint32_t tags[2 * NG];  // tagged form: 8 columns per word
 #pragma unroll
-                    for (int q = 0; q < NG; ++q) p1l[q] = p1h[q] = p2l[q] = p2h[q] = 8388608.0f;
+                    for (int q = 0; q < NG; ++q) {
+                        p1l[q] = p1h[q] = p2l[q] = p2h[q] = 8388608.0f;
+                        tags[2 * q] = tags[2 * q + 1] = 0u;
+                    }
 #pragma unroll
                     for (int k = 0; k < TW; ++k) {
                         const uint32_t sub = prmt(ta, tb, sel[k]);  // s - gap_ref - gap_read
                         const uint32_t up = H[k];
                         uint32_t h;
-                        if (ALIGN) {
+                        if (INBAND) {
+                            const uint32_t t = POLICY == 0 ? __viaddmax_s16x2(up, 0x00010001u, left) : __viaddmax_s16x2(left, 0x00010001u, up);
+                            const uint32_t hh = __viaddmax_s16x2(diag, sub, t);
+                            h = hh & 0xFFFCFFFCu;
+                            // tag = hh - h, word = word * 4 + tag: both on the FMA pipe (as plain C they come back as
+                            // integer-pipe adds and shifts)
+                            uint32_t tag;
+                            asm("mad.lo.u32 %0, %1, -1, %2;" : "=r"(tag) : "r"(h), "r"(hh));
+                            asm("mad.lo.u32 %0, %0, 4, %1;" : "+r"(tags[k >> 3]) : "r"(tag));
+                        } else if (ALIGN) {
                             bool dl, dh, ul, uh;
                             // policy 0: up >= left -> UP before LEFT; policy 1: left >= up -> LEFT before UP
                             const uint32_t t = POLICY == 0 ? __vibmax_s16x2(up, left, &uh, &ul) : __vibmax_s16x2(left, up, &uh, &ul);
@@ -184,7 +210,17 @@ __global__ void __maxnreg__((Block<ALIGN, TW, SOLO>::MAXREG)) fill_nw_kernel(Chu
                         best = __viaddmax_s16x2(left, corr, best);
                         corr = add2(corr, gF2);
                     }
-                    if (ALIGN) {
+                    if (INBAND) {
+                        // a strip's last word may hold fewer than 8 columns: left-align it, so that column c of every
+                        // word sits at bits 2*(7 - c)
+                        constexpr int LASTN = TW - 8 * ((TW - 1) / 8);
+                        if (LASTN < 8) tags[(TW - 1) / 8] <<= 2 * (8 - LASTN);
+#pragma unroll
+                        for (int q = 0; q < NG; ++q) {
+                            w[q].x = tags[2 * q];
+                            w[q].y = tags[2 * q + 1];
+                        }
+                    } else if (ALIGN) {
 #pragma unroll
                         for (int q = 0; q < NG; ++q) {
                             w[q].x = __byte_perm(__float_as_uint(p1l[q]), __float_as_uint(p1h[q]), 0x5410);
@@ -268,7 +304,8 @@ __global__ void __maxnreg__((Block<ALIGN, TW, SOLO>::MAXREG)) fill_nw_kernel(Chu
 #pragma unroll
                 for (int k = 0; k < TW; ++k) {
                     const int col = max(c0 + k - pad, max(c0 - 1, 0));  // 0-based ref column of register k
-                    const uint32_t cand = add2(H[k], pk(fc.gR * (col + 1)));
+                    const uint32_t vk = INBAND ? (H[k] >> 2) & 0x3FFF3FFFu : H[k];  // (values are non-negative)
+                    const uint32_t cand = add2(vk, pk(fc.gR * (col + 1)));
                     const uint32_t low = 0xFFFFu - (uint32_t)col;
                     key_a = max(key_a, (int)((cand << 16) | low));
                     key_b = max(key_b, (int)((cand & 0xFFFF0000u) | low));
@@ -301,18 +338,18 @@ __global__ void __maxnreg__((Block<ALIGN, TW, SOLO>::MAXREG)) fill_nw_kernel(Chu
     if ((threadIdx.x & 31) == 0 && cells) atomicAdd(b.cell_count, cells);
 }
 
-template <bool ALIGN, int TW, int POLICY>
+template <bool ALIGN, int TW, int POLICY, bool INBAND = false>
 void launch_one(const ChunkGeom &g, const ChunkBuffers &b, const FastConsts &fc, cudaStream_t stream) {
     const int duos = (g.n + 1) / 2;
     if (g.n >= 2) {
         const int threads = Block<ALIGN, TW, false>::NT;
-        fill_nw_kernel<ALIGN, TW, false, POLICY><<<(duos + threads - 1) / threads, threads, 0, stream>>>(g, b, fc);
+        fill_nw_kernel<ALIGN, TW, false, POLICY, INBAND><<<(duos + threads - 1) / threads, threads, 0, stream>>>(g, b, fc);
     }
     // leftovers of the bucketing: a fixed grid strides over the list the prep kernel compiled (empty on a
     // uniform batch: the blocks read the count and leave)
     if (g.solo) {
         const int threads = Block<ALIGN, TW, true>::NT;
-        fill_nw_kernel<ALIGN, TW, true, POLICY><<<std::min(2 * ((duos + threads - 1) / threads), 148 * 4), threads, 0, stream>>>(g, b, fc);
+        fill_nw_kernel<ALIGN, TW, true, POLICY, INBAND><<<std::min(2 * ((duos + threads - 1) / threads), 148 * 4), threads, 0, stream>>>(g, b, fc);
     }
 }
 
@@ -321,12 +358,17 @@ void launch_one(const ChunkGeom &g, const ChunkBuffers &b, const FastConsts &fc,
 int launch_fill_nw(const ChunkGeom &g, const ChunkBuffers &b, int mode, const FastConsts &fc, cudaStream_t stream) {
     const bool align = mode == MODE_NW_ALIGN;
     const bool simd = align && g.policy == 1;
+    const bool tagged = align && g.inband != 0;
     if (g.fast_tw == 30) {
-        if (simd) launch_one<true, 30, 1>(g, b, fc, stream);
+        if (tagged && simd) launch_one<true, 30, 1, true>(g, b, fc, stream);
+        else if (tagged) launch_one<true, 30, 0, true>(g, b, fc, stream);
+        else if (simd) launch_one<true, 30, 1>(g, b, fc, stream);
         else if (align) launch_one<true, 30, 0>(g, b, fc, stream);
         else launch_one<false, 30, 0>(g, b, fc, stream);
     } else {
-        if (simd) launch_one<true, 32, 1>(g, b, fc, stream);
+        if (tagged && simd) launch_one<true, 32, 1, true>(g, b, fc, stream);
+        else if (tagged) launch_one<true, 32, 0, true>(g, b, fc, stream);
+        else if (simd) launch_one<true, 32, 1>(g, b, fc, stream);
         else if (align) launch_one<true, 32, 0>(g, b, fc, stream);
         else launch_one<false, 32, 0>(g, b, fc, stream);
     }

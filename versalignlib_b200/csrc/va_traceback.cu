@@ -124,11 +124,12 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
         // one of the min(pad columns, rows) matrix rows above comes down a zero-score diagonal; the
         // arg-max is then past max_ref_pos and gets clipped to it (DefaultKernel.cpp:387).
         const int pad_cols = g.ref_length - cols, reach = min(pad_cols, rows);
+        const int vshift = g.inband ? 2 : 0;  // the tagged fill kernel keeps 4V in the boundary column (va_nw.cu)
         int col_max = (reach == rows && rows > 0) ? 0 : INT_MIN;  // matrix row 0
         if (reach > 0) {
             const uint32_t *bl = b.fboundary + duo;  // last true column (matrix column `cols`), shifted
             for (int r = rows - 2; r >= rows - 1 - reach && r >= 0; --r)
-                col_max = max(col_max, (int)(int16_t)(bl[(size_t)(r + row_off) * g.duos] >> lane_shift) + (r + 1) * gap_ref + cols * sc.gap_read);
+                col_max = max(col_max, ((int)(int16_t)(bl[(size_t)(r + row_off) * g.duos] >> lane_shift) >> vshift) + (r + 1) * gap_ref + cols * sc.gap_read);
         }
         j = (pad_cols > 0 && col_max > best) ? (int)meta.max_ref_pos : min((int)meta.max_ref_pos, idx);
         b.end_cell[2 * pair] = (int16_t)i;
@@ -181,9 +182,21 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
                 const uint32_t pol = (uint32_t)g.policy & 1u;
                 ByteWindow wread(seq_ptr(b.raw_reads, b.read_off, pair, g.read_length), seq_end(b.raw_reads, b.read_off, g.n, g.read_length));
                 ByteWindow wref(seq_ptr(b.raw_refs, b.ref_off, pair, g.ref_length), seq_end(b.raw_refs, b.ref_off, g.n, g.ref_length));
+                // NW, tagged direction words (ChunkGeom::inband, va_nw.cu): .x = columns 0..7 of the group, .y = columns
+                // 8..15; column c of a word at bits 2*(7 - c) of the lane's half: 2 = DIAG, 1 = the move that wins the
+                // UP / LEFT tie under the call's policy, 0 = the other one
+                const bool tagged = NW && g.inband != 0;
                 while (true) {
                     if (sw_simd && !((__ldg(z32 + off) >> bit) & 1u)) break;  // START
-                    const uint32_t dbit = (w.x >> bit) & 1u, ubit = (w.y >> bit) & 1u;
+                    uint32_t dbit, ubit;
+                    if (tagged) {
+                        const uint32_t tag = (((k & 8) ? w.y : w.x) >> (lane_shift + 14 - 2 * (k & 7))) & 3u;
+                        dbit = tag >> 1;
+                        ubit = tag & 1u;
+                    } else {
+                        dbit = (w.x >> bit) & 1u;
+                        ubit = (w.y >> bit) & 1u;
+                    }
                     // second plane: UP >= LEFT (policy 0) or LEFT >= UP (policy 1, SSE/AVX tie order)
                     const int code = dbit ? DIR_DIAG : ((ubit ^ pol) ? DIR_UP : DIR_LEFT);
                     sink(code, n_moves);
