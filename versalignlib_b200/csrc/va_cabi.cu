@@ -431,7 +431,8 @@ int reserve_slot(ChunkSlot &s, const Shape &sh, int cap_pairs, SlotKind kind) {
     if ((rc = s.pair_of.reserve(slots * 4))) return rc;
     if ((rc = s.prep_scratch.reserve(prep_scratch_bytes((int)slots, sh.read_length, sh.ref_length)))) return rc;
     // general region [rows][slots] + packed region [rows][duos] (kept apart: one chunk can hold both kinds)
-    if ((rc = s.boundary.reserve(slots * sh.rows_alloc * 6 + 512))) return rc;
+    // (+16 rows: the tagged NW fill kernel stages the boundary column 16 rows at a time without a row test, va_nw.cu)
+    if ((rc = s.boundary.reserve(slots * ((size_t)sh.rows_alloc + 16) * 6 + 512))) return rc;
     if ((rc = s.scores.reserve(slots * 2))) return rc;
     if ((rc = s.end_cell.reserve(slots * 4))) return rc;
     if (sh.affine && (rc = s.boundary_e.reserve(slots * sh.rows_alloc * 4 + 512))) return rc;
