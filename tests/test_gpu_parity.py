@@ -564,3 +564,50 @@ def test_device_resident_large_call_into_dirty_blocks(ctx):
             ctx.set_profiling(False)
             assert np.array_equal(dst.cpu().numpy(), ostart) and np.array_equal(de.cpu().numpy(), oend), (opt, policy, profiled)
             assert np.array_equal(da.cpu().numpy(), oa) and np.array_equal(db.cpu().numpy(), ob), (opt, policy, profiled)
+
+
+def test_nw_align_plane_form_in_a_fresh_process():
+    """The packed NW align kernel has two forms (va_nw.cu): tagged lanes (4V + tag, the default whenever 4x the value range
+    fits 16 bits) and two bit planes.  The other parity tests run the tagged form; here the plane form takes the same
+    kinds of deck (VERSALIGN_CUDA_NO_INBAND=1, read once per process): uniform, mixed-length (end-aligned duos, padded
+    last strips, solo slots) and dirty, both pointer policies, flat and packed entry points."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import numpy as np
+from oracle import binding as ora
+from versalignlib_b200 import capi, synth
+decks = [synth.uniform_batch(3000, 150, 150, p_sub=0.08, q_indel=0.02, seed=5)]
+r, f, _, _ = synth.mixed_batch(4000, 30, 170, p_sub=0.08, q_indel=0.02, seed=6)
+decks.append((r, f))
+decks.append((synth.sprinkle(13, r, 0.02), synth.sprinkle(14, f, 0.02)))
+with capi.CudaContext(devices=[0]) as ctx:
+    for reads, refs in decks:
+        for pol in (0, 1):
+            a, b, s, e = ctx.align_flat(1, pol, reads, refs)
+            oa, ob, os_, oe = ora.align(1, pol, reads, refs)
+            assert np.array_equal(s, os_) and np.array_equal(e, oe)
+            assert np.array_equal(a, oa) and np.array_equal(b, ob)
+print("plane form ok")
+'''
+    env = dict(os.environ, VERSALIGN_CUDA_NO_INBAND="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "plane form ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_nw_align_scores_outside_the_tagged_range(ctx):
+    """Scorings whose 4x value range or 4s' + 2 table entries leave the tagged form's 16-bit lanes / 8-bit tables run the
+    plane form of the packed kernel in the same process, next to calls that run the tagged form."""
+    reads, refs = synth.uniform_batch(2000, 150, 150, p_sub=0.08, q_indel=0.02, seed=synth.BASE_SEED + 51)
+    long_r, long_f = synth.uniform_batch(64, 800, 800, p_sub=0.08, q_indel=0.02, seed=synth.BASE_SEED + 52)
+    for (r, f), sc in (((reads, refs), (25, -4, -3, -5)),      # 4 * (25 + 8) + 2 does not fit a signed byte
+                       ((reads, refs), (2, -1, -3, -3)),       # tagged
+                       ((long_r, long_f), (6, -2, -3, -3)),    # 4 * (6 * 800 + 6 * 802) leaves 16 bits; V itself fits
+                       ((long_r, long_f), (2, -1, -1, -1))):   # tagged again, longer strips
+        for pol in (0, 1):
+            a, b, start, end = ctx.align_flat(ora.NW, pol, r, f, sc)
+            oa, ob, ostart, oend = ora.align(ora.NW, pol, r, f, sc)
+            assert np.array_equal(start, ostart) and np.array_equal(end, oend), (sc, pol)
+            assert np.array_equal(a, oa) and np.array_equal(b, ob), (sc, pol)
