@@ -186,17 +186,36 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(ChunkGeom g, Chun
                 // 8..15; column c of a word at bits 2*(7 - c) of the lane's half: 2 = DIAG, 1 = the move that wins the
                 // UP / LEFT tie under the call's policy, 0 = the other one
                 const bool tagged = NW && g.inband != 0;
+                if (tagged) {
+                    // Its own loop, written without branches: the 32 walks of a warp leave their groups and strips at
+                    // different steps, so a side path taken by one lane is paid for by all of them on nearly every step.
+                    // DIR_UP = 1, DIR_LEFT = 2, DIR_DIAG = 3: bit 0 of the code is "one row up", bit 1 "one column left".
+                    const uint32_t first = pol ? DIR_LEFT : DIR_UP, second = pol ? DIR_UP : DIR_LEFT;
+                    const uint32_t lut = second | (first << 2) | ((uint32_t)DIR_DIAG << 4);
+                    const int sh0 = lane_shift + 14;
+                    while (true) {
+                        const uint32_t word = (k & 8) ? w.y : w.x;
+                        const uint32_t tag = (word >> (sh0 - 2 * (k & 7))) & 3u;
+                        const uint32_t code = (lut >> (2u * tag)) & 3u;
+                        sink((int)code, n_moves);
+                        ++n_moves;
+                        const uint32_t um = code & 1u, lm = code >> 1;
+                        off -= um ? ((si & 1) ? 1u : up_even) : 0u;
+                        si -= (int)um;
+                        i -= (int)um;
+                        const bool xs = lm && k == kmin;             // leaving the strip
+                        const bool xg = lm && (k & 15) == 0 && !xs;  // leaving the 16-column group
+                        off -= xs ? strip_back + (uint32_t)(k >> 4) * group_step2 : (xg ? group_step2 : 0u);
+                        k = xs ? tw - 1 : k - (int)lm;
+                        kmin = xs ? 0 : kmin;
+                        j -= (int)lm;
+                        if ((i | j) < 0) break;
+                        w = __ldg(base2 + off);
+                    }
+                } else
                 while (true) {
                     if (sw_simd && !((__ldg(z32 + off) >> bit) & 1u)) break;  // START
-                    uint32_t dbit, ubit;
-                    if (tagged) {
-                        const uint32_t tag = (((k & 8) ? w.y : w.x) >> (lane_shift + 14 - 2 * (k & 7))) & 3u;
-                        dbit = tag >> 1;
-                        ubit = tag & 1u;
-                    } else {
-                        dbit = (w.x >> bit) & 1u;
-                        ubit = (w.y >> bit) & 1u;
-                    }
+                    const uint32_t dbit = (w.x >> bit) & 1u, ubit = (w.y >> bit) & 1u;
                     // second plane: UP >= LEFT (policy 0) or LEFT >= UP (policy 1, SSE/AVX tie order)
                     const int code = dbit ? DIR_DIAG : ((ubit ^ pol) ? DIR_UP : DIR_LEFT);
                     sink(code, n_moves);
