@@ -611,3 +611,17 @@ def test_nw_align_scores_outside_the_tagged_range(ctx):
             oa, ob, ostart, oend = ora.align(ora.NW, pol, r, f, sc)
             assert np.array_equal(start, ostart) and np.array_equal(end, oend), (sc, pol)
             assert np.array_equal(a, oa) and np.array_equal(b, ob), (sc, pol)
+
+
+def test_scattered_pointers_with_long_sequences(ctx):
+    """The gather of scattered sequences goes through a line buffer (va_cabi.cu, LineStreamer): sequences longer than the
+    buffer take its direct path, short and long ones in one call order must not swap bytes.  9 k / 4.2 k / 130 base reads
+    through the pointer entry points (what the plug-in calls), scores and alignments against the oracle."""
+    for rl, fl, n in ((9000, 9500, 6), (4200, 300, 40), (130, 8300, 24), (8180, 4090, 20), (4097, 4095, 33)):
+        reads, refs = synth.uniform_batch(n, rl, fl, p_sub=0.1, q_indel=0.02, seed=synth.BASE_SEED + 61 + rl)
+        for opt in (ora.SW, ora.NW):
+            assert np.array_equal(ctx.score_ptrs(opt, reads, refs), ora.score(opt, reads, refs)), (rl, fl, opt)
+        a, b, start, end = ctx.align_ptrs(ora.NW, 0, reads, refs)
+        oa, ob, ostart, oend = ora.align(ora.NW, 0, reads, refs)
+        assert np.array_equal(start, ostart) and np.array_equal(end, oend), (rl, fl)
+        assert used_region_equal(a, b, start, oa, ob, ostart).size == 0, (rl, fl)

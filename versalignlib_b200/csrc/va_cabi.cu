@@ -708,24 +708,28 @@ class LineStreamer {
   public:
     explicit LineStreamer(char *dst) : dst_(dst) {}
     void append(const char *src, size_t len) {
-        if (fill_ + len > sizeof(buf_)) flush();
-        if (len > sizeof(buf_)) {  // (not with sequences of <= 32000 bases)
+        if (len > sizeof(buf_) / 2) {  // long sequences: what is pending goes out first, then a plain copy
+            drain();
             memcpy(dst_, src, len);
             dst_ += len;
             return;
         }
+        if (fill_ + len > sizeof(buf_)) flush();
         memcpy(buf_ + fill_, src, len);
         fill_ += len;
     }
     void finish() {
-        flush();
-        memcpy(dst_, buf_, fill_);
-        dst_ += fill_;
-        fill_ = 0;
+        drain();
         _mm_sfence();  // the copy engine reads these lines next
     }
 
   private:
+    void drain() {  // everything collected so far reaches the destination (whole lines streamed, the rest copied)
+        flush();
+        memcpy(dst_, buf_, fill_);
+        dst_ += fill_;
+        fill_ = 0;
+    }
     void flush() {
         size_t pos = 0;
         const size_t head = (size_t)(-(intptr_t)reinterpret_cast<uintptr_t>(dst_)) & 63u;
@@ -1325,6 +1329,7 @@ int run_host_call(va_cuda_ctx *ctx, HostCall &c) {
 
 int prepare_call(va_cuda_ctx *ctx, HostCall &c, int opt, bool align, int policy, const va_cuda_scoring *sc, int n,
                  int read_length, int ref_length, bool *noop) {
+    call_begin();  // (trace marks count from here)
     *noop = false;
     if (!ctx) return set_error(VA_ERR_ARG, "context is null");
     if (n < 0) return set_error(VA_ERR_ARG, "n < 0");
@@ -1588,11 +1593,9 @@ int va_cuda_align_packed(va_cuda_ctx *ctx, int opt, int policy, const va_cuda_sc
     if (n > 0 && (!reads || !refs || !read_off || !ref_off)) return set_error(VA_ERR_ARG, "null buffer");
     if (cigar && (!alloc || !cigar_off)) return set_error(VA_ERR_ARG, "cigar output needs alloc and cigar_off");
     if (cigar) *cigar = nullptr;
-    call_begin();
     int rl = 0, fl = 0;
     int rc = packed_lengths(ctx, n, read_off, ref_off, &rl, &fl);
     if (rc) return rc;
-    call_mark("lengths");
     HostCall c;
     bool noop;
     rc = prepare_call(ctx, c, opt, true, policy, sc, n, rl, fl, &noop);
