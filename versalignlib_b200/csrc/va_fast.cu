@@ -111,6 +111,13 @@ __global__ void __maxnreg__((FastBlock<MODE, TW, SYM, SOLO, POLICY>::MAXREG)) fi
             const int c0 = s * TW;
             const bool first = s == 0, last = s == nstrips - 1;
             uint32_t sel[TW], H[TW];
+            // (score mode only: the align kernels' row loops sit at a register-allocation cliff, their prologue stays as it is)
+            constexpr bool LEAN = !SWA;
+            if (LEAN && c0 + TW <= n) {  // full strip, the common case: va_fast.cuh
+                fast_strip_selectors<TW>(g, b.code_refs, slot_a, c0, sel);
+#pragma unroll
+                for (int k = 0; k < TW; ++k) H[k] = 0u;  // matrix row 0
+            } else
 #pragma unroll
             for (int k = 0; k < TW; ++k) {
                 // Columns past n (partial last strip) get a selector that yields s <= 0 for both lanes (the sign
@@ -153,7 +160,8 @@ __global__ void __maxnreg__((FastBlock<MODE, TW, SYM, SOLO, POLICY>::MAXREG)) fi
                         const uint32_t *src = bnd + (size_t)(c * 16) * g.duos + duo;
 #pragma unroll
                         for (int r = 0; r < 16; ++r)
-                            if (c * 16 + r < m) cp_async4(&s_bnd[buf][r][threadIdx.x], src + (size_t)r * g.duos);
+                            // (score mode: no row test -- the boundary block is allocated 16 rows past the last one)
+                            if (LEAN || c * 16 + r < m) cp_async4(&s_bnd[buf][r][threadIdx.x], src + (size_t)r * g.duos);
                     }
                     cp_async_commit();
                 };

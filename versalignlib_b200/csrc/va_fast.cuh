@@ -127,6 +127,47 @@ __device__ __forceinline__ void store_half(uint4 *p, int half, uint2 v, const Fa
     }
 }
 
+// PRMT selectors of a FULL strip of the packed inter-task kernels (columns c0 .. c0 + TW - 1, all inside the ref):
+// sel[k] pairs, in its low 16 bits, lane A's "table byte f, then its sign" with lane B's (bytes 4..7 of the PRMT
+// sources).  The TW ref codes of each lane come in as three 16-byte chunks, are shifted to byte 0 as words (the strip
+// starts at an arbitrary column of its first chunk), turned into selector bytes four columns at a time, and one PRMT per
+// column pairs the two lanes' bytes -- 0.5 k instructions per strip where byte loads with their 64-bit addresses took
+// 1.8 k, and the integer pipe is what bounds the score kernels and the tagged align kernel.
+template <int TW>
+__device__ __forceinline__ void fast_strip_selectors(const ChunkGeom &g, const uint4 *__restrict__ code_refs, int slot_a, int c0,
+                                                     uint32_t (&sel)[TW]) {
+    static_assert(TW <= 32, "three 16-byte chunks hold a strip that starts anywhere in the first");
+    const int a = c0 & 15, q0 = c0 >> 4;
+    uint32_t wa[12], wb[12];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        const int q = min(q0 + t, g.ref_chunks - 1);
+        const uint4 *pc = code_refs + (size_t)q * g.slots + slot_a;
+        const uint4 va = pc[0], vb = pc[1];
+        wa[4 * t] = va.x, wa[4 * t + 1] = va.y, wa[4 * t + 2] = va.z, wa[4 * t + 3] = va.w;
+        wb[4 * t] = vb.x, wb[4 * t + 1] = vb.y, wb[4 * t + 2] = vb.z, wb[4 * t + 3] = vb.w;
+    }
+    if (a & 8) {
+#pragma unroll
+        for (int i = 0; i < 10; ++i) wa[i] = wa[i + 2], wb[i] = wb[i + 2];
+    }
+    if (a & 4) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) wa[i] = wa[i + 1], wb[i] = wb[i + 1];
+    }
+    const int bsh = (a & 3) * 8;
+    constexpr int NW4 = (TW + 3) / 4;
+#pragma unroll
+    for (int i = 0; i < NW4; ++i) {
+        const uint32_t ca = __funnelshift_r(wa[i], wa[i + 1], bsh), cb = __funnelshift_r(wb[i], wb[i + 1], bsh);
+        // per byte: lane A  f | (f | 8) << 4,  lane B  (f | 4) | (f | 12) << 4   (f <= 5: nothing crosses a byte)
+        wa[i] = ca | ((ca | 0x08080808u) << 4);
+        wb[i] = (cb | 0x04040404u) | ((cb | 0x0C0C0C0Cu) << 4);
+    }
+#pragma unroll
+    for (int k = 0; k < TW; ++k) sel[k] = prmt(wa[k >> 2], wb[k >> 2], (uint32_t)((k & 3) | ((4 + (k & 3)) << 4)));
+}
+
 __device__ __forceinline__ int fast_groups(int tw) { return (tw + 15) >> 4; }
 
 // Intra-task kernels (va_intra.cu): a lane's strip is 16 columns; direction words are uint2 (DIAG plane, second

@@ -121,43 +121,14 @@ __global__ void __maxnreg__((Block<ALIGN, TW, SOLO>::MAXREG)) fill_nw_kernel(Chu
             const int kv = min(TW, n - c0);  // valid columns of this strip
             const int pad = TW - kv;
             uint32_t sel[TW], H[TW];
-            if (INBAND && pad == 0) {
-                // Full strip (the common case), tagged form -- whose integer pipe is the bound, so the prologue counts:
-                // the 30-32 ref codes of each lane come in as three 16-byte chunks, are shifted to byte 0 as words
-                // (the strip starts at an arbitrary column of its first chunk), turned into selector bytes four columns
-                // at a time, and one PRMT per column pairs the two lanes' bytes (only the selector's low 16 bits count).
-                const int a = c0 & 15, q0 = c0 >> 4;
-                uint32_t wa[12], wb[12];
-#pragma unroll
-                for (int t = 0; t < 3; ++t) {
-                    const int q = min(q0 + t, g.ref_chunks - 1);
-                    const uint4 *pc = b.code_refs + (size_t)q * g.slots + slot_a;
-                    const uint4 va = pc[0], vb = pc[1];
-                    wa[4 * t] = va.x, wa[4 * t + 1] = va.y, wa[4 * t + 2] = va.z, wa[4 * t + 3] = va.w;
-                    wb[4 * t] = vb.x, wb[4 * t + 1] = vb.y, wb[4 * t + 2] = vb.z, wb[4 * t + 3] = vb.w;
-                }
-                if (a & 8) {
-#pragma unroll
-                    for (int i = 0; i < 10; ++i) wa[i] = wa[i + 2], wb[i] = wb[i + 2];
-                }
-                if (a & 4) {
-#pragma unroll
-                    for (int i = 0; i < 9; ++i) wa[i] = wa[i + 1], wb[i] = wb[i + 1];
-                }
-                const int bsh = (a & 3) * 8;
-                constexpr int NW4 = (TW + 3) / 4;
-#pragma unroll
-                for (int i = 0; i < NW4; ++i) {
-                    const uint32_t ca = __funnelshift_r(wa[i], wa[i + 1], bsh), cb = __funnelshift_r(wb[i], wb[i + 1], bsh);
-                    // per byte: lane A  f | (f | 8) << 4,  lane B  (f | 4) | (f | 12) << 4   (f <= 5: nothing crosses a byte)
-                    wa[i] = ca | ((ca | 0x08080808u) << 4);
-                    wb[i] = (cb | 0x04040404u) | ((cb | 0x0C0C0C0Cu) << 4);
-                }
+            // (the plane form of align keeps the byte-wise prologue: its row loop sits at a register-allocation cliff)
+            constexpr bool LEAN = INBAND || !ALIGN;
+            if (LEAN && pad == 0) {  // full strip, the common case
+                fast_strip_selectors<TW>(g, b.code_refs, slot_a, c0, sel);
                 const uint32_t hstep = pk(VS * ngR);
                 uint32_t hv = pk(VS * ngR * c0);
 #pragma unroll
                 for (int k = 0; k < TW; ++k) {
-                    sel[k] = prmt(wa[k >> 2], wb[k >> 2], (uint32_t)((k & 3) | ((4 + (k & 3)) << 4)));
                     hv += hstep;  // V(0,J) = -gap_read*J, both lanes (no carry between them: the range check)
                     H[k] = hv;
                 }
@@ -192,9 +163,9 @@ __global__ void __maxnreg__((Block<ALIGN, TW, SOLO>::MAXREG)) fill_nw_kernel(Chu
                         const uint32_t *src = bnd + (size_t)(c * 16) * g.duos + duo;
 #pragma unroll
                         for (int r = 0; r < 16; ++r)
-                            // (tagged form: no row test -- the boundary block is allocated 16 rows past the last one, the
-                            // rows staged in excess are never read back)
-                            if (INBAND || c * 16 + r < m) cp_async4(&s_bnd[buf][r][threadIdx.x], src + (size_t)r * g.duos);
+                            // (no row test -- the boundary block is allocated 16 rows past the last one, the rows staged in
+                            // excess are never read back)
+                            if (LEAN || c * 16 + r < m) cp_async4(&s_bnd[buf][r][threadIdx.x], src + (size_t)r * g.duos);
                     }
                     cp_async_commit();
                 };
