@@ -121,8 +121,9 @@ __global__ void __maxnreg__((Block<ALIGN, TW, SOLO>::MAXREG)) fill_nw_kernel(Chu
             const int kv = min(TW, n - c0);  // valid columns of this strip
             const int pad = TW - kv;
             uint32_t sel[TW], H[TW];
-            // (the plane form of align keeps the byte-wise prologue: its row loop sits at a register-allocation cliff)
-            constexpr bool LEAN = INBAND || !ALIGN;
+            // (the plane form of align keeps the byte-wise prologue: its row loop sits at a register-allocation cliff; the
+            // score form measured 1 % slower with the lean one -- 96-thread blocks under another register cap)
+            constexpr bool LEAN = INBAND;
             if (LEAN && pad == 0) {  // full strip, the common case
                 fast_strip_selectors<TW>(g, b.code_refs, slot_a, c0, sel);
                 const uint32_t hstep = pk(VS * ngR);
