@@ -31,7 +31,7 @@ NVCC_FLAGS = [
 ]
 
 CUDA_SOURCES = ["va_prep.cu", "va_kernels.cu", "va_fast.cu", "va_nw.cu", "va_intra.cu", "va_traceback.cu", "va_cabi.cu", "va_fasta.cpp", "cuda_kernel_plugin.cpp"]
-CUDA_HEADERS = ["va_device.cuh", "va_fast.cuh", "va_internal.h"]
+CUDA_HEADERS = ["va_device.cuh", "va_fast.cuh", "va_internal.h", "va_line_streamer.h"]
 
 
 def _newer(target: str, deps: list[str]) -> bool:
