@@ -117,19 +117,20 @@ __global__ void __maxnreg__((FastBlock<MODE, TW, SYM, SOLO, POLICY>::MAXREG)) fi
                 fast_strip_selectors<TW>(g, b.code_refs, slot_a, c0, sel);
 #pragma unroll
                 for (int k = 0; k < TW; ++k) H[k] = 0u;  // matrix row 0
-            } else
+            } else {  // partial strip (and the kernels that keep the byte-wise prologue)
 #pragma unroll
-            for (int k = 0; k < TW; ++k) {
-                // Columns past n (partial last strip) get a selector that yields s <= 0 for both lanes (the sign
-                // byte of a table entry): with both gap scores <= 0 such a cell never exceeds the real cells
-                // above / left of it, so the running maximum and the best-cell search need no per-column guards.
-                const int col = min(c0 + k, n - 1);
-                const size_t off = ((size_t)(col >> 4) * g.slots) * 16 + (col & 15);
-                const uint32_t fa = cref[off + (size_t)slot_a * 16], fb = cref[off + (size_t)slot_b * 16];
-                // nibbles: lane A low byte <- table a[fa], high byte <- its sign; lane B from table b (bytes 4..7)
-                sel[k] = c0 + k < n ? (fa | ((fa | 8u) << 4) | ((fb | 4u) << 8) | ((fb | 12u) << 12)) : 0xCC88u;
-                // matrix row 0 is 0 (SW align keeps H + gF, biased, see below)
-                H[k] = SWA ? fc.swa_g0 : 0u;
+                for (int k = 0; k < TW; ++k) {
+                    // Columns past n (partial last strip) get a selector that yields s <= 0 for both lanes (the sign
+                    // byte of a table entry): with both gap scores <= 0 such a cell never exceeds the real cells
+                    // above / left of it, so the running maximum and the best-cell search need no per-column guards.
+                    const int col = min(c0 + k, n - 1);
+                    const size_t off = ((size_t)(col >> 4) * g.slots) * 16 + (col & 15);
+                    const uint32_t fa = cref[off + (size_t)slot_a * 16], fb = cref[off + (size_t)slot_b * 16];
+                    // nibbles: lane A low byte <- table a[fa], high byte <- its sign; lane B from table b (bytes 4..7)
+                    sel[k] = c0 + k < n ? (fa | ((fa | 8u) << 4) | ((fb | 4u) << 8) | ((fb | 12u) << 12)) : 0xCC88u;
+                    // matrix row 0 is 0 (SW align keeps H + gF, biased, see below)
+                    H[k] = SWA ? fc.swa_g0 : 0u;
+                }
             }
             // H[i][c0] feeding the first column's diagonal: 0 for matrix row 0
             uint32_t diag_next = SWA ? fc.swa_g0 : 0u;

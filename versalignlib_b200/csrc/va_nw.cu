@@ -133,15 +133,16 @@ __global__ void __maxnreg__((Block<ALIGN, TW, SOLO>::MAXREG)) fill_nw_kernel(Chu
                     hv += hstep;  // V(0,J) = -gap_read*J, both lanes (no carry between them: the range check)
                     H[k] = hv;
                 }
-            } else
+            } else {  // partial strip (and the kernels that keep the byte-wise prologue)
 #pragma unroll
-            for (int k = 0; k < TW; ++k) {
-                const int col = max(c0 + k - pad, c0);
-                const size_t off = ((size_t)(col >> 4) * g.slots) * 16 + (col & 15);
-                const uint32_t fa = cref[off + (size_t)slot_a * 16], fb = cref[off + (size_t)slot_b * 16];
-                // nibbles: lane A low byte <- table a[fa], high byte <- its sign; lane B from table b (bytes 4..7)
-                sel[k] = k >= pad ? (fa | ((fa | 8u) << 4) | ((fb | 4u) << 8) | ((fb | 12u) << 12)) : 0xCC88u;
-                H[k] = pk(VS * ngR * (max(c0 + k - pad, c0 - 1) + 1));  // V(0,J) = -gap_read*J: matrix row 0 is 0
+                for (int k = 0; k < TW; ++k) {
+                    const int col = max(c0 + k - pad, c0);
+                    const size_t off = ((size_t)(col >> 4) * g.slots) * 16 + (col & 15);
+                    const uint32_t fa = cref[off + (size_t)slot_a * 16], fb = cref[off + (size_t)slot_b * 16];
+                    // nibbles: lane A low byte <- table a[fa], high byte <- its sign; lane B from table b (bytes 4..7)
+                    sel[k] = k >= pad ? (fa | ((fa | 8u) << 4) | ((fb | 4u) << 8) | ((fb | 12u) << 12)) : 0xCC88u;
+                    H[k] = pk(VS * ngR * (max(c0 + k - pad, c0 - 1) + 1));  // V(0,J) = -gap_read*J: matrix row 0 is 0
+                }
             }
             uint32_t diag_next = pk(VS * ngR * c0);  // V(0, c0)
             // matrix column 0 in shifted form: H(I,0) = I*gap_ref -> 0 (align); H(I,0) = 0 -> -gap_ref*I (score)
